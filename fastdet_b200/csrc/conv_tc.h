@@ -1,0 +1,70 @@
+// conv_tc.h — host-side interface of the tcgen05 implicit-GEMM convolution.
+//
+// Replaces the Conv(+BatchNormalization)(+LeakyRelu)(+Add) node groups that the reference hands
+// to ONNX Runtime in `self.model.run` (reference server/detector.py:135).  Activations are bf16
+// NHWC ("pixel rows" of `pitch` channels), weights are bf16 [Cout][kh][kw][Cin] (K-major), the
+// accumulator is fp32 in TMEM.
+#pragma once
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace fd {
+
+struct ConvDesc {
+    // input feature map: NHWC view, `in` already points at the first channel of the slice
+    int n, hi, wi, cin;
+    int in_pitch;  // channels between consecutive pixels (>= cin; > cin when reading a concat slice)
+    const __nv_bfloat16* in;
+    // filter
+    int cout, ksize, stride;
+    int pad_lo, pad_hi;  // begin / end padding (same for h and w)
+    const __nv_bfloat16* w;  // [cout][ksize*ksize*cin], tap-major then channel
+    const float* bias;       // [>= round_up(cout, 256)] fp32 (BatchNorm folded in)
+    int act;                 // 0 = linear, 1 = LeakyReLU(alpha)
+    float alpha;
+    // optional residual (added after the activation, like ONNX Add after LeakyRelu)
+    const __nv_bfloat16* residual;
+    int res_pitch;
+    // output: bf16 NHWC slice (pitch >= cout) or fp32 rows (heads; pitch = padded cout)
+    void* out;
+    int out_pitch;
+    int out_fp32;
+    int upsample2x;  // write every output pixel to its 2x2 nearest-neighbour block of a (2Ho,2Wo) map
+    int ho, wo;      // filled by conv_tc_prepare
+};
+
+struct ConvParams {
+    int M, cout, num_k_blocks, cin_blocks, ksize, stride, pad_lo, ho, wo;
+    int block_k;  // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    int a_im2col; // 0: A via 2D tiled map (1x1 s1), 1: via im2col map
+    int num_m_tiles, num_n_tiles;
+    const float* bias;
+    int act;
+    float alpha;
+    const __nv_bfloat16* residual;
+    long long res_pitch;
+    void* out;
+    long long out_pitch;
+    int out_fp32, upsample2x;
+    int n_store_limit;
+};
+
+struct ConvLaunch {
+    CUtensorMap tmA, tmB;
+    ConvParams p;
+    int block_n;
+    int grid;
+    size_t smem_bytes;
+    double flops;  // algorithmic: 2*M*cout*K
+};
+
+// Builds tensor maps + launch geometry.  block_n_hint: 0 = choose, else one of 32/64/128/256.
+// Returns 0 on success; on failure writes a message to err (if non-null).
+int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* out, char* err, size_t errlen);
+int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);
+// One-time per device: opt in to the large dynamic shared memory the kernels need.
+int conv_tc_init(char* err, size_t errlen);
+
+}  // namespace fd

@@ -1,0 +1,245 @@
+// test_conv.cu — developer harness for conv_tc (not part of the shipped library).
+// Checks the tcgen05 implicit-GEMM conv against a double-precision CPU loop on small shapes, then
+// times the hot YOLOv3 layer shapes at batch 64.   Usage: test_conv [check|time|all]
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../conv_tc.h"
+
+using namespace fd;
+
+#define CK(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            exit(2);                                                                       \
+        }                                                                                  \
+    } while (0)
+
+static uint32_t rng_state = 12345;
+static float frand() {
+    rng_state = rng_state * 1664525u + 1013904223u;
+    return ((rng_state >> 8) & 0xFFFF) / 65536.0f - 0.5f;
+}
+static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
+
+struct Case {
+    const char* name;
+    int n, h, w, cin, cout, k, stride, pad_lo, pad_hi, act, residual, fp32, upsample, in_pitch_extra, block_n;
+};
+
+static int run_case(const Case& c, int num_sms) {
+    const int in_pitch = c.cin + c.in_pitch_extra;
+    const int ho = (c.h + c.pad_lo + c.pad_hi - c.k) / c.stride + 1;
+    const int wo = (c.w + c.pad_lo + c.pad_hi - c.k) / c.stride + 1;
+    const long long M = 1LL * c.n * ho * wo;
+    const int K = c.k * c.k * c.cin;
+    const int out_pitch = c.fp32 ? ((c.cout + 15) / 16) * 16 : c.cout + 8;  // exercise pitch != cout
+    const int oh = c.upsample ? 2 * ho : ho, ow = c.upsample ? 2 * wo : wo;
+
+    std::vector<float> x(1LL * c.n * c.h * c.w * in_pitch), wt(1LL * c.cout * K), bias(1024, 0.f),
+        res(c.residual ? M * c.cout : 0);
+    for (auto& v : x) v = bf16r(frand() * 2.f);
+    for (auto& v : wt) v = bf16r(frand() * 0.25f);
+    for (int i = 0; i < c.cout; ++i) bias[i] = frand();
+    for (auto& v : res) v = bf16r(frand());
+
+    std::vector<__nv_bfloat16> xb(x.size()), wb(wt.size()), rb(res.size());
+    for (size_t i = 0; i < x.size(); ++i) xb[i] = __float2bfloat16(x[i]);
+    for (size_t i = 0; i < wt.size(); ++i) wb[i] = __float2bfloat16(wt[i]);
+    for (size_t i = 0; i < res.size(); ++i) rb[i] = __float2bfloat16(res[i]);
+
+    __nv_bfloat16 *dx, *dw, *dr = nullptr;
+    float* dbias;
+    void* dout;
+    const size_t out_elems = 1ULL * c.n * oh * ow * out_pitch;
+    const size_t out_bytes = out_elems * (c.fp32 ? 4 : 2);
+    CK(cudaMalloc(&dx, xb.size() * 2));
+    CK(cudaMalloc(&dw, wb.size() * 2));
+    CK(cudaMalloc(&dbias, bias.size() * 4));
+    CK(cudaMalloc(&dout, out_bytes));
+    CK(cudaMemset(dout, 0xFF, out_bytes));
+    if (c.residual) {
+        CK(cudaMalloc(&dr, rb.size() * 2));
+        CK(cudaMemcpy(dr, rb.data(), rb.size() * 2, cudaMemcpyHostToDevice));
+    }
+    CK(cudaMemcpy(dx, xb.data(), xb.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw, wb.data(), wb.size() * 2, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dbias, bias.data(), bias.size() * 4, cudaMemcpyHostToDevice));
+
+    ConvDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n = c.n; d.hi = c.h; d.wi = c.w; d.cin = c.cin; d.in_pitch = in_pitch; d.in = dx;
+    d.cout = c.cout; d.ksize = c.k; d.stride = c.stride; d.pad_lo = c.pad_lo; d.pad_hi = c.pad_hi;
+    d.w = dw; d.bias = dbias; d.act = c.act; d.alpha = 0.1f;
+    d.residual = dr; d.res_pitch = c.cout;
+    d.out = dout; d.out_pitch = out_pitch; d.out_fp32 = c.fp32; d.upsample2x = c.upsample;
+    ConvLaunch L;
+    char err[256] = {0};
+    if (conv_tc_prepare(d, num_sms, c.block_n, &L, err, sizeof(err))) {
+        printf("[%s] prepare failed: %s\n", c.name, err);
+        return 1;
+    }
+    if (conv_tc_launch(L, 0)) {
+        printf("[%s] launch failed: %s\n", c.name, cudaGetErrorString(cudaGetLastError()));
+        return 1;
+    }
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) {
+        printf("[%s] kernel failed: %s\n", c.name, cudaGetErrorString(e));
+        exit(3);
+    }
+    std::vector<uint8_t> hout(out_bytes);
+    CK(cudaMemcpy(hout.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
+
+    // CPU reference
+    double max_err = 0, max_ref = 0;
+    long long bad = 0, first_bad_m = -1;
+    int first_bad_n = -1;
+    for (long long m = 0; m < M; ++m) {
+        const int img = (int)(m / (ho * wo));
+        const int rem = (int)(m % (ho * wo));
+        const int oy = rem / wo, ox = rem % wo;
+        for (int co = 0; co < c.cout; ++co) {
+            double acc = 0;
+            for (int r = 0; r < c.k; ++r)
+                for (int s = 0; s < c.k; ++s) {
+                    const int iy = oy * c.stride - c.pad_lo + r, ix = ox * c.stride - c.pad_lo + s;
+                    if (iy < 0 || iy >= c.h || ix < 0 || ix >= c.w) continue;
+                    const float* xp = &x[((1LL * img * c.h + iy) * c.w + ix) * in_pitch];
+                    const float* wp = &wt[1LL * co * K + (r * c.k + s) * c.cin];
+                    for (int ci = 0; ci < c.cin; ++ci) acc += double(xp[ci]) * wp[ci];
+                }
+            double v = acc + bias[co];
+            if (c.act) v = v > 0 ? v : v * 0.1f;
+            if (c.residual) v += res[m * c.cout + co];
+            const int ndst = c.upsample ? 4 : 1;
+            for (int dd = 0; dd < ndst; ++dd) {
+                long long row = m;
+                if (c.upsample) row = (1LL * img * oh + 2 * oy + (dd >> 1)) * ow + 2 * ox + (dd & 1);
+                float got;
+                if (c.fp32) got = reinterpret_cast<float*>(hout.data())[row * out_pitch + co];
+                else got = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(hout.data())[row * out_pitch + co]);
+                const double er = fabs(double(got) - v);
+                const double tol = c.fp32 ? 1e-3 + 1e-4 * fabs(v) : 2e-2 + 1e-2 * fabs(v);
+                if (!(er <= tol)) {
+                    if (bad == 0) { first_bad_m = m; first_bad_n = co; }
+                    ++bad;
+                }
+                if (er > max_err || er != er) max_err = er;
+                if (fabs(v) > max_ref) max_ref = fabs(v);
+            }
+        }
+    }
+    // untouched padding channels of a bf16 slice must still hold the 0xFF fill
+    long long clobbered = 0;
+    if (!c.fp32) {
+        const uint16_t* o = reinterpret_cast<const uint16_t*>(hout.data());
+        for (long long row = 0; row < 1LL * c.n * oh * ow; ++row)
+            for (int ch = c.cout; ch < out_pitch; ++ch)
+                if (o[row * out_pitch + ch] != 0xFFFF) ++clobbered;
+    }
+    printf("[%-28s] M=%lld N=%d K=%d bn=%d grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
+           c.name, M, c.cout, K, L.block_n, L.grid, max_err, max_ref, bad, clobbered,
+           (bad == 0 && clobbered == 0) ? "OK" : "FAIL");
+    if (bad) printf("    first bad at m=%lld n=%d\n", first_bad_m, first_bad_n);
+    cudaFree(dx); cudaFree(dw); cudaFree(dbias); cudaFree(dout);
+    if (dr) cudaFree(dr);
+    return (bad == 0 && clobbered == 0) ? 0 : 1;
+}
+
+static void time_case(const char* name, int n, int h, int cin, int cout, int k, int stride, int num_sms,
+                      int block_n) {
+    const int pad = k == 3 ? 1 : 0;
+    ConvDesc d;
+    memset(&d, 0, sizeof(d));
+    const int ho = (h + 2 * pad - k) / stride + 1;
+    const size_t in_e = 1ULL * n * h * h * cin, out_e = 1ULL * n * ho * ho * cout, w_e = 1ULL * cout * k * k * cin;
+    __nv_bfloat16 *dx, *dw, *dout;
+    float* dbias;
+    CK(cudaMalloc(&dx, in_e * 2));
+    CK(cudaMalloc(&dw, w_e * 2));
+    CK(cudaMalloc(&dout, out_e * 2));
+    CK(cudaMalloc(&dbias, 1024 * 4));
+    CK(cudaMemset(dx, 0x3C, in_e * 2));  // bf16 0x3C3C ~ 0.0115
+    CK(cudaMemset(dw, 0x3C, w_e * 2));
+    CK(cudaMemset(dbias, 0, 1024 * 4));
+    d.n = n; d.hi = h; d.wi = h; d.cin = cin; d.in_pitch = cin; d.in = dx;
+    d.cout = cout; d.ksize = k; d.stride = stride; d.pad_lo = pad; d.pad_hi = pad;
+    d.w = dw; d.bias = dbias; d.act = 1; d.alpha = 0.1f;
+    d.out = dout; d.out_pitch = cout;
+    ConvLaunch L;
+    char err[256] = {0};
+    if (conv_tc_prepare(d, num_sms, block_n, &L, err, sizeof(err))) { printf("[%s] prepare failed: %s\n", name, err); return; }
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0); cudaEventCreate(&e1);
+    for (int i = 0; i < 3; ++i) conv_tc_launch(L, 0);
+    CK(cudaDeviceSynchronize());
+    const int iters = 20;
+    cudaEventRecord(e0);
+    for (int i = 0; i < iters; ++i) conv_tc_launch(L, 0);
+    cudaEventRecord(e1);
+    CK(cudaDeviceSynchronize());
+    float ms;
+    cudaEventElapsedTime(&ms, e0, e1);
+    ms /= iters;
+    const double bytes = (in_e + out_e + w_e) * 2.0;
+    printf("[time %-24s] bn=%3d tiles=%6d  %.3f ms  %.1f TFLOP/s  %.0f GB/s(min traffic)\n", name, L.block_n,
+           L.p.num_m_tiles * L.p.num_n_tiles, ms, L.flops / ms * 1e-9, bytes / ms * 1e-6);
+    cudaFree(dx); cudaFree(dw); cudaFree(dout); cudaFree(dbias);
+}
+
+int main(int argc, char** argv) {
+    const char* mode = argc > 1 ? argv[1] : "all";
+    cudaDeviceProp prop;
+    CK(cudaGetDeviceProperties(&prop, 0));
+    printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
+    char err[256] = {0};
+    if (conv_tc_init(err, sizeof(err))) { printf("init failed: %s\n", err); return 2; }
+    const int sms = prop.multiProcessorCount;
+    int fails = 0;
+    if (!strcmp(mode, "check") || !strcmp(mode, "all")) {
+        const Case cases[] = {
+            // name                     n  h   w  cin cout k s pl ph act res fp32 up extra bn
+            {"1x1 64->128",             2, 13, 13, 64, 128, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0},
+            {"1x1 64->128 pitch+64",    2, 13, 13, 64, 128, 1, 1, 0, 0, 1, 0, 0, 0, 64, 0},
+            {"1x1 128->64 res",         1, 26, 26, 128, 64, 1, 1, 0, 0, 1, 1, 0, 0, 0, 0},
+            {"1x1 256->255 head fp32",  2, 13, 13, 256, 255, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0},
+            {"1x1 128->42 head fp32",   1, 26, 26, 128, 42, 1, 1, 0, 0, 0, 0, 1, 0, 0, 0},
+            {"1x1 256->128 upsample",   2, 13, 13, 256, 128, 1, 1, 0, 0, 1, 0, 0, 1, 0, 0},
+            {"1x1 32->64 (bk32)",       1, 20, 20, 32, 64, 1, 1, 0, 0, 1, 0, 0, 0, 0, 0},
+            {"3x3 64->64 s1",           2, 13, 13, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"3x3 64->128 s1 res",      3, 13, 13, 64, 128, 3, 1, 1, 1, 1, 1, 0, 0, 0, 0},
+            {"3x3 64->128 s2",          2, 26, 26, 64, 128, 3, 2, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"3x3 64->128 s2 pad(1,0)", 2, 26, 26, 64, 128, 3, 2, 1, 0, 1, 0, 0, 0, 0, 0},
+            {"3x3 32->64 s1 (bk32)",    2, 16, 16, 32, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"3x3 32->64 s2 (bk32)",    1, 32, 32, 32, 64, 3, 2, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"3x3 128->512 s1 bn256",   2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 256},
+            {"3x3 128->512 s1 bn128",   2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 128},
+            {"3x3 64->32 pitch+32",     1, 19, 19, 64, 32, 3, 1, 1, 1, 1, 0, 0, 0, 32, 0},
+            {"1x1 512->256 many tiles", 8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 0, 0, 0, 0, 64},
+            {"3x3 tiny map 64->64",     1, 5, 5, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+        };
+        for (const Case& c : cases) fails += run_case(c, sms);
+        printf("check: %d failing case(s)\n", fails);
+    }
+    if (!strcmp(mode, "time") || !strcmp(mode, "all")) {
+        time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0);
+        time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, 0);
+        time_case("3x3 256->512 @26 bn128", 64, 26, 256, 512, 3, 1, sms, 128);
+        time_case("3x3 512->1024 @13 bs64", 64, 13, 512, 1024, 3, 1, sms, 0);
+        time_case("3x3 512->1024 @13 bn128", 64, 13, 512, 1024, 3, 1, sms, 128);
+        time_case("1x1 256->128 @52 bs64", 64, 52, 256, 128, 1, 1, sms, 0);
+        time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0);
+        time_case("1x1 1024->512 @13 bs64", 64, 13, 1024, 512, 1, 1, sms, 0);
+        time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0);
+        time_case("3x3 32->64 s2 @416 bs64", 64, 416, 32, 64, 3, 2, sms, 0);
+        time_case("3x3 512->1024 @13 bs1", 1, 13, 512, 1024, 3, 1, sms, 0);
+    }
+    return fails ? 1 : 0;
+}
