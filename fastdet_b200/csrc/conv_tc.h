@@ -37,7 +37,7 @@ struct ConvDesc {
 
 struct ConvParams {
     int M, cout, num_k_blocks, cin_blocks, ksize, stride, pad_lo, ho, wo;
-    int block_k;  // 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)
+    int block_k;  // 64 (SWIZZLE_128B), 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B)
     int a_im2col; // 0: A via 2D tiled map (1x1 s1), 1: via im2col map
     int num_m_tiles, num_n_tiles;
     const float* bias;

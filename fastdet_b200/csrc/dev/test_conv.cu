@@ -224,6 +224,8 @@ int main(int argc, char** argv) {
             {"3x3 64->32 pitch+32",     1, 19, 19, 64, 32, 3, 1, 1, 1, 1, 0, 0, 0, 32, 0},
             {"1x1 512->256 many tiles", 8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 0, 0, 0, 0, 64},
             {"3x3 tiny map 64->64",     1, 5, 5, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"3x3 16->32 s1 (bk16)",    2, 20, 20, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"1x1 48->64 (bk16)",       1, 20, 20, 48, 64, 1, 1, 0, 0, 1, 0, 0, 0, 16, 0},
         };
         for (const Case& c : cases) fails += run_case(c, sms);
         printf("check: %d failing case(s)\n", fails);

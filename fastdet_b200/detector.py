@@ -1,0 +1,157 @@
+#!/usr/bin/env python
+"""detector.py — drop-in for the reference's ``server/detector.py`` with the model executed by
+libfastdet_b200.so (hand-written sm_100a kernels) instead of ONNX Runtime.
+
+Same surface as the reference module (server/detector.py): ``Detector`` (:64-76), ``DummyDetector``
+(:78-92), ``ONNXDetector(path, mode=None, num_classes=80, dbgout=None)`` (:94-146) with
+``perform(data, threshold=0.1) -> [(klass, conf, x, y, w, h), ...]`` in network-input pixels, klass 1-based,
+Soft-NMS order; same exception types (``ValueError('invalid image size')`` :132, PIL's
+``UnidentifiedImageError`` for undecodable bytes, ``KeyError`` when the graph has neither 2 nor 3 outputs
+:136); the same CLI (:169-195).  ``server/server.py`` imports ``DummyDetector, ONNXDetector`` from a module
+named ``detector`` (:17) and needs nothing else.
+
+Additive extras (not in the reference): ``image_size=`` and ``device=`` keyword arguments,
+``perform_batch`` / ``perform_frames`` for decoded RGB frames, ``forward_raw`` for parity tests.
+``mode`` is accepted and stored like the reference does; every mode runs on the B200 — there is no
+CPU execution provider here and no fallback.
+"""
+import io
+import logging
+import sys
+import time
+
+import numpy as np
+
+from . import _native
+
+
+class Detector:
+
+    def __init__(self, image_size=(416, 416), num_classes=80, dbgout=None):
+        self.image_size = image_size
+        self.num_classes = num_classes
+        self.dbgout = dbgout
+        return
+
+    def perform(self, data, threshold=0.1):
+        if self.dbgout is not None:
+            with open(self.dbgout, 'wb') as fp:
+                fp.write(data)
+        return
+
+
+class DummyDetector(Detector):
+    """Fixed answer regardless of input — lets the transport be exercised without a model."""
+
+    def __repr__(self):
+        return '<DummyDetector>'
+
+    def perform(self, data, threshold=0.1):
+        super().perform(data)
+        (width, height) = self.image_size
+        return [(16, 1.0, 0.5 * width, 0.5 * height, 0.4 * width, 0.4 * height)]
+
+
+class ONNXDetector(Detector):
+
+    ANCHORS = {
+        3: (((116, 90), (156, 198), (373, 326)),
+            ((30, 61), (62, 45), (59, 119)),
+            ((10, 13), (16, 30), (33, 23))),
+        2: (((81, 82), (135, 169), (344, 319)),
+            ((10, 14), (23, 27), (37, 58))),
+    }
+
+    def __init__(self, path, mode=None, num_classes=80, dbgout=None, image_size=(416, 416), device=0,
+                 max_det=2048):
+        super().__init__(image_size=tuple(image_size), num_classes=num_classes, dbgout=dbgout)
+        self.mode = mode
+        self.path = path
+        self.max_det = max_det
+        if isinstance(path, (bytes, bytearray)):
+            data = bytes(path)
+            self.path = '<bytes>'
+        else:
+            with open(path, 'rb') as fp:
+                data = fp.read()
+        self.model = _native.Model(data, num_classes, self.image_size, device=device)
+        self.logger = logging.getLogger()
+        self.logger.info(f'load: path={self.path}, providers=[\'fastdet_b200:sm_100a\'], '
+                         f'layers={self.model.info.n_layers}, heads={self.model.head_shapes}')
+        return
+
+    def __repr__(self):
+        return (f'<ONNXDetector mode={self.mode}, path={self.path}, num_classes={self.num_classes}>')
+
+    # -- the reference entry point -------------------------------------------------------------
+    def perform(self, data, threshold=0.1):
+        super().perform(data)
+        from PIL import Image
+        (width, height) = self.image_size
+        img = Image.open(io.BytesIO(data))
+        if img.size != self.image_size:
+            raise ValueError('invalid image size')
+        frame = np.array(img)
+        if frame.ndim != 3 or frame.shape[2] != 3:
+            # the reference's reshape(1,height,width,3) raises ValueError for non-RGB modes (:133)
+            raise ValueError(f'cannot reshape array of size {frame.size} into shape (1,{height},{width},3)')
+        results = self.perform_frames(frame.reshape(1, height, width, 3), threshold=threshold)[0]
+        self.logger.info(f'perform: results={results}')
+        return results
+
+    # -- extras --------------------------------------------------------------------------------
+    def perform_frames(self, frames, threshold=0.1, allow_resize=False):
+        """frames: [n, h, w, 3] u8 decoded RGB.  Returns one reference-style result list per frame."""
+        self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
+        dets, counts = self.model.detect(np.asarray(frames), threshold, allow_resize=allow_resize,
+                                         max_det=self.max_det)
+        out = []
+        for f in range(dets.shape[0]):
+            d = dets[f, :counts[f]]
+            out.append([(int(k), float(c), float(x), float(y), float(w), float(h))
+                        for k, c, x, y, w, h in zip(d['klass'], d['conf'], d['x'], d['y'], d['w'], d['h'])])
+        return out
+
+    perform_batch = perform_frames
+
+    def forward_raw(self, frames):
+        """Raw head tensors (what ``model.run`` returns in the reference): list of f32 [n, C, H, W]."""
+        frames = np.ascontiguousarray(frames, np.uint8)
+        n, h, w, _ = frames.shape
+        if (w, h) != self.image_size:
+            raise ValueError('invalid image size')
+        self.model.preprocess(frames, n, (w, h))
+        self.model.forward(n)
+        return self.model.heads(n)
+
+
+USAGE = 'usage: {prog} [-m mode] [-c num_classes] [-t threshold] onnx images ...'
+
+
+def main(argv):
+    """Command line of the reference (server/detector.py:169-195): one line ``<seconds> <results>`` per image."""
+    import getopt
+    settings = {'-m': None, '-c': '80', '-t': '0.1'}
+    try:
+        flags, rest = getopt.getopt(argv[1:], 'm:c:t:')
+    except getopt.GetoptError:
+        rest = []
+    else:
+        settings.update(flags)
+    if not rest:
+        print(USAGE.format(prog=argv[0]))
+        return 100
+    onnx_path, images = rest[0], rest[1:]
+    det = ONNXDetector(onnx_path, mode=settings['-m'], num_classes=int(settings['-c']))
+    thr = float(settings['-t'])
+    for image in images:
+        with open(image, 'rb') as fp:
+            payload = fp.read()
+        started = time.time()
+        found = det.perform(payload, threshold=thr)
+        print(time.time() - started, found)
+    return None
+
+
+if __name__ == '__main__':
+    sys.exit(main(sys.argv))

@@ -276,7 +276,8 @@ class ExportOptions:
     packed_attrs: bool = True
     batch: object = "N"  # declared batch dim: symbolic or an int (Unity export pins 1)
     bn_eps: float = 1e-5
-    obj_bias: float = -4.5
+    obj_bias: float = -4.5  # objectness channels' bias: keeps candidates at thr 0.1 down to tens per frame
+    head_gain: float = 2.0  # head weights ~ N(0, (head_gain/sqrt(fan_in))^2): logits of O(1) spread
     opset: int = 11
 
 
@@ -315,7 +316,7 @@ def build_onnx(arch: str, num_classes: int, size: int = 416, seed: int = 0,
             fan_in = c * l.size * l.size
             is_head = not l.bn
             if is_head:
-                w = rng.normal(0.0, 0.5 / np.sqrt(fan_in), size=(l.filters, c, l.size, l.size)).astype(np.float32)
+                w = rng.normal(0.0, opts.head_gain / np.sqrt(fan_in), size=(l.filters, c, l.size, l.size)).astype(np.float32)
                 b = np.zeros(l.filters, np.float32)
                 b[4::5 + num_classes] = opts.obj_bias
             else:

@@ -1,0 +1,121 @@
+/* fastdet_b200.h — C ABI of libfastdet_b200.so: the B200-native replacement for the work
+ * `ONNXDetector` hands to ONNX Runtime plus its Python pre/post-processing.
+ *
+ * Reference interface each entry point replaces (paths relative to the reference repo):
+ *   fd_model_create      ort.InferenceSession(path, providers)          server/detector.py:108-121
+ *   fd_preprocess        PIL frame -> /255 -> f32 -> NCHW               server/detector.py:131-134
+ *   fd_forward           self.model.run(None, {'input': a})             server/detector.py:135
+ *   fd_postprocess       process_yolo + soft_nms + pixel scaling        server/detector.py:136-144, 45-59, 148-166
+ *   fd_detect            ONNXDetector.perform after image decode        server/detector.py:126-146
+ *   fd_heads_fp32 ...    parity hooks (the raw tensors model.run returns, the f32 NCHW input tensor)
+ *
+ * Conventions: plain C types only; every function returns 0 on success or a negative FD_ERR_* code, with a
+ * human-readable reason available from fd_last_error() (thread-local).  `stream` is a cudaStream_t passed as
+ * void*; NULL selects the model's own stream.  Calls with a stream are asynchronous on it unless stated.
+ * A model belongs to one CUDA device; calls on one model must not overlap in time (the reference's caller
+ * is single-threaded, server/server.py:156-163).  There is no CPU fallback: without a CUDA device every
+ * compute entry point fails with FD_ERR_CUDA.
+ */
+#ifndef FASTDET_B200_H_
+#define FASTDET_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FD_OK 0
+#define FD_ERR_ARG (-1)      /* bad argument */
+#define FD_ERR_MODEL (-2)    /* ONNX file malformed or outside the supported operator subset */
+#define FD_ERR_HEADS (-3)    /* graph has a number of outputs other than 2 or 3 (reference: KeyError at detector.py:136) */
+#define FD_ERR_CUDA (-4)     /* CUDA runtime / driver failure, or no device */
+#define FD_ERR_SIZE (-5)     /* frame size not accepted (reference: ValueError('invalid image size'), detector.py:132) */
+
+#define FD_MAX_HEADS 4
+#define FD_ABI_VERSION 1
+
+typedef struct fd_model fd_model;
+
+/* One detection, in network-input pixels, (x, y) = top-left corner: the tuple perform() returns
+ * (server/detector.py:142-144).  `box` is the insertion-order index of the anchor box (head, row, column,
+ * anchor) and has no counterpart in the reference; it makes results traceable to head-tensor cells. */
+typedef struct fd_det {
+    int32_t klass; /* 1-based class id (detector.py:165 `mi+1`) */
+    int32_t box;
+    double conf, x, y, w, h;
+} fd_det;
+
+typedef struct fd_info {
+    int32_t abi_version;
+    int32_t device;
+    int32_t net_w, net_h, num_classes;
+    int32_t n_heads;
+    int32_t head_h[FD_MAX_HEADS], head_w[FD_MAX_HEADS], head_c[FD_MAX_HEADS];
+    float anchors[FD_MAX_HEADS][3][2]; /* (w, h) in network-input pixels, chosen by n_heads as detector.py:96-106,136 */
+    int32_t boxes_per_frame;
+    int32_t n_layers;             /* fused layers = kernel launches per forward pass */
+    int32_t n_conv;               /* convolutions among them */
+    int32_t launches_per_detect;  /* n_layers + postprocess kernels */
+    double conv_flops_per_frame;  /* algorithmic: sum 2*Cout*Cin*k*k*Ho*Wo */
+    uint64_t num_params;
+    uint64_t weight_bytes;        /* packed device weights */
+} fd_info;
+
+typedef struct fd_layer_desc {
+    int32_t kind; /* 0 first conv (u8 in), 1 conv (tcgen05), 2 maxpool, 3 copy/upsample */
+    int32_t c, h, w;                /* output tensor, per frame */
+    int32_t cin, ksize, stride, act, has_residual, upsample2x, out_fp32, block_n;
+    double flops;                   /* per frame */
+    char name[96];                  /* ONNX node name */
+    char out_name[96];              /* ONNX tensor name the output corresponds to */
+} fd_layer_desc;
+
+const char* fd_last_error(void);
+int fd_abi_version(void);
+/* Number of CUDA devices visible; 0 when there is no driver/GPU (never fails). */
+int fd_device_count(void);
+
+/* Parse + plan + upload.  net_w/net_h: network input size (the reference hard-wires 416x416, detector.py:66). */
+int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net_w, int net_h, int device,
+                    fd_model** out);
+void fd_model_destroy(fd_model* m);
+int fd_model_info(const fd_model* m, fd_info* out);
+int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out);
+
+/* Stage `n` RGB u8 HWC frames for the next fd_forward.  src_w x src_h must equal the network size unless
+ * allow_resize != 0, in which case the frames are letterboxed on the device (extension).  on_device: frames
+ * is a device pointer on the model's device; otherwise host memory (pinned memory makes the copy async). */
+int fd_preprocess(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
+                  void* stream);
+/* Run the conv stack on the staged frames (captured CUDA graph per batch size). */
+int fd_forward(fd_model* m, int n, void* stream);
+/* Decode + Soft-NMS on the head tensors of the last fd_forward.  Results land in device/pinned buffers owned by
+ * the model; fd_fetch copies them out.  threshold is the reference's `threshold` (a Python float). */
+int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stream);
+/* Synchronise `stream` and copy the results of the last fd_postprocess: counts[n] and out[n][max_det]
+ * (max_det as given to fd_postprocess).  total[n] (optional) receives the untruncated kept count. */
+int fd_fetch(fd_model* m, int n, fd_det* out, int32_t* counts, int32_t* total, void* stream);
+/* preprocess -> forward -> postprocess -> fetch; synchronous; frames in host (or device) memory. */
+int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
+              double threshold, int max_det, fd_det* out, int32_t* counts);
+
+/* ---- parity / profiling hooks (synchronous; host pointers) ---- */
+/* Raw head tensor `head` of the last forward as f32 NCHW [n, C, H, W] — what model.run returns. */
+int fd_heads_fp32(fd_model* m, int head, float* dst_nchw, int n);
+/* Overwrite head tensor `head` with f32 NCHW data (to test postprocess on exact inputs). */
+int fd_set_heads_fp32(fd_model* m, int head, const float* src_nchw, int n);
+/* Output of fused layer `layer` of the last forward as f32 NCHW. */
+int fd_layer_output_fp32(fd_model* m, int layer, float* dst_nchw, int n);
+/* The f32 NCHW tensor the reference feeds to model.run, computed on the device from net-sized u8 frames. */
+int fd_normalise_f32(fd_model* m, const uint8_t* frames, int n, float* dst_nchw);
+/* Device letterbox of host frames [n, src_h, src_w, 3] to [n, net_h, net_w, 3]. */
+int fd_letterbox_u8(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, uint8_t* dst);
+/* Per-layer device time (ms, mean over reps) of the forward pass at batch n, each layer timed alone. */
+int fd_time_layers(fd_model* m, int n, int reps, float* ms_per_layer);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTDET_B200_H_ */
