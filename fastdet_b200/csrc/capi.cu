@@ -459,7 +459,8 @@ int fd_set_heads_fp32(fd_model* m, int head, const float* src, int n) {
     const size_t elems = size_t(n) * t.c * t.h * t.w;
     if (int rc = ensure_scratch(e, elems * 4)) return rc;
     CU(cudaDeviceSynchronize());
-    CU(cudaMemcpy(e->scratch, src, elems * 4, cudaMemcpyHostToDevice));
+    // same stream as the layout kernel: a plain cudaMemcpy from pageable memory may return before its DMA lands
+    CU(cudaMemcpyAsync(e->scratch, src, elems * 4, cudaMemcpyHostToDevice, m->stream));
     if (launch_nchw_to_rows_f32(e->scratch, static_cast<float*>(loc_ptr(*e, t, true)), t.pitch, n, t.h, t.w, t.c, m->stream))
         return fail(FD_ERR_CUDA, "layout kernel launch failed");
     CU(cudaStreamSynchronize(m->stream));
@@ -487,10 +488,10 @@ int fd_normalise_f32(fd_model* m, const uint8_t* frames, int n, float* dst) {
     CU(cudaMalloc(&d_in, px * 3));
     if (cudaMalloc(&d_out, px * 3 * 4) != cudaSuccess) { cudaFree(d_in); return fail(FD_ERR_CUDA, "cudaMalloc failed"); }
     int rc = FD_OK;
-    if (cudaMemcpy(d_in, frames, px * 3, cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMemcpyAsync(d_in, frames, px * 3, cudaMemcpyHostToDevice, m->stream) != cudaSuccess ||
         launch_normalise_f32_nchw(d_in, d_out, n, m->plan.net_h, m->plan.net_w, m->stream) ||
-        cudaStreamSynchronize(m->stream) != cudaSuccess ||
-        cudaMemcpy(dst, d_out, px * 3 * 4, cudaMemcpyDeviceToHost) != cudaSuccess)
+        cudaMemcpyAsync(dst, d_out, px * 3 * 4, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess ||
+        cudaStreamSynchronize(m->stream) != cudaSuccess)
         rc = fail(FD_ERR_CUDA, "fd_normalise_f32 failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(d_in); cudaFree(d_out);
     return rc;
@@ -505,9 +506,10 @@ int fd_letterbox_u8(fd_model* m, const uint8_t* frames, int n, int src_w, int sr
     CU(cudaMalloc(&d_in, in_b));
     if (cudaMalloc(&d_out, out_b) != cudaSuccess) { cudaFree(d_in); return fail(FD_ERR_CUDA, "cudaMalloc failed"); }
     int rc = FD_OK;
-    if (cudaMemcpy(d_in, frames, in_b, cudaMemcpyHostToDevice) != cudaSuccess ||
+    if (cudaMemcpyAsync(d_in, frames, in_b, cudaMemcpyHostToDevice, m->stream) != cudaSuccess ||
         launch_letterbox_u8(d_in, d_out, n, src_h, src_w, m->plan.net_h, m->plan.net_w, 128, m->stream) ||
-        cudaStreamSynchronize(m->stream) != cudaSuccess || cudaMemcpy(dst, d_out, out_b, cudaMemcpyDeviceToHost) != cudaSuccess)
+        cudaMemcpyAsync(dst, d_out, out_b, cudaMemcpyDeviceToHost, m->stream) != cudaSuccess ||
+        cudaStreamSynchronize(m->stream) != cudaSuccess)
         rc = fail(FD_ERR_CUDA, "fd_letterbox_u8 failed: %s", cudaGetErrorString(cudaGetLastError()));
     cudaFree(d_in); cudaFree(d_out);
     return rc;

@@ -88,18 +88,57 @@ struct Builder {
     }
 
     // ---- constant folding of the integer/float shape arithmetic exporters wrap around Resize / Pad ----
-    static std::vector<double> as_doubles(const OnnxTensor& t) {
+    // Small N-d tensors (row-major); values are carried as doubles and stored back as f32 or i64.
+    struct CT {
+        std::vector<int64_t> dims;
         std::vector<double> v;
-        if (t.is_float()) v.assign(t.f.begin(), t.f.end());
-        else v.assign(t.i.begin(), t.i.end());
-        return v;
+        bool fl = false;
+    };
+    static CT to_ct(const OnnxTensor& t) {
+        CT c;
+        c.dims = t.dims;
+        c.fl = t.is_float();
+        if (c.fl) c.v.assign(t.f.begin(), t.f.end());
+        else c.v.assign(t.i.begin(), t.i.end());
+        return c;
     }
-    static OnnxTensor from_doubles(const std::vector<double>& v, bool is_float, std::vector<int64_t> dims) {
+    static OnnxTensor from_ct(const CT& c) {
         OnnxTensor t;
-        t.dims = std::move(dims);
-        if (is_float) { t.dtype = 1; t.f.assign(v.begin(), v.end()); }
-        else { t.dtype = 7; t.i.resize(v.size()); for (size_t k = 0; k < v.size(); ++k) t.i[k] = static_cast<int64_t>(v[k]); }
+        t.dims = c.dims;
+        if (c.fl) { t.dtype = 1; t.f.assign(c.v.begin(), c.v.end()); }
+        else { t.dtype = 7; t.i.resize(c.v.size()); for (size_t k = 0; k < c.v.size(); ++k) t.i[k] = static_cast<int64_t>(c.v[k]); }
         return t;
+    }
+    static std::vector<int64_t> strides_of(const std::vector<int64_t>& dims) {
+        std::vector<int64_t> st(dims.size(), 1);
+        for (int k = static_cast<int>(dims.size()) - 2; k >= 0; --k) st[k] = st[k + 1] * dims[k + 1];
+        return st;
+    }
+    static int64_t numel_of(const std::vector<int64_t>& dims) {
+        int64_t n = 1;
+        for (int64_t d : dims) n *= d;
+        return n;
+    }
+    // out[idx] = in[map(idx)] where map gives, per output axis, (input axis, start, step)
+    static CT gather_nd(const CT& in, const std::vector<int64_t>& out_dims, const std::vector<int>& in_axis,
+                        const std::vector<int64_t>& start, const std::vector<int64_t>& step) {
+        CT out;
+        out.dims = out_dims;
+        out.fl = in.fl;
+        const int64_t n = numel_of(out_dims);
+        out.v.resize(static_cast<size_t>(n));
+        const std::vector<int64_t> ist = strides_of(in.dims);
+        std::vector<int64_t> idx(out_dims.size(), 0);
+        for (int64_t k = 0; k < n; ++k) {
+            int64_t off = 0;
+            for (size_t a = 0; a < out_dims.size(); ++a) off += (start[a] + idx[a] * step[a]) * ist[in_axis[a]];
+            out.v[static_cast<size_t>(k)] = in.v[static_cast<size_t>(off)];
+            for (int a = static_cast<int>(out_dims.size()) - 1; a >= 0; --a) {
+                if (++idx[a] < out_dims[a]) break;
+                idx[a] = 0;
+            }
+        }
+        return out;
     }
     bool try_fold(const OnnxNode& n) {
         const std::string& op = n.op;
@@ -114,82 +153,177 @@ struct Builder {
             consts[n.outputs[0]] = t;
             return true;
         }
-        std::vector<const OnnxTensor*> in;
+        std::vector<CT> in;
+        std::vector<bool> have;
         for (const auto& nm : n.inputs) {
-            if (nm.empty()) { in.push_back(nullptr); continue; }
+            if (nm.empty()) { in.emplace_back(); have.push_back(false); continue; }
             const OnnxTensor* c = cst(nm);
             if (!c) return false;
-            in.push_back(c);
+            in.push_back(to_ct(*c));
+            have.push_back(true);
         }
-        if (in.empty() || !in[0]) return false;
-        OnnxTensor out;
+        if (in.empty() || !have[0]) return false;
+        if (numel_of(in[0].dims) > (1 << 20)) return false;  // shape arithmetic only, never weights
+        auto ints_of = [](const CT& c) { std::vector<int64_t> r; for (double d : c.v) r.push_back(static_cast<int64_t>(d)); return r; };
+        CT out;
         if (op == "Identity") {
-            out = *in[0];
+            out = in[0];
         } else if (op == "Cast") {
             const int64_t to = n.attr_i("to", 1);
-            out = from_doubles(as_doubles(*in[0]), to == 1 || to == 10 || to == 11, in[0]->dims);
-            if (!(to == 1 || to == 10 || to == 11)) for (auto& v : out.i) v = static_cast<int64_t>(v);
-        } else if (op == "Gather") {
-            if (in.size() < 2 || !in[1] || n.attr_i("axis", 0) != 0) return false;
-            const std::vector<double> src = as_doubles(*in[0]);
-            std::vector<double> v;
-            for (int64_t idx : in[1]->i) {
-                if (idx < 0) idx += static_cast<int64_t>(src.size());
-                if (idx < 0 || idx >= static_cast<int64_t>(src.size())) return false;
-                v.push_back(src[idx]);
+            out = in[0];
+            out.fl = (to == 1 || to == 10 || to == 11);
+            if (!out.fl) for (auto& x : out.v) x = trunc(x);
+        } else if (op == "Floor") {
+            out = in[0];
+            for (auto& x : out.v) x = floor(x);
+        } else if (op == "Mul" || op == "Div" || op == "Add" || op == "Sub") {
+            if (in.size() < 2 || !have[1] || in[0].v.empty() || in[1].v.empty()) return false;
+            const CT &a = in[0], &b = in[1];
+            if (a.v.size() != b.v.size() && a.v.size() != 1 && b.v.size() != 1) return false;
+            out.fl = a.fl || b.fl;
+            out.dims = a.v.size() >= b.v.size() ? a.dims : b.dims;
+            const size_t nn = std::max(a.v.size(), b.v.size());
+            out.v.resize(nn);
+            for (size_t k = 0; k < nn; ++k) {
+                const double x = a.v[a.v.size() == 1 ? 0 : k], y = b.v[b.v.size() == 1 ? 0 : k];
+                double r = op == "Mul" ? x * y : op == "Add" ? x + y : op == "Sub" ? x - y : (y != 0 ? x / y : 0);
+                if (op == "Div" && !out.fl) r = trunc(r);
+                out.v[k] = r;
             }
-            out = from_doubles(v, in[0]->is_float(), in[1]->dims);
-        } else if (op == "Unsqueeze" || op == "Squeeze" || op == "Reshape") {
-            out = *in[0];
-            out.dims = {static_cast<int64_t>(out.numel())};
+        } else if (op == "Gather") {
+            if (in.size() < 2 || !have[1] || n.attr_i("axis", 0) != 0 || in[0].dims.empty()) return false;
+            const int64_t d0 = in[0].dims[0];
+            const int64_t inner = d0 ? numel_of(in[0].dims) / d0 : 0;
+            out.fl = in[0].fl;
+            out.dims = in[1].dims;
+            out.dims.insert(out.dims.end(), in[0].dims.begin() + 1, in[0].dims.end());
+            for (double di : in[1].v) {
+                int64_t idx = static_cast<int64_t>(di);
+                if (idx < 0) idx += d0;
+                if (idx < 0 || idx >= d0) return false;
+                out.v.insert(out.v.end(), in[0].v.begin() + idx * inner, in[0].v.begin() + (idx + 1) * inner);
+            }
+        } else if (op == "ConstantOfShape") {
+            out.dims = ints_of(in[0]);
+            double fill = 0.0;
+            out.fl = true;
+            auto it = n.attrs.find("value");
+            if (it != n.attrs.end()) {
+                const OnnxTensor& t = it->second.t;
+                out.fl = t.is_float();
+                if (out.fl && !t.f.empty()) fill = t.f[0];
+                if (!out.fl && !t.i.empty()) fill = static_cast<double>(t.i[0]);
+            }
+            const int64_t cnt = numel_of(out.dims);
+            if (cnt < 0 || cnt > (1 << 20)) return false;
+            out.v.assign(static_cast<size_t>(cnt), fill);
         } else if (op == "Concat") {
-            std::vector<double> v;
-            bool fl = false;
-            for (const OnnxTensor* t : in) { if (!t) return false; fl |= t->is_float(); const auto d = as_doubles(*t); v.insert(v.end(), d.begin(), d.end()); }
-            out = from_doubles(v, fl, {static_cast<int64_t>(v.size())});
+            int64_t axis = n.attr_i("axis", 0);
+            const size_t rank = in[0].dims.size();
+            if (axis < 0) axis += static_cast<int64_t>(rank);
+            if (rank == 0 || axis < 0 || axis >= static_cast<int64_t>(rank)) return false;
+            out.dims = in[0].dims;
+            out.dims[axis] = 0;
+            int64_t outer = 1;
+            for (int64_t a = 0; a < axis; ++a) outer *= in[0].dims[a];
+            for (size_t k = 0; k < in.size(); ++k) {
+                if (!have[k] || in[k].dims.size() != rank) return false;
+                out.dims[axis] += in[k].dims[axis];
+                out.fl = out.fl || in[k].fl;
+            }
+            for (int64_t o = 0; o < outer; ++o)
+                for (const CT& t : in) {
+                    const int64_t chunk = outer ? numel_of(t.dims) / outer : 0;
+                    out.v.insert(out.v.end(), t.v.begin() + o * chunk, t.v.begin() + (o + 1) * chunk);
+                }
+        } else if (op == "Reshape") {
+            if (in.size() < 2 || !have[1]) return false;
+            std::vector<int64_t> shape = ints_of(in[1]);
+            const int64_t total = numel_of(in[0].dims);
+            int64_t known = 1;
+            int infer = -1;
+            for (size_t k = 0; k < shape.size(); ++k) {
+                if (shape[k] == 0 && k < in[0].dims.size()) shape[k] = in[0].dims[k];
+                if (shape[k] == -1) infer = static_cast<int>(k);
+                else known *= shape[k];
+            }
+            if (infer >= 0) { if (known == 0) return false; shape[infer] = total / known; }
+            if (numel_of(shape) != total) return false;
+            out = in[0];
+            out.dims = shape;
+        } else if (op == "Unsqueeze" || op == "Squeeze") {
+            std::vector<int64_t> axes;
+            if (const auto* ax = n.attr_ints("axes")) axes = *ax;
+            else if (in.size() > 1 && have[1]) axes = ints_of(in[1]);
+            out = in[0];
+            if (op == "Unsqueeze") {
+                const int64_t rank = static_cast<int64_t>(in[0].dims.size() + axes.size());
+                for (auto& a : axes) if (a < 0) a += rank;
+                std::sort(axes.begin(), axes.end());
+                for (int64_t a : axes) { if (a < 0 || a > static_cast<int64_t>(out.dims.size())) return false; out.dims.insert(out.dims.begin() + a, 1); }
+            } else {
+                const int64_t rank = static_cast<int64_t>(in[0].dims.size());
+                std::vector<int64_t> keep;
+                for (int64_t a = 0; a < rank; ++a) {
+                    bool drop = axes.empty() ? in[0].dims[a] == 1 : false;
+                    for (int64_t x : axes) if ((x < 0 ? x + rank : x) == a) drop = true;
+                    if (!drop) keep.push_back(in[0].dims[a]);
+                }
+                out.dims = keep;
+            }
+        } else if (op == "Transpose") {
+            const size_t rank = in[0].dims.size();
+            std::vector<int64_t> perm;
+            if (const auto* pp = n.attr_ints("perm")) perm = *pp;
+            else for (size_t k = 0; k < rank; ++k) perm.push_back(static_cast<int64_t>(rank - 1 - k));
+            if (perm.size() != rank) return false;
+            std::vector<int64_t> od(rank), start(rank, 0), step(rank, 1);
+            std::vector<int> axis(rank);
+            for (size_t k = 0; k < rank; ++k) {
+                if (perm[k] < 0 || perm[k] >= static_cast<int64_t>(rank)) return false;
+                od[k] = in[0].dims[perm[k]];
+                axis[k] = static_cast<int>(perm[k]);
+            }
+            out = gather_nd(in[0], od, axis, start, step);
         } else if (op == "Slice") {
-            const std::vector<double> src = as_doubles(*in[0]);
-            int64_t s = 0, e = static_cast<int64_t>(src.size()), st = 1;
-            if (in.size() >= 3 && in[1] && in[2]) {
-                s = in[1]->i.empty() ? 0 : in[1]->i[0];
-                e = in[2]->i.empty() ? e : in[2]->i[0];
-                if (in.size() >= 5 && in[4] && !in[4]->i.empty()) st = in[4]->i[0];
+            const size_t rank = in[0].dims.size();
+            std::vector<int64_t> starts, ends, axes, steps;
+            if (in.size() >= 3 && have[1] && have[2]) {
+                starts = ints_of(in[1]); ends = ints_of(in[2]);
+                if (in.size() >= 4 && have[3]) axes = ints_of(in[3]);
+                if (in.size() >= 5 && have[4]) steps = ints_of(in[4]);
             } else {
                 const auto* ss = n.attr_ints("starts"); const auto* ee = n.attr_ints("ends");
-                if (!ss || !ee || ss->empty() || ee->empty()) return false;
-                s = (*ss)[0]; e = (*ee)[0];
+                if (!ss || !ee) return false;
+                starts = *ss; ends = *ee;
+                if (const auto* ax = n.attr_ints("axes")) axes = *ax;
             }
-            const int64_t len = static_cast<int64_t>(src.size());
-            if (s < 0) s += len;
-            if (e < 0) e += len;
-            s = std::max<int64_t>(0, std::min(s, len));
-            e = std::max<int64_t>(0, std::min(e, len));
-            if (st <= 0) return false;
-            std::vector<double> v;
-            for (int64_t k = s; k < e; k += st) v.push_back(src[k]);
-            out = from_doubles(v, in[0]->is_float(), {static_cast<int64_t>(v.size())});
-        } else if (op == "Mul" || op == "Div" || op == "Add" || op == "Sub") {
-            if (in.size() < 2 || !in[1]) return false;
-            const auto a = as_doubles(*in[0]), b = as_doubles(*in[1]);
-            if (a.empty() || b.empty()) return false;
-            const size_t nn = std::max(a.size(), b.size());
-            const bool fl = in[0]->is_float() || in[1]->is_float();
-            std::vector<double> v(nn);
-            for (size_t k = 0; k < nn; ++k) {
-                const double x = a[a.size() == 1 ? 0 : k], y = b[b.size() == 1 ? 0 : k];
-                double r = op == "Mul" ? x * y : op == "Add" ? x + y : op == "Sub" ? x - y : (y != 0 ? x / y : 0);
-                if (op == "Div" && !fl) r = trunc(r);
-                v[k] = r;
+            if (axes.empty()) for (size_t k = 0; k < starts.size(); ++k) axes.push_back(static_cast<int64_t>(k));
+            if (steps.empty()) steps.assign(starts.size(), 1);
+            if (ends.size() != starts.size() || axes.size() != starts.size() || steps.size() != starts.size()) return false;
+            std::vector<int64_t> od = in[0].dims, start(rank, 0), step(rank, 1);
+            std::vector<int> axis(rank);
+            for (size_t k = 0; k < rank; ++k) axis[k] = static_cast<int>(k);
+            for (size_t k = 0; k < starts.size(); ++k) {
+                int64_t a = axes[k];
+                if (a < 0) a += static_cast<int64_t>(rank);
+                if (a < 0 || a >= static_cast<int64_t>(rank) || steps[k] == 0) return false;
+                const int64_t dim = in[0].dims[a], st = steps[k];
+                int64_t s0 = starts[k], e0 = ends[k];
+                // ONNX Slice clamping rules (INT64 extremes mean "to the end")
+                if (s0 < 0) s0 = std::max<int64_t>(s0 + dim, st > 0 ? 0 : -1);
+                if (e0 < 0) e0 = std::max<int64_t>(e0 + dim, -1);
+                if (st > 0) { s0 = std::min(s0, dim); e0 = std::min(e0, dim); }
+                else { s0 = std::min(s0, dim - 1); e0 = std::min(e0, dim - 1); if (ends[k] < -dim) e0 = -1; }
+                int64_t cnt = st > 0 ? (e0 - s0 + st - 1) / st : (s0 - e0 + (-st) - 1) / (-st);
+                if (cnt < 0) cnt = 0;
+                od[a] = cnt; start[a] = s0; step[a] = st;
             }
-            out = from_doubles(v, fl, a.size() >= b.size() ? in[0]->dims : in[1]->dims);
-        } else if (op == "Floor") {
-            auto v = as_doubles(*in[0]);
-            for (auto& x : v) x = floor(x);
-            out = from_doubles(v, in[0]->is_float(), in[0]->dims);
+            out = gather_nd(in[0], od, axis, start, step);
         } else {
             return false;
         }
-        consts[n.outputs[0]] = out;
+        consts[n.outputs[0]] = from_ct(out);
         return true;
     }
 

@@ -276,8 +276,9 @@ class ExportOptions:
     packed_attrs: bool = True
     batch: object = "N"  # declared batch dim: symbolic or an int (Unity export pins 1)
     bn_eps: float = 1e-5
-    obj_bias: float = -4.5  # objectness channels' bias: keeps candidates at thr 0.1 down to tens per frame
-    head_gain: float = 2.0  # head weights ~ N(0, (head_gain/sqrt(fan_in))^2): logits of O(1) spread
+    obj_fraction: float = 0.005  # share of anchor boxes whose objectness clears 0.11 on the calibration frames
+    obj_spread: float = 1.5  # standard deviation of the objectness logits over positions
+    head_gain: float = 1.0  # RMS of the head logits (calibrated)
     opset: int = 11
 
 
@@ -286,9 +287,26 @@ def _he_sigma(fan_in: int) -> float:
     return float(np.sqrt(2.0 / (1.01 * fan_in)))
 
 
+def _leaky(x):
+    return np.where(x > 0, x, np.float32(0.1) * x)
+
+
 def build_onnx(arch: str, num_classes: int, size: int = 416, seed: int = 0,
                opts: Optional[ExportOptions] = None) -> bytes:
-    """Serialized ModelProto for `arch` in {"tiny", "full", "rsu"} with seeded random weights."""
+    """Serialized ModelProto for `arch` in {"tiny", "full", "rsu"} with seeded random weights.
+
+    Weights are the SURVEY §8d recipe — He-normal convs, BatchNorm gamma~U(.8,1.2), beta~N(0,.1),
+    mean~N(0,.1), var~U(.8,1.2) — followed by one scalar per layer, fitted on two synthetic frames: each
+    BatchNorm's affine pair (gamma, beta) is multiplied by k so the activation RMS after the LeakyReLU is ~1,
+    residual branches end at 0.3x the RMS of the stream they are added to, and head logits have RMS
+    `head_gain`, with the objectness channels biased so ~`obj_fraction` of the boxes become candidates.  Without the scalars
+    the 23 residual adds let the RMS drift by three orders of magnitude, exp(tw) overflows and the boxes are
+    garbage.  The statistics are deliberately NOT fitted per channel: subtracting a data-fitted per-channel
+    mean from an untrained random net makes it amplify any perturbation (fp32-vs-fp64 noise grows 12x, bf16
+    rounding reaches 10% at the heads in a CPU emulation), which says nothing about the kernels."""
+    import torch
+    import torch.nn.functional as F
+
     opts = opts or ExportOptions()
     layers = ARCHS[arch](num_classes)
     rng = np.random.default_rng(seed)
@@ -298,6 +316,7 @@ def build_onnx(arch: str, num_classes: int, size: int = 416, seed: int = 0,
     names: List[str] = []  # output tensor name per darknet layer
     chans: List[int] = []
     spatial: List[int] = []
+    acts: List = []  # calibration activations per darknet layer (torch f32 [1,C,H,W])
 
     def add_const(name: str, arr: np.ndarray):
         if opts.const_as == "constant_node":
@@ -306,113 +325,142 @@ def build_onnx(arch: str, num_classes: int, size: int = 416, seed: int = 0,
         else:
             inits.append(tensor_proto(name, arr, raw=opts.raw_data))
 
+    def rms(t) -> float:
+        return float(torch.sqrt(torch.mean(t.double() ** 2)))
+
+    calib = np.stack([synthetic_frame(987654321 + seed + k, size) for k in range(2)])
+    x = torch.from_numpy(np.ascontiguousarray((calib / 255).astype(np.float32).transpose(0, 3, 1, 2)))
     cur, c, s = "input", 3, size
     head_c = 3 * (5 + num_classes)
     n_conv = 0
-    for i, l in enumerate(layers):
-        if l.kind == "conv":
-            n_conv += 1
-            tag = f"conv{n_conv}"
-            fan_in = c * l.size * l.size
-            is_head = not l.bn
-            if is_head:
-                w = rng.normal(0.0, opts.head_gain / np.sqrt(fan_in), size=(l.filters, c, l.size, l.size)).astype(np.float32)
-                b = np.zeros(l.filters, np.float32)
-                b[4::5 + num_classes] = opts.obj_bias
-            else:
+    with torch.no_grad():
+        for i, l in enumerate(layers):
+            if l.kind == "conv":
+                n_conv += 1
+                tag = f"conv{n_conv}"
+                fan_in = c * l.size * l.size
+                pad = l.size // 2
                 w = rng.normal(0.0, _he_sigma(fan_in), size=(l.filters, c, l.size, l.size)).astype(np.float32)
-                if l.res_tail:
-                    w *= 0.5
-                b = None
-            pad = l.size // 2
-            conv_attrs = dict(dilations=[1, 1], group=1, kernel_shape=[l.size, l.size],
-                              pads=[pad, pad, pad, pad], strides=[l.stride, l.stride])
-            out = f"{tag}_out"
-            if l.bn:
-                gamma = rng.uniform(0.8, 1.2, l.filters).astype(np.float32)
-                beta = rng.normal(0.0, 0.1, l.filters).astype(np.float32)
-                mean = rng.normal(0.0, 0.1, l.filters).astype(np.float32)
-                var = rng.uniform(0.8, 1.2, l.filters).astype(np.float32)
-                if opts.fold_bn:
-                    inv = gamma / np.sqrt(var + np.float32(opts.bn_eps))
-                    wf = (w * inv[:, None, None, None]).astype(np.float32)
-                    bf = (beta - mean * inv).astype(np.float32)
-                    add_const(f"{tag}_w", wf)
-                    add_const(f"{tag}_b", bf)
+                conv_attrs = dict(dilations=[1, 1], group=1, kernel_shape=[l.size, l.size],
+                                  pads=[pad, pad, pad, pad], strides=[l.stride, l.stride])
+                out = f"{tag}_out"
+                raw = F.conv2d(x, torch.from_numpy(w), None, stride=l.stride, padding=pad)
+                if l.bn:
+                    gamma = rng.uniform(0.8, 1.2, l.filters).astype(np.float32)
+                    beta = rng.normal(0.0, 0.1, l.filters).astype(np.float32)
+                    mean = rng.normal(0.0, 0.1, l.filters).astype(np.float32)
+                    var = rng.uniform(0.8, 1.2, l.filters).astype(np.float32)
+                    inv = 1.0 / np.sqrt(var + np.float32(opts.bn_eps))
+                    y = (raw - torch.from_numpy(mean).view(1, -1, 1, 1)) * torch.from_numpy(gamma * inv).view(1, -1, 1, 1) \
+                        + torch.from_numpy(beta).view(1, -1, 1, 1)
+                    a = F.leaky_relu(y, 0.1) if l.leaky else y
+                    target = 1.0
+                    if l.res_tail:
+                        target = 0.3 * rms(acts[i - 2])  # the stream this branch is added to (shortcut from -3)
+                    k = np.float32(target / max(rms(a), 1e-12))
+                    gamma, beta = (gamma * k).astype(np.float32), (beta * k).astype(np.float32)
+                    a = a * float(k)
+                    if opts.fold_bn:
+                        g_inv = (gamma * inv).astype(np.float32)
+                        add_const(f"{tag}_w", (w * g_inv[:, None, None, None]).astype(np.float32))
+                        add_const(f"{tag}_b", (beta - mean * g_inv).astype(np.float32))
+                        nodes.append(node_proto("Conv", [cur, f"{tag}_w", f"{tag}_b"], [out], name=tag,
+                                                packed=opts.packed_attrs, **conv_attrs))
+                    else:
+                        add_const(f"{tag}_w", w)
+                        nodes.append(node_proto("Conv", [cur, f"{tag}_w"], [f"{tag}_raw"], name=tag,
+                                                packed=opts.packed_attrs, **conv_attrs))
+                        for nm, arr in (("gamma", gamma), ("beta", beta), ("mean", mean), ("var", var)):
+                            add_const(f"{tag}_bn_{nm}", arr)
+                        nodes.append(node_proto(
+                            "BatchNormalization",
+                            [f"{tag}_raw", f"{tag}_bn_gamma", f"{tag}_bn_beta", f"{tag}_bn_mean", f"{tag}_bn_var"],
+                            [out], name=tag + "_bn", epsilon=float(opts.bn_eps), momentum=0.9))
+                else:  # detection head: linear, bias, logits of RMS head_gain
+                    k = np.float32(opts.head_gain / max(rms(raw), 1e-12))
+                    w = (w * k).astype(np.float32)
+                    b = np.zeros(l.filters, np.float32)
+                    gain = np.full(l.filters, k, np.float32)
+                    # objectness channels: a random net's channel is a big frame-wide offset plus a small
+                    # position-dependent part, so a fixed bias yields either zero or thousands of candidates all
+                    # sitting on the threshold.  Standardise these channels on the calibration frames (spread
+                    # `obj_spread`) and place the bias so ~`obj_fraction` of the boxes clear sigmoid(obj) >= 0.11.
+                    cut = float(np.log(0.11 / 0.89))
+                    for ch in range(4, l.filters, 5 + num_classes):
+                        v = raw[:, ch].reshape(-1).double()
+                        # (capped: a channel that barely varies over positions would otherwise turn bf16
+                        # rounding of its large common-mode part into logit noise)
+                        gain[ch] = np.float32(min(opts.obj_spread / max(float(v.std()), 1e-12), 4.0 * float(k)))
+                        b[ch] = cut - float(torch.quantile(v * float(gain[ch]), 1.0 - opts.obj_fraction))
+                    w = (w * (gain / k)[:, None, None, None]).astype(np.float32)
+                    raw = raw * torch.from_numpy(gain / k).view(1, -1, 1, 1)
+                    a = raw * float(k) + torch.from_numpy(b).view(1, -1, 1, 1)
+                    add_const(f"{tag}_w", w)
+                    add_const(f"{tag}_b", b)
                     nodes.append(node_proto("Conv", [cur, f"{tag}_w", f"{tag}_b"], [out], name=tag,
                                             packed=opts.packed_attrs, **conv_attrs))
+                if l.leaky:
+                    nodes.append(node_proto("LeakyRelu", [out], [f"{tag}_act"], name=tag + "_leaky", alpha=0.1))
+                    out = f"{tag}_act"
+                cur, c, s, x = out, l.filters, s // l.stride, a
+            elif l.kind == "shortcut":
+                j = i + l.frm[0]
+                out = f"add{i}_out"
+                nodes.append(node_proto("Add", [cur, names[j]], [out], name=f"add{i}"))
+                cur, x = out, x + acts[j]
+            elif l.kind == "route":
+                idx = [j if j >= 0 else i + j for j in l.frm]
+                if len(idx) == 1:
+                    cur, c, s, x = names[idx[0]], chans[idx[0]], spatial[idx[0]], acts[idx[0]]
                 else:
-                    add_const(f"{tag}_w", w)
-                    nodes.append(node_proto("Conv", [cur, f"{tag}_w"], [f"{tag}_raw"], name=tag,
-                                            packed=opts.packed_attrs, **conv_attrs))
-                    for nm, arr in (("gamma", gamma), ("beta", beta), ("mean", mean), ("var", var)):
-                        add_const(f"{tag}_bn_{nm}", arr)
-                    nodes.append(node_proto(
-                        "BatchNormalization",
-                        [f"{tag}_raw", f"{tag}_bn_gamma", f"{tag}_bn_beta", f"{tag}_bn_mean", f"{tag}_bn_var"],
-                        [out], name=tag + "_bn", epsilon=float(opts.bn_eps), momentum=0.9))
-            else:
-                add_const(f"{tag}_w", w)
-                add_const(f"{tag}_b", b)
-                nodes.append(node_proto("Conv", [cur, f"{tag}_w", f"{tag}_b"], [out], name=tag,
-                                        packed=opts.packed_attrs, **conv_attrs))
-            if l.leaky:
-                nodes.append(node_proto("LeakyRelu", [out], [f"{tag}_act"], name=tag + "_leaky", alpha=0.1))
-                out = f"{tag}_act"
-            cur, c, s = out, l.filters, s // l.stride
-        elif l.kind == "shortcut":
-            other = names[i + l.frm[0]]
-            out = f"add{i}_out"
-            nodes.append(node_proto("Add", [cur, other], [out], name=f"add{i}"))
-            cur = out
-        elif l.kind == "route":
-            idx = [j if j >= 0 else i + j for j in l.frm]
-            if len(idx) == 1:
-                cur, c, s = names[idx[0]], chans[idx[0]], spatial[idx[0]]
-            else:
-                out = f"concat{i}_out"
-                nodes.append(node_proto("Concat", [names[j] for j in idx], [out], name=f"concat{i}", axis=1))
-                cur, c, s = out, sum(chans[j] for j in idx), spatial[idx[0]]
-        elif l.kind == "upsample":
-            out = f"up{i}_out"
-            scales = np.array([1.0, 1.0, 2.0, 2.0], np.float32)
-            add_const(f"up{i}_scales", scales)
-            if opts.upsample_op == "Resize":
-                add_const(f"up{i}_roi", np.zeros((0,), np.float32))
-                nodes.append(node_proto("Resize", [cur, f"up{i}_roi", f"up{i}_scales"], [out], name=f"up{i}",
-                                        coordinate_transformation_mode="asymmetric", mode="nearest",
-                                        nearest_mode="floor"))
-            elif opts.upsample_op == "Upsample":
-                nodes.append(node_proto("Upsample", [cur, f"up{i}_scales"], [out], name=f"up{i}", mode="nearest"))
-            else:
-                raise ValueError(opts.upsample_op)
-            cur, s = out, s * 2
-        elif l.kind == "maxpool":
-            out = f"pool{i}_out"
-            if l.stride == 1:
-                if opts.pool_pad == "pad_node":
-                    pads = np.array([0, 0, 0, 0, 0, 0, 1, 1], np.int64)
-                    add_const(f"pool{i}_pads", pads)
-                    add_const(f"pool{i}_padval", np.array(-3.0e38, np.float32))
-                    nodes.append(node_proto("Pad", [cur, f"pool{i}_pads", f"pool{i}_padval"], [f"pool{i}_padded"],
-                                            name=f"pool{i}_pad", mode="constant"))
-                    nodes.append(node_proto("MaxPool", [f"pool{i}_padded"], [out], name=f"pool{i}",
-                                            packed=opts.packed_attrs, kernel_shape=[2, 2], pads=[0, 0, 0, 0],
-                                            strides=[1, 1]))
+                    out = f"concat{i}_out"
+                    nodes.append(node_proto("Concat", [names[j] for j in idx], [out], name=f"concat{i}", axis=1))
+                    cur, c, s = out, sum(chans[j] for j in idx), spatial[idx[0]]
+                    x = torch.cat([acts[j] for j in idx], dim=1)
+            elif l.kind == "upsample":
+                out = f"up{i}_out"
+                scales = np.array([1.0, 1.0, 2.0, 2.0], np.float32)
+                add_const(f"up{i}_scales", scales)
+                if opts.upsample_op == "Resize":
+                    add_const(f"up{i}_roi", np.zeros((0,), np.float32))
+                    nodes.append(node_proto("Resize", [cur, f"up{i}_roi", f"up{i}_scales"], [out], name=f"up{i}",
+                                            coordinate_transformation_mode="asymmetric", mode="nearest",
+                                            nearest_mode="floor"))
+                elif opts.upsample_op == "Upsample":
+                    nodes.append(node_proto("Upsample", [cur, f"up{i}_scales"], [out], name=f"up{i}", mode="nearest"))
+                else:
+                    raise ValueError(opts.upsample_op)
+                cur, s = out, s * 2
+                x = x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3)
+            elif l.kind == "maxpool":
+                out = f"pool{i}_out"
+                if l.stride == 1:
+                    if opts.pool_pad == "pad_node":
+                        pads = np.array([0, 0, 0, 0, 0, 0, 1, 1], np.int64)
+                        add_const(f"pool{i}_pads", pads)
+                        add_const(f"pool{i}_padval", np.array(-3.0e38, np.float32))
+                        nodes.append(node_proto("Pad", [cur, f"pool{i}_pads", f"pool{i}_padval"],
+                                                [f"pool{i}_padded"], name=f"pool{i}_pad", mode="constant"))
+                        nodes.append(node_proto("MaxPool", [f"pool{i}_padded"], [out], name=f"pool{i}",
+                                                packed=opts.packed_attrs, kernel_shape=[2, 2], pads=[0, 0, 0, 0],
+                                                strides=[1, 1]))
+                    else:
+                        nodes.append(node_proto("MaxPool", [cur], [out], name=f"pool{i}", packed=opts.packed_attrs,
+                                                kernel_shape=[2, 2], pads=[0, 0, 1, 1], strides=[1, 1]))
+                    x = F.max_pool2d(F.pad(x, (0, 1, 0, 1), value=float("-inf")), 2, 1)
                 else:
                     nodes.append(node_proto("MaxPool", [cur], [out], name=f"pool{i}", packed=opts.packed_attrs,
-                                            kernel_shape=[2, 2], pads=[0, 0, 1, 1], strides=[1, 1]))
-            else:
-                nodes.append(node_proto("MaxPool", [cur], [out], name=f"pool{i}", packed=opts.packed_attrs,
-                                        kernel_shape=[l.size, l.size], pads=[0, 0, 0, 0],
-                                        strides=[l.stride, l.stride]))
-                s = s // l.stride
-            cur = out
-        elif l.kind == "yolo":
-            outputs.append((cur, (opts.batch, head_c, s, s)))
-        names.append(cur)
-        chans.append(c)
-        spatial.append(s)
+                                            kernel_shape=[l.size, l.size], pads=[0, 0, 0, 0],
+                                            strides=[l.stride, l.stride]))
+                    s = s // l.stride
+                    x = F.max_pool2d(x, l.size, l.stride)
+                cur = out
+            elif l.kind == "yolo":
+                outputs.append((cur, (opts.batch, head_c, s, s)))
+            names.append(cur)
+            chans.append(c)
+            spatial.append(s)
+            acts.append(x)
 
     graph = b"".join(_f_bytes(1, n) for n in nodes)
     graph += _f_str(2, f"yolov3-{arch}")
@@ -433,15 +481,19 @@ def write_model(path: str, arch: str, num_classes: int, size: int = 416, seed: i
 
 
 def synthetic_frame(seed: int, size: int = 416) -> np.ndarray:
-    """'dog-shaped' synthetic frame: per-channel N(mu=[135,136,116], sigma=54), 3x3 box blur, u8."""
+    """'dog-shaped' synthetic frame: matches the first two moments of the reference's testdata/dog.jpg
+    (per-channel mean ~[135,136,116], sigma ~54) with image-like spatial structure: a coarse
+    16-pixel block pattern (sigma 50) plus 3x3-blurred pixel noise (sigma ~18), clipped to u8."""
     rng = np.random.default_rng(seed)
     mu = np.array([135.0, 136.0, 116.0])
-    a = rng.normal(mu, 54.0, size=(size + 2, size + 2, 3))
-    acc = np.zeros((size, size, 3))
+    g = (size + 15) // 16
+    coarse = rng.normal(0.0, 50.0, size=(g, g, 3)).repeat(16, axis=0).repeat(16, axis=1)[:size, :size]
+    a = rng.normal(0.0, 54.0, size=(size + 2, size + 2, 3))
+    fine = np.zeros((size, size, 3))
     for dy in range(3):
         for dx in range(3):
-            acc += a[dy:dy + size, dx:dx + size]
-    return np.clip(np.rint(acc / 9.0), 0, 255).astype(np.uint8)
+            fine += a[dy:dy + size, dx:dx + size]
+    return np.clip(np.rint(mu + coarse + fine / 9.0), 0, 255).astype(np.uint8)
 
 
 if __name__ == "__main__":

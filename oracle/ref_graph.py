@@ -206,12 +206,14 @@ class GraphExecutor:
                         starts, ends = n.attrs["starts"], n.attrs["ends"]
                         axes = n.attrs.get("axes", list(range(len(starts))))
                         steps = [1] * len(starts)
-                    out = ins[0]
+                    arr = ins[0].numpy()
+                    index = [slice(None)] * arr.ndim
                     for s, e, ax, st in zip(starts, ends, axes, steps):
-                        dim = out.shape[ax]
-                        s = max(min(s + dim if s < 0 else s, dim), 0)
-                        e = max(min(e + dim if e < 0 else e, dim), 0)
-                        out = out.narrow(ax, s, max(e - s, 0))[(slice(None),) * ax + (slice(None, None, st),)]
+                        # numpy slicing clamps exactly like the ONNX Slice specification (INT64 extremes included)
+                        index[ax] = slice(int(np.clip(s, -2**62, 2**62)), int(np.clip(e, -2**62, 2**62)), st)
+                        if st < 0 and e < -arr.shape[ax]:
+                            index[ax] = slice(int(np.clip(s, -2**62, 2**62)), None, st)
+                    out = torch.from_numpy(np.ascontiguousarray(arr[tuple(index)]))
                 elif op == "Unsqueeze":
                     axes = n.attrs.get("axes") or [int(v) for v in ins[1]]
                     out = ins[0]

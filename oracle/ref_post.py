@@ -122,7 +122,7 @@ def overlap(sel: Sequence[float], other: Sequence[float]) -> float:
     return (iw * ih) / (w0 * h0)
 
 
-def soft_nms(cands: List[Cand], threshold: float) -> List[Tuple[float, Cand]]:
+def soft_nms(cands: List[Cand], threshold: float, leftovers: dict = None) -> List[Tuple[float, Cand]]:
     """Returns [(decayed_score_at_selection, candidate)] in the reference's output order.
 
     detector.py:45-59: repeatedly take the arg-max of the current scores (first in insertion order on ties,
@@ -143,11 +143,13 @@ def soft_nms(cands: List[Cand], threshold: float) -> List[Tuple[float, Cand]]:
         picked.append((top, sel))
         box = sel[3:7]
         live = [(c, s * math.exp(-3 * (overlap(box, c[3:7]) ** 2))) for (c, s) in live]
+    if leftovers is not None:  # test aid: final (decayed) score of every candidate that was never selected
+        leftovers.update({c[0]: s for (c, s) in live})
     return picked
 
 
 def detect_from_heads(heads: Sequence[np.ndarray], frame: int, num_classes: int, net_wh, threshold: float,
-                      fast: bool = True):
+                      fast: bool = True, leftovers: dict = None):
     """heads: graph outputs [N,C,H,W] float32 in graph order.  Returns the reference's result tuples
     ``(klass, conf, x, y, w, h)`` for one frame (detector.py:136-144) plus the candidate indices kept."""
     net_w, net_h = net_wh
@@ -159,7 +161,7 @@ def detect_from_heads(heads: Sequence[np.ndarray], frame: int, num_classes: int,
         m = np.ascontiguousarray(out[frame].transpose(1, 2, 0))
         cands.extend(dec(anchors, m, num_classes, net_wh, threshold, first))
         first += m.shape[0] * m.shape[1] * 3
-    kept = soft_nms(cands, threshold)
+    kept = soft_nms(cands, threshold, leftovers)
     results = [(c[1], c[2], c[3] * net_w, c[4] * net_h, c[5] * net_w, c[6] * net_h) for (_, c) in kept]
     return results, [c[0] for (_, c) in kept], [s for (s, _) in kept]
 

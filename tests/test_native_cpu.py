@@ -1,0 +1,128 @@
+"""CPU-side checks of the native library: it loads, exports every symbol include/fastdet_b200.h declares,
+plans ONNX graphs (host logic only) and refuses — loudly — to compute without a CUDA device."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from fastdet_b200 import _native, modelgen
+from fastdet_b200 import detector as fdet
+from tests import torch_export
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HAS_GPU = torch.cuda.is_available()
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(ROOT, "include", "fastdet_b200.h")).read()
+    declared = set(re.findall(r"\b(fd_[a-z0-9_]+)\s*\(", header))
+    assert len(declared) >= 18
+    lib = _native.lib()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in the header but not exported"
+    assert declared == set(_native._PROTOS), "ctypes prototypes and header disagree"
+    assert lib.fd_abi_version() == 1
+    assert ctypes.sizeof(_native.FdDet) == 48
+
+
+@pytest.mark.parametrize("arch,nc,convs,layers", [("tiny", 80, 13, 19), ("full", 80, 75, 75), ("rsu", 9, 75, 75)])
+def test_planner_on_generated_models(arch, nc, convs, layers):
+    size = 416 if arch == "tiny" else 160
+    data = modelgen.build_onnx(arch, nc, size, seed=3)
+    m = _native.Model(data, nc, (size, size), device=-1)
+    info = m.info
+    assert info.n_conv == convs and info.n_layers == layers  # every Add/Resize/Concat fused away
+    assert info.n_heads == (2 if arch == "tiny" else 3)
+    g = size // 32
+    assert m.head_shapes == [(3 * (5 + nc), g * (1 << i), g * (1 << i)) for i in range(info.n_heads)]
+    assert info.boxes_per_frame == sum(3 * h * w for _, h, w in m.head_shapes)
+    assert abs(info.conv_flops_per_frame * 1e-9 - modelgen.conv_gflops(arch, nc, size)) < 1e-6
+    L = m.layers()
+    assert L[0]["kind"] == 0 and L[0]["cin"] == 3
+    if arch != "tiny":
+        assert sum(l["has_residual"] for l in L) == 23 and sum(l["upsample2x"] for l in L) == 2
+    anchors = np.array(info.anchors).reshape(4, 3, 2)
+    want = fdet.ONNXDetector.ANCHORS[info.n_heads]
+    assert np.array_equal(anchors[:info.n_heads], np.array(want, np.float32))
+    m.close()
+
+
+def test_flop_table_matches_survey():
+    assert round(modelgen.conv_gflops("tiny", 80, 416), 3) == 5.565
+    assert round(modelgen.conv_gflops("full", 80, 416), 3) == 65.864
+    assert round(modelgen.conv_gflops("rsu", 9, 416), 3) == 65.348
+    assert round(modelgen.conv_gflops("full", 80, 608), 3) == 140.692
+
+
+def test_planner_accepts_every_exporter_form():
+    base = _native.Model(modelgen.build_onnx("tiny", 5, 96, seed=2), 5, (96, 96), device=-1).layers()
+    alt = modelgen.ExportOptions(fold_bn=False, upsample_op="Upsample", pool_pad="pad_node", const_as="constant_node",
+                                 raw_data=False, packed_attrs=False, batch=1)
+    other = _native.Model(modelgen.build_onnx("tiny", 5, 96, seed=2, opts=alt), 5, (96, 96), device=-1).layers()
+    keys = ("kind", "c", "h", "w", "cin", "ksize", "stride", "act", "has_residual", "upsample2x", "out_fp32")
+    assert [[l[k] for k in keys] for l in base] == [[l[k] for k in keys] for l in other]
+    for training_form in (False, True):  # torch's own serializer: Pad built from Shape/Gather/Slice/Transpose chains
+        net = torch_export.MiniYolo(nc=4, width=16).eval()
+        m = _native.Model(torch_export.export(net, 64, training_form=training_form), 4, (64, 64), device=-1)
+        assert m.info.n_layers == 12 and m.head_shapes == [(27, 16, 16), (27, 32, 32)]
+
+
+def test_planner_errors():
+    good = modelgen.build_onnx("tiny", 3, 64, seed=1)
+    with pytest.raises(_native.NativeError) as e:
+        _native.Model(b"not an onnx file at all", 3, (64, 64), device=-1)
+    assert e.value.code == _native.FD_ERR_MODEL
+    with pytest.raises(_native.NativeError) as e:  # head channels do not match num_classes
+        _native.Model(good, 80, (64, 64), device=-1)
+    assert e.value.code == _native.FD_ERR_MODEL and "num_classes" in e.value.msg
+    with pytest.raises(_native.NativeError) as e:  # reference feeds {'input': a}: any other input name fails
+        _native.Model(good.replace(b"\x0a\x05input", b"\x0a\x05inpux"), 3, (64, 64), device=-1)
+    assert "input" in e.value.msg
+    with pytest.raises(_native.NativeError) as e:
+        _native.Model(good, 3, (70, 64), device=-1)
+    assert e.value.code == _native.FD_ERR_ARG
+    with pytest.raises(_native.NativeError) as e:  # truncated file
+        _native.Model(good[: len(good) // 2], 3, (64, 64), device=-1)
+    assert e.value.code == _native.FD_ERR_MODEL
+
+
+def test_no_cpu_fallback():
+    data = modelgen.build_onnx("tiny", 3, 64, seed=1)
+    m = _native.Model(data, 3, (64, 64), device=-1)
+    frames = np.zeros((1, 64, 64, 3), np.uint8)
+    for call in (lambda: m.forward(1), lambda: m.detect(frames, 0.1), lambda: m.normalise(frames),
+                 lambda: m.heads(1), lambda: m.preprocess(frames, 1, (64, 64))):
+        with pytest.raises(_native.NativeError) as e:
+            call()
+        assert e.value.code == _native.FD_ERR_CUDA
+    if not HAS_GPU:
+        assert _native.device_count() == 0
+        with pytest.raises(_native.NativeError) as e:  # the product path never falls back to a CPU implementation
+            fdet.ONNXDetector(data, num_classes=3, image_size=(64, 64))
+        assert e.value.code == _native.FD_ERR_CUDA and "no CPU fallback" in e.value.msg
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "fastdet_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cc", ".h", ".cuh")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert not re.search(r"^\s*(from|import)\s+oracle\b", text, re.M), f"{f} imports the oracle"
+                assert "oracle/" not in text or f in ("build.py",), f"{f} references oracle/"
+
+
+def test_dummy_detector_golden(golden_dir):
+    z = np.load(os.path.join(golden_dir, "kat.npz"))
+    got = fdet.DummyDetector().perform(b"anything")
+    assert np.array_equal(np.array(got, np.float64), z["dummy"])  # (16, 1.0, 208.0, 208.0, 166.4, 166.4)
+    assert repr(fdet.DummyDetector()) == "<DummyDetector>"
+
+
+def test_dbgout_dump(tmp_path):
+    p = tmp_path / "dump.bin"
+    fdet.DummyDetector(dbgout=str(p)).perform(b"\x01\x02\x03")
+    assert p.read_bytes() == b"\x01\x02\x03"
