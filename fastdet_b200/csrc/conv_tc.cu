@@ -6,12 +6,17 @@
 // Stands in for the Conv/BatchNormalization/LeakyRelu/Add (and the Resize+Concat that follow a
 // branch conv) nodes ONNX Runtime executes at reference server/detector.py:135.
 //
-// CTA = 8 warps:  warp 0 lane 0  TMA producer (A: 2D tiled map for 1x1, im2col map for 3x3; B: 2D tiled)
+// CTA = 12 warps: warp 0 lane 0  TMA producer (A: 2D tiled map for 1x1, im2col map for 3x3; B: 2D tiled)
 //                 warp 1 lane 0  tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction)
 //                 warp 2         TMEM allocator
-//                 warps 4..7     epilogue (TMEM lane quarter = warp % 4)
-// Pipelines: smem ring (full/empty mbarriers, STAGES deep) between TMA and MMA; two TMEM accumulator
-// stages (tmem_full/tmem_empty) between MMA and epilogue so tile i's epilogue overlaps tile i+1's mainloop.
+//                 warps 4..7     epilogue group 0 (even tiles, TMEM accumulator stage 0)
+//                 warps 8..11    epilogue group 1 (odd tiles,  TMEM accumulator stage 1)   (TMEM lane quarter = warp % 4)
+// Pipelines: smem ring (full/empty mbarriers, num_stages deep) between TMA and MMA; two TMEM accumulator
+// stages (tmem_full/tmem_empty) between MMA and the epilogue groups, so two tiles' epilogues and the next
+// tile's mainloop are in flight at once (the per-tile epilogue latency, not the MMAs, bounds small-K layers).
+// Epilogue: tcgen05.ld -> bias + LeakyReLU in fp32 (lane = pixel row) -> bf16 staging tile in shared memory
+// (XOR-swizzled, conflict-free) -> re-read "transposed" so that 4 lanes cover 64 contiguous bytes of one pixel
+// row: the residual loads and the output stores are coalesced 16-byte-per-lane accesses.
 #include "conv_tc.h"
 #include "ptx.cuh"
 
@@ -21,18 +26,19 @@
 namespace fd {
 
 static constexpr int BLOCK_M = 128;
-static constexpr int NUM_THREADS = 256;
-static constexpr int A_STAGE_BYTES = BLOCK_M * 64 * 2;  // sized for block_k = 64
+static constexpr int NUM_THREADS = 384;
+static constexpr int MAX_STAGES = 32;
+// dynamic shared memory map (after aligning the base to 1024 B):
+//   [0, 1024)       full[32] + empty[32] + tmem_full[2] + tmem_empty[2] mbarriers, TMEM base slot
+//   [1024, 33792)   epilogue staging: 8 warps x (32 rows x 32 fp32) = 8 x 4 KB
+//   [33792, ...)    operand ring: num_stages x (A stage | B stage), every stage 1024-byte aligned
+static constexpr int SMEM_STAGING_OFF = 1024;
+static constexpr int SMEM_RING_OFF = 1024 + 8 * 4096;
+static constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int BLOCK_N>
 struct TileCfg {
-    static constexpr int B_STAGE_BYTES = BLOCK_N * 64 * 2;
-    static constexpr int STAGES = (BLOCK_N == 256) ? 4 : (BLOCK_N == 128 ? 6 : 8);
     static constexpr int TMEM_COLS = (2 * BLOCK_N < 32) ? 32 : 2 * BLOCK_N;  // 64,128,256,512: powers of two
-    static constexpr int BAR_BYTES = (2 * STAGES + 4) * 8 + 16;
-    static constexpr int BIAS_BYTES = 2 * BLOCK_N * 4;
-    static constexpr size_t SMEM_BYTES =
-        1024 /*align slack*/ + size_t(STAGES) * (A_STAGE_BYTES + B_STAGE_BYTES) + BIAS_BYTES + BAR_BYTES;
 };
 
 __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
@@ -42,26 +48,177 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// One accumulator tile (128 rows x BLOCK_N columns of this CTA's TMEM) -> global memory.
+//   taddr0     TMEM address of the warp's lane quarter at the accumulator stage's first column
+//   m_base     global output-pixel index of the warp's first row
+//   empty_addr shared address of the tmem_empty barrier to arrive on once the accumulator is drained
+//              (for a CTA pair: the leader's barrier, reached through the shared::cluster window)
 template <int BLOCK_N>
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr0, float* stage_buf, long long m_base,
+                                              int n0, int lane, uint32_t full_addr, uint32_t aphase,
+                                              uint32_t empty_addr, long long* t_acc) {
+    const int hw = p.ho * p.wo;
+    const int sub = lane >> 2;  // row within an 8-row pass of the transposed phase
+    const int j = lane & 3;     // which 8 of the chunk's 32 channels this lane owns there
+    // destination rows of the 4 pixel rows this lane touches in the transposed phase
+    long long orow[4];
+    bool ok[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const long long m = m_base + 8 * i + sub;
+        ok[i] = m < p.M;
+        orow[i] = m;
+        if (p.upsample2x && ok[i]) {
+            const int img = static_cast<int>(m / hw);
+            const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+            const int oy = rem / p.wo;
+            const int ox = rem - oy * p.wo;
+            orow[i] = (static_cast<long long>(img) * 2 * p.ho + 2 * oy) * (2LL * p.wo) + 2 * ox;
+        }
+    }
+    const bool has_res = p.residual != nullptr;
+    uint4 rnext[4];
+    auto fetch_res = [&](int c0) {
+        const int ch = n0 + c0 + 8 * j;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            rnext[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res && ok[i] && ch < p.cout)
+                rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (m_base + 8 * i + sub) * p.res_pitch + ch));
+        }
+    };
+    fetch_res(0);  // independent of the accumulator: in flight while the MMAs finish
+
+    const long long ta0 = t_acc ? clock64() : 0;
+    ptx::mbar_wait_addr(full_addr, aphase);
+    if (t_acc) *t_acc += clock64() - ta0;
+    ptx::tc_fence_after();
+
+    const long long m_own = m_base + lane;  // the pixel row this lane holds in the row-major phase
+    const bool own_ok = m_own < p.M;
+    uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_buf);
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(taddr0 + c0, acc);
+        uint4 rcur[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
+        if (c0 + 32 < BLOCK_N) fetch_res(c0 + 32);
+        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);  // same address in every lane: L1 broadcast
+        float4 bv[8];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) bv[g] = __ldg(bias4 + g);
+        ptx::tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N) {
+            // last TMEM read of this accumulator stage: hand it back to the MMA warp early
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
+        }
+        if (p.debug & 1) continue;
+        // row-major phase (lane = pixel row): bias + LeakyReLU in fp32
+        float v[32];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + bv[g].x;
+            v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + bv[g].y;
+            v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + bv[g].z;
+            v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + bv[g].w;
+        }
+        if (p.act) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
+        }
+        if (p.out_fp32) {
+            // head tensors (3 small layers): fp32 rows straight from the row-major phase
+            if (own_ok) {
+                float* op = reinterpret_cast<float*>(p.out) + m_own * p.out_pitch + n0 + c0;
+#pragma unroll
+                for (int g = 0; g < 8; ++g)
+                    if (n0 + c0 + 4 * g < p.n_store_limit)
+                        *reinterpret_cast<float4*>(op + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+            }
+            continue;
+        }
+        // stage the bf16 row (64 B = 4 x 16 B) swizzled: chunk c of row r sits at slot c ^ ((r >> 1) & 3), which makes
+        // both this write (8 consecutive rows per quarter-warp) and the transposed read below bank-conflict free
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            *reinterpret_cast<uint4*>(stage16 + lane * 32 + ((c ^ ((lane >> 1) & 3)) << 3)) =
+                make_uint4(pack_bf16(v[8 * c + 0], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
+                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+        __syncwarp();
+        // transposed phase: 4 lanes cover the 64 contiguous bytes of one pixel row -> coalesced residual add + store
+        const int ch = n0 + c0 + 8 * j;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int r = 8 * i + sub;
+            uint4 q = *reinterpret_cast<const uint4*>(stage16 + r * 32 + ((j ^ ((r >> 1) & 3)) << 3));
+            if (has_res) {
+                // (the branch value was rounded to bf16 once above; it is ~0.3x the stream it is added to, so the
+                // extra rounding is well below the rounding of the sum)
+                const uint4 rr = rcur[i];
+                q.x = pack_bf16(bf16_lo(q.x) + bf16_lo(rr.x), bf16_hi(q.x) + bf16_hi(rr.x));
+                q.y = pack_bf16(bf16_lo(q.y) + bf16_lo(rr.y), bf16_hi(q.y) + bf16_hi(rr.y));
+                q.z = pack_bf16(bf16_lo(q.z) + bf16_lo(rr.z), bf16_hi(q.z) + bf16_hi(rr.z));
+                q.w = pack_bf16(bf16_lo(q.w) + bf16_lo(rr.w), bf16_hi(q.w) + bf16_hi(rr.w));
+            }
+            if (!ok[i] || ch >= p.n_store_limit) continue;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.out_pitch + ch;
+            *reinterpret_cast<uint4*>(op) = q;
+            if (p.upsample2x) {  // the other three pixels of the 2x2 nearest-neighbour block
+                const long long w2p = 2LL * p.wo * p.out_pitch;
+                *reinterpret_cast<uint4*>(op + p.out_pitch) = q;
+                *reinterpret_cast<uint4*>(op + w2p) = q;
+                *reinterpret_cast<uint4*>(op + w2p + p.out_pitch) = q;
+            }
+        }
+        __syncwarp();  // staging tile is rewritten by the next chunk
+    }
+}
+
+template <int KS, bool TWO>
+__device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc0) {
+#pragma unroll
+    for (int k = 0; k < KS; ++k) {
+        if (TWO) ptx::umma2_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
+        else ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
+    }
+}
+
+// TWO = false: one CTA per 128 x BLOCK_N tile (tcgen05 cta_group::1).
+// TWO = true : a cluster of two CTAs (one TPC) per 256 x 256 tile (cta_group::2): CTA r owns output rows
+//              [128r, 128r+128) and stages B rows [128r, 128r+128); the leader (rank 0) issues the MMAs, which
+//              read both CTAs' shared memory.  Per SM and K block this needs 16 KB of A + 16 KB of B instead of
+//              16 + 32 KB, which is what the L2->SM fill latency x shared-memory capacity product can sustain.
+template <int BLOCK_N, bool TWO>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
     using Cfg = TileCfg<BLOCK_N>;
-    constexpr int STAGES = Cfg::STAGES;
+    static_assert(!TWO || BLOCK_N == 256, "the CTA-pair kernel is built for 256-wide tiles");
+    constexpr int B_ROWS = TWO ? BLOCK_N / 2 : BLOCK_N;  // B rows this CTA stages per K block
+    const int STAGES = p.num_stages;
 
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* sA = smem;
-    uint8_t* sB = smem + STAGES * A_STAGE_BYTES;
-    float* sBias = reinterpret_cast<float*>(sB + STAGES * Cfg::B_STAGE_BYTES);
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sBias) + Cfg::BIAS_BYTES);
-    uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tmem_full_bar = empty_bar + STAGES;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+    uint64_t* empty_bar = full_bar + MAX_STAGES;
+    uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+    uint8_t* ring = smem + SMEM_RING_OFF;
+    const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
+    const uint32_t b_bytes = B_ROWS * p.block_k * 2;
+    const uint32_t stage_bytes = a_bytes + b_bytes;  // both multiples of 1024
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // TWO: m tiles are 256 rows
+    const uint32_t cta_rank = TWO ? ptx::cluster_ctarank() : 0u;
+    const int unit = TWO ? (blockIdx.x >> 1) : blockIdx.x;          // tile-stream index of this CTA (pair)
+    const int units = TWO ? (gridDim.x >> 1) : gridDim.x;
 
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmA);
@@ -74,203 +231,174 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], 4);  // one arrive per epilogue warp
+            ptx::mbar_init(&tmem_empty_bar[i], TWO ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
         }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
-        ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        ptx::tmem_relinquish();
+        if (TWO) { ptx::tmem_alloc2(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish2(); }
+        else { ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS); ptx::tmem_relinquish(); }
     }
     ptx::tc_fence_before();
-    __syncthreads();
+    if (TWO) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
-    const uint32_t b_bytes = BLOCK_N * p.block_k * 2;
+    // Everything the single-thread producer / MMA loops need is copied into registers first: the inline-asm
+    // "memory" clobbers would otherwise make the compiler re-read every p.* field from the constant bank on each
+    // k-block, and integer divisions per k-block put ~700 dependent cycles in the producer's way (measured).
+    const uint32_t bar_base = ptx::smem_u32(full_bar);       // full[i] at +8i, empty[i] at +8(MAX_STAGES+i)
+    const uint32_t ring_base = ptx::smem_u32(ring);
+    const uint32_t tmem_full_addr = ptx::smem_u32(tmem_full_bar), tmem_empty_addr = ptx::smem_u32(tmem_empty_bar);
+    const int nkb = p.num_k_blocks, cin_blocks = p.cin_blocks, ksize = p.ksize, block_k = p.block_k;
+    const int n_tiles_n = p.num_n_tiles;
+    const bool prof = p.prof != nullptr;
+    constexpr int TILE_M = TWO ? 2 * BLOCK_M : BLOCK_M;
 
-    if (warp == 0 && lane == 0) {
-        // ------------------------------------------------------------------ TMA producer
+    if (warp == 0) {
+        // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
+        // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
+        // registers); one elected lane issues.
+        const bool issuer = ptx::elect_one();
+        const bool im2col = p.a_im2col != 0, load_a = !(p.debug & 2);
+        const int ho_wo = p.ho * p.wo, wo = p.wo, cstride = p.stride, pad = p.pad_lo;
+        const uint32_t tx_bytes = ((load_a ? a_bytes : 0u) + b_bytes) * (TWO ? 2u : 1u);
+        const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
         int stage = 0;
         uint32_t phase = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
-            const int m0 = m_tile * BLOCK_M;
-            const int n0 = n_tile * BLOCK_N;
+        long long t_wait = 0, t_start = clock64();
+        for (int tile = unit; tile < num_tiles && !(p.debug & 8); tile += units) {
+            const int m_tile = tile / n_tiles_n;
+            const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS * (TWO ? 1 : 0);
+            const int m0 = m_tile * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
             int img = 0, base_w = 0, base_h = 0;
-            if (p.a_im2col) {
-                const int hw = p.ho * p.wo;
-                img = m0 / hw;
-                const int rem = m0 - img * hw;
-                const int oy = rem / p.wo;
-                const int ox = rem - oy * p.wo;
-                base_w = ox * p.stride - p.pad_lo;
-                base_h = oy * p.stride - p.pad_lo;
+            if (im2col) {
+                img = m0 / ho_wo;
+                const int rem = m0 - img * ho_wo;
+                const int oy = rem / wo;
+                base_w = (rem - oy * wo) * cstride - pad;
+                base_h = oy * cstride - pad;
             }
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-                ptx::mbar_arrive_expect_tx(&full_bar[stage], a_bytes + b_bytes);
-                const int tap = kb / p.cin_blocks;
-                const int cb = kb - tap * p.cin_blocks;
-                if (p.a_im2col) {
-                    const int r = tap / p.ksize;
-                    const int s = tap - r * p.ksize;
-                    ptx::tma_load_im2col_4d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cb * p.block_k,
-                                            base_w, base_h, img, static_cast<uint16_t>(s),
-                                            static_cast<uint16_t>(r));
+            int cb = 0, tap_s = 0, tap_r = 0, kcoord = 0;
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t full_addr = bar_base + 8u * stage;
+                const uint32_t dst = ring_base + stage * stage_bytes;
+                const long long tw0 = prof ? clock64() : 0;
+                ptx::mbar_wait_addr(full_addr + 8u * MAX_STAGES, phase ^ 1);
+                if (prof) t_wait += clock64() - tw0;
+                if (!issuer) {
+                } else if (TWO) {
+                    // transaction bytes of both CTAs land on the leader's barrier; only the leader arms it
+                    if (cta_rank == 0) ptx::mbar_arrive_expect_tx_addr(full_addr, tx_bytes);
+                    const uint32_t lead_bar = full_addr & ptx::kPeerBitMask;
+                    if (load_a) {
+                        if (im2col)
+                            ptx::tma2_load_im2col_4d_addr(dst, mapA, lead_bar, cb * block_k, base_w, base_h, img,
+                                                          static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
+                        else
+                            ptx::tma2_load_2d_addr(dst, mapA, lead_bar, cb * block_k, m0);
+                    }
+                    ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
                 } else {
-                    ptx::tma_load_2d(sA + stage * A_STAGE_BYTES, &tmA, &full_bar[stage], cb * p.block_k, m0);
+                    ptx::mbar_arrive_expect_tx_addr(full_addr, tx_bytes);
+                    if (load_a) {
+                        if (im2col)
+                            ptx::tma_load_im2col_4d_addr(dst, mapA, full_addr, cb * block_k, base_w, base_h, img,
+                                                         static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
+                        else
+                            ptx::tma_load_2d_addr(dst, mapA, full_addr, cb * block_k, m0);
+                    }
+                    ptx::tma_load_2d_addr(dst + a_bytes, mapB, full_addr, kcoord, n0);
                 }
-                ptx::tma_load_2d(sB + stage * Cfg::B_STAGE_BYTES, &tmB, &full_bar[stage], kb * p.block_k, n0);
+                kcoord += block_k;
+                if (++cb == cin_blocks) {
+                    cb = 0;
+                    if (++tap_s == ksize) { tap_s = 0; ++tap_r; }
+                }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-    } else if (warp == 1 && lane == 0) {
-        // ------------------------------------------------------------------ MMA issuer
-        const uint32_t idesc = ptx::make_idesc_bf16_f32(BLOCK_M, BLOCK_N);
+        if (prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = clock64() - t_start; p.prof[blockIdx.x * 8 + 1] = t_wait; }
+    } else if (warp == 1 && cta_rank == 0) {
+        // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+        const uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_M, BLOCK_N);
         // swizzle span = one K block: 128 B (block_k 64), 64 B (32) or 32 B (16)
-        const uint32_t layout = (p.block_k == 64) ? 2u : (p.block_k == 32 ? 4u : 6u);
-        const uint32_t sbo = 16u * p.block_k;                       // 8 rows x swizzle span
-        const int k_steps = p.block_k / 16;
+        const uint32_t layout = (block_k == 64) ? 2u : (block_k == 32 ? 4u : 6u);
+        const uint32_t sbo = 16u * block_k;  // 8 rows x swizzle span
+        const int k_steps = (p.debug & 4) ? 0 : block_k / 16;
+        const uint64_t desc0 = ptx::make_kmajor_desc(ring_base, sbo, layout);  // stage 0, A operand
+        const uint32_t stage_units = stage_bytes >> 4, a_units = a_bytes >> 4;
+        const bool issuer = ptx::elect_one();
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
+        long long t_full = 0, t_tmem = 0, t_start = clock64();
+        for (int tile = unit; tile < num_tiles; tile += units, ++it) {
             const int as = it & 1;
             const uint32_t aphase = (it >> 1) & 1;
-            ptx::mbar_wait(&tmem_empty_bar[as], aphase ^ 1);
+            const long long tq0 = prof ? clock64() : 0;
+            ptx::mbar_wait_addr(tmem_empty_addr + 8u * as, aphase ^ 1);
+            if (prof) t_tmem += clock64() - tq0;
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-            for (int kb = 0; kb < p.num_k_blocks; ++kb) {
-                ptx::mbar_wait(&full_bar[stage], phase);
+            for (int kb = 0; kb < nkb; ++kb) {
+                const uint32_t full_addr = bar_base + 8u * stage;
+                const long long tf0 = prof ? clock64() : 0;
+                if (!(p.debug & 8)) ptx::mbar_wait_addr(full_addr, phase);  // debug 8: MMA-only (operands = whatever is in smem)
+                if (prof) t_full += clock64() - tf0;
                 ptx::tc_fence_after();
-                const uint64_t adesc =
-                    ptx::make_kmajor_desc(ptx::smem_u32(sA + stage * A_STAGE_BYTES), sbo, layout);
-                const uint64_t bdesc =
-                    ptx::make_kmajor_desc(ptx::smem_u32(sB + stage * Cfg::B_STAGE_BYTES), sbo, layout);
-                for (int k = 0; k < k_steps; ++k) {
-                    // advance 16 elements (32 B) along K inside the swizzle span: +2 in 16-byte units
-                    ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0);
+                const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * stage_units);
+                const uint64_t bdesc = adesc + a_units;
+                if (issuer) {
+                    // 16 elements (32 B) along K inside the swizzle span per MMA: +2 in 16-byte units.  Unrolled with
+                    // compile-time counts so the descriptor arithmetic of the four MMAs overlaps instead of forming a
+                    // serial chain in front of every tcgen05.mma (measured: ~200 cycles per MMA with a runtime loop).
+                    if (k_steps == 4) issue_mmas<4, TWO>(tmem_d, adesc, bdesc, idesc, kb != 0);
+                    else if (k_steps == 2) issue_mmas<2, TWO>(tmem_d, adesc, bdesc, idesc, kb != 0);
+                    else if (k_steps == 1) issue_mmas<1, TWO>(tmem_d, adesc, bdesc, idesc, kb != 0);
+                    // smem slot free (in both CTAs) once these MMAs retire
+                    if (p.debug & 16) {
+                    } else if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
+                    else ptx::umma_commit_addr(full_addr + 8u * MAX_STAGES);
                 }
-                ptx::umma_commit(&empty_bar[stage]);  // smem slot free once these MMAs retire
+                __syncwarp();
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            ptx::umma_commit(&tmem_full_bar[as]);  // accumulator complete
+            // accumulator complete (each CTA of a pair drains its own 128 rows)
+            if (issuer) {
+                if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, 3);
+                else ptx::umma_commit_addr(tmem_full_addr + 8u * as);
+            }
+            __syncwarp();
         }
+        if (prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = clock64() - t_start; p.prof[blockIdx.x * 8 + 3] = t_full; p.prof[blockIdx.x * 8 + 4] = t_tmem; }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
-        const int quarter = warp & 3;
-        const int et = threadIdx.x - 128;  // 0..127 within the epilogue group
-        const int row_in_tile = quarter * 32 + lane;
-        const int hw = p.ho * p.wo;
-        int it = 0;
-        for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
-            const int as = it & 1;
+        const int group = (warp - 4) >> 2;  // which accumulator stage / tile parity this warp serves
+        const int quarter = warp & 3;       // TMEM lanes [32*quarter, 32*quarter + 32)
+        float* stage_buf = reinterpret_cast<float*>(smem + SMEM_STAGING_OFF + (warp - 4) * 4096);
+        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * BLOCK_N;
+        // the MMA issuer that waits for "accumulator drained" lives in the leader CTA
+        const uint32_t empty_addr = (tmem_empty_addr + 8u * group) & (TWO ? ptx::kPeerBitMask : 0xFFFFFFFFu);
+        int it = group;
+        long long t_acc = 0, t_start = clock64();
+        for (int tile = unit + group * units; tile < num_tiles; tile += 2 * units, it += 2) {
             const uint32_t aphase = (it >> 1) & 1;
-            const int m_tile = tile / p.num_n_tiles;
-            const int n_tile = tile - m_tile * p.num_n_tiles;
-            const int n0 = n_tile * BLOCK_N;
-            const long long m = static_cast<long long>(m_tile) * BLOCK_M + row_in_tile;
-            const bool row_ok = m < p.M;
-
-            // stage this tile's bias slice (buffer `as`; its previous reader finished two tiles ago,
-            // and every epilogue thread passes the named barrier below once per tile)
-            float* bias_s = sBias + as * BLOCK_N;
-            for (int i = et; i < BLOCK_N; i += 128) bias_s[i] = __ldg(p.bias + n0 + i);
-            asm volatile("bar.sync 1, 128;" ::: "memory");
-
-            ptx::mbar_wait(&tmem_full_bar[as], aphase);
-            ptx::tc_fence_after();
-
-            long long out_row[4];
-            int n_dst = 1;
-            if (p.upsample2x) {
-                const int img = static_cast<int>(m / hw);
-                const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
-                const int oy = rem / p.wo;
-                const int ox = rem - oy * p.wo;
-                const long long w2 = 2LL * p.wo;
-                const long long r0 = (static_cast<long long>(img) * 2 * p.ho + 2 * oy) * w2 + 2 * ox;
-                out_row[0] = r0;
-                out_row[1] = r0 + 1;
-                out_row[2] = r0 + w2;
-                out_row[3] = r0 + w2 + 1;
-                n_dst = 4;
-            } else {
-                out_row[0] = m;
-            }
-
-#pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                uint32_t acc[32];
-                const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + as * BLOCK_N + c0;
-                ptx::tmem_ld_32x32(taddr, acc);
-                ptx::tmem_ld_wait();
-                if (c0 + 32 >= BLOCK_N) {
-                    // last TMEM read of this accumulator stage: hand it back to the MMA warp early
-                    ptx::tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) ptx::mbar_arrive(&tmem_empty_bar[as]);
-                }
-                const int nbase = n0 + c0;
-                if (!row_ok || nbase >= p.n_store_limit) continue;
-                float v[32];
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(acc[j]) + bias_s[c0 + j];
-                    if (p.act) x = x > 0.f ? x : x * p.alpha;
-                    v[j] = x;
-                }
-                if (p.residual != nullptr) {
-                    const __nv_bfloat16* rp = p.residual + m * p.res_pitch + nbase;
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        if (nbase + g * 8 < p.cout) {
-                            const uint4 r = __ldg(reinterpret_cast<const uint4*>(rp + g * 8));
-                            v[g * 8 + 0] += bf16_lo(r.x); v[g * 8 + 1] += bf16_hi(r.x);
-                            v[g * 8 + 2] += bf16_lo(r.y); v[g * 8 + 3] += bf16_hi(r.y);
-                            v[g * 8 + 4] += bf16_lo(r.z); v[g * 8 + 5] += bf16_hi(r.z);
-                            v[g * 8 + 6] += bf16_lo(r.w); v[g * 8 + 7] += bf16_hi(r.w);
-                        }
-                    }
-                }
-                if (p.out_fp32) {
-                    float* op = reinterpret_cast<float*>(p.out) + out_row[0] * p.out_pitch + nbase;
-#pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        if (nbase + g * 4 < p.n_store_limit)
-                            *reinterpret_cast<float4*>(op + g * 4) =
-                                make_float4(v[g * 4], v[g * 4 + 1], v[g * 4 + 2], v[g * 4 + 3]);
-                    }
-                } else {
-                    uint4 q[4];
-#pragma unroll
-                    for (int g = 0; g < 4; ++g) {
-                        q[g].x = pack_bf16(v[g * 8 + 0], v[g * 8 + 1]);
-                        q[g].y = pack_bf16(v[g * 8 + 2], v[g * 8 + 3]);
-                        q[g].z = pack_bf16(v[g * 8 + 4], v[g * 8 + 5]);
-                        q[g].w = pack_bf16(v[g * 8 + 6], v[g * 8 + 7]);
-                    }
-                    for (int d = 0; d < n_dst; ++d) {
-                        __nv_bfloat16* op =
-                            reinterpret_cast<__nv_bfloat16*>(p.out) + out_row[d] * p.out_pitch + nbase;
-#pragma unroll
-                        for (int g = 0; g < 4; ++g) {
-                            if (nbase + g * 8 < p.n_store_limit) *reinterpret_cast<uint4*>(op + g * 8) = q[g];
-                        }
-                    }
-                }
-            }
+            const int m_tile = tile / n_tiles_n;
+            const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
+            const long long m_base = static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
+            epilogue_tile<BLOCK_N>(p, taddr0, stage_buf, m_base, n0, lane, tmem_full_addr + 8u * group, aphase, empty_addr,
+                                   prof ? &t_acc : nullptr);
         }
+        if (prof && warp == 4 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = clock64() - t_start; p.prof[blockIdx.x * 8 + 6] = t_acc; }
     }
 
     ptx::tc_fence_before();
-    __syncthreads();
+    if (TWO) ptx::cluster_sync(); else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (TWO) ptx::tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
@@ -293,10 +421,9 @@ void set_err(char* err, size_t n, const char* fmt, long long a = 0, long long b 
     if (err && n) snprintf(err, n, fmt, a, b, c);
 }
 
-template <int BN>
+template <int BN, bool TWO>
 int set_smem_attr() {
-    return cudaFuncSetAttribute(conv_tc_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                static_cast<int>(TileCfg<BN>::SMEM_BYTES)) == cudaSuccess
+    return cudaFuncSetAttribute(conv_tc_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess
                ? 0
                : -1;
 }
@@ -320,7 +447,8 @@ int conv_tc_init(char* err, size_t errlen) {
         g_encodeIm2col = reinterpret_cast<PFN_encodeIm2col>(f);
         cudaDriverGetVersion(&g_driver_version);
     }
-    if (set_smem_attr<32>() || set_smem_attr<64>() || set_smem_attr<128>() || set_smem_attr<256>()) {
+    if (set_smem_attr<32, false>() || set_smem_attr<64, false>() || set_smem_attr<128, false>() ||
+        set_smem_attr<256, false>() || set_smem_attr<256, true>()) {
         set_err(err, errlen, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %lld",
                 static_cast<long long>(cudaGetLastError()));
         return -1;
@@ -362,10 +490,16 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     const int block_k = (d.cin % 64 == 0) ? 64 : (d.cin % 32 == 0 ? 32 : 16);
     const int cin_blocks = d.cin / block_k;
     const int K = k * k * d.cin;
-    const long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    int two = -1;  // -1: decide below
+    if (block_n_hint == 512) { two = 1; block_n_hint = 256; }
+    if (block_n_hint == 257) { two = 0; block_n_hint = 256; }
     int bn = block_n_hint ? block_n_hint : choose_block_n(d.cout, m_tiles, num_sms);
     if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256)) { set_err(err, errlen, "conv_tc: bad block_n %lld", bn); return -1; }
 
+    if (two < 0) two = (bn == 256 && block_k == 64 && m_tiles >= 2 && !getenv("FASTDET_NO_2CTA")) ? 1 : 0;
+    if (two && (bn != 256 || block_k != 64)) { set_err(err, errlen, "conv_tc: the CTA-pair kernel needs Cout > 128 and Cin %% 64 == 0"); return -1; }
+    if (two) m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
     ConvParams& p = L->p;
     p.M = static_cast<int>(M);
     p.cout = d.cout;
@@ -426,7 +560,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.cout)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(bn)};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(two ? bn / 2 : bn)};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -434,22 +568,47 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map B encode failed (CUresult %lld)", r); return -1; }
     }
     L->block_n = bn;
+    L->two_cta = two;
     const long long tiles = m_tiles * p.num_n_tiles;
-    L->grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
-    L->smem_bytes = bn == 32 ? TileCfg<32>::SMEM_BYTES
-                  : bn == 64 ? TileCfg<64>::SMEM_BYTES
-                  : bn == 128 ? TileCfg<128>::SMEM_BYTES : TileCfg<256>::SMEM_BYTES;
+    if (two) {
+        const long long pairs = num_sms / 2;
+        L->grid = 2 * static_cast<int>(tiles < pairs ? tiles : pairs);
+    } else {
+        L->grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
+    }
+    // operand ring: as many stages as fit (bytes in flight, not stage count, is what hides the ~1.5 us TMA latency)
+    const int stage_bytes = (BLOCK_M + (two ? bn / 2 : bn)) * block_k * 2;
+    int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF) / stage_bytes;
+    if (stages > MAX_STAGES) stages = MAX_STAGES;
+    if (stages < 2) { set_err(err, errlen, "conv_tc: stage does not fit in shared memory"); return -1; }
+    p.num_stages = stages;
+    L->smem_bytes = 1024 + SMEM_RING_OFF + static_cast<size_t>(stages) * stage_bytes;
     L->flops = 2.0 * double(M) * d.cout * K;
     return 0;
 }
 
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
     dim3 grid(L.grid), block(NUM_THREADS);
+    if (L.two_cta) {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = grid;
+        cfg.blockDim = block;
+        cfg.dynamicSmemBytes = L.smem_bytes;
+        cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2;
+        attr[0].val.clusterDim.y = 1;
+        attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, L.tmA, L.tmB, L.p) == cudaSuccess ? 0 : -1;
+    }
     switch (L.block_n) {
-        case 32: conv_tc_kernel<32><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
-        case 64: conv_tc_kernel<64><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
-        case 128: conv_tc_kernel<128><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
-        case 256: conv_tc_kernel<256><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
+        case 32: conv_tc_kernel<32, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
+        case 64: conv_tc_kernel<64, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
+        case 128: conv_tc_kernel<128, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
+        case 256: conv_tc_kernel<256, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
         default: return -1;
     }
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

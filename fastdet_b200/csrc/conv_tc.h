@@ -40,6 +40,7 @@ struct ConvParams {
     int block_k;  // 64 (SWIZZLE_128B), 32 (SWIZZLE_64B) or 16 (SWIZZLE_32B)
     int a_im2col; // 0: A via 2D tiled map (1x1 s1), 1: via im2col map
     int num_m_tiles, num_n_tiles;
+    int num_stages;  // depth of the shared-memory operand ring
     const float* bias;
     int act;
     float alpha;
@@ -49,18 +50,22 @@ struct ConvParams {
     long long out_pitch;
     int out_fp32, upsample2x;
     int n_store_limit;
+    long long* prof;  // developer: per-CTA cycle counters [grid][8] (null in production)
+    int debug;  // developer switches (0 in production): 1 skip epilogue stores, 2 skip A loads, 4 skip MMA issue
 };
 
 struct ConvLaunch {
     CUtensorMap tmA, tmB;
     ConvParams p;
     int block_n;
+    int two_cta;  // 1: CTA-pair kernel (cta_group::2, 256 x 256 tiles)
     int grid;
     size_t smem_bytes;
     double flops;  // algorithmic: 2*M*cout*K
 };
 
-// Builds tensor maps + launch geometry.  block_n_hint: 0 = choose, else one of 32/64/128/256.
+// Builds tensor maps + launch geometry.  block_n_hint: 0 = choose, else one of 32/64/128/256;
+// 512 = force the CTA-pair kernel, 257 = force the single-CTA 256-wide kernel.
 // Returns 0 on success; on failure writes a message to err (if non-null).
 int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* out, char* err, size_t errlen);
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);

@@ -144,8 +144,8 @@ static int run_case(const Case& c, int num_sms) {
             for (int ch = c.cout; ch < out_pitch; ++ch)
                 if (o[row * out_pitch + ch] != 0xFFFF) ++clobbered;
     }
-    printf("[%-28s] M=%lld N=%d K=%d bn=%d grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
-           c.name, M, c.cout, K, L.block_n, L.grid, max_err, max_ref, bad, clobbered,
+    printf("[%-28s] M=%lld N=%d K=%d bn=%d%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
+           c.name, M, c.cout, K, L.block_n, L.two_cta ? "x2" : "", L.grid, max_err, max_ref, bad, clobbered,
            (bad == 0 && clobbered == 0) ? "OK" : "FAIL");
     if (bad) printf("    first bad at m=%lld n=%d\n", first_bad_m, first_bad_n);
     cudaFree(dx); cudaFree(dw); cudaFree(dbias); cudaFree(dout);
@@ -154,7 +154,7 @@ static int run_case(const Case& c, int num_sms) {
 }
 
 static void time_case(const char* name, int n, int h, int cin, int cout, int k, int stride, int num_sms,
-                      int block_n) {
+                      int block_n, int debug = 0, int residual = 0, int grid_limit = 0) {
     const int pad = k == 3 ? 1 : 0;
     ConvDesc d;
     memset(&d, 0, sizeof(d));
@@ -175,7 +175,11 @@ static void time_case(const char* name, int n, int h, int cin, int cout, int k, 
     d.out = dout; d.out_pitch = cout;
     ConvLaunch L;
     char err[256] = {0};
+    __nv_bfloat16* dres = nullptr;
+    if (residual) { CK(cudaMalloc(&dres, out_e * 2)); CK(cudaMemset(dres, 0x3C, out_e * 2)); d.residual = dres; d.res_pitch = cout; }
     if (conv_tc_prepare(d, num_sms, block_n, &L, err, sizeof(err))) { printf("[%s] prepare failed: %s\n", name, err); return; }
+    L.p.debug = debug;
+    if (grid_limit && grid_limit < L.grid) L.grid = grid_limit;
     cudaEvent_t e0, e1;
     cudaEventCreate(&e0); cudaEventCreate(&e1);
     for (int i = 0; i < 3; ++i) conv_tc_launch(L, 0);
@@ -189,8 +193,21 @@ static void time_case(const char* name, int n, int h, int cin, int cout, int k, 
     cudaEventElapsedTime(&ms, e0, e1);
     ms /= iters;
     const double bytes = (in_e + out_e + w_e) * 2.0;
-    printf("[time %-24s] bn=%3d tiles=%6d  %.3f ms  %.1f TFLOP/s  %.0f GB/s(min traffic)\n", name, L.block_n,
-           L.p.num_m_tiles * L.p.num_n_tiles, ms, L.flops / ms * 1e-9, bytes / ms * 1e-6);
+    if (getenv("FD_PROF")) {
+        long long* dprof; CK(cudaMalloc(&dprof, 8 * 8 * 256)); CK(cudaMemset(dprof, 0, 8 * 8 * 256));
+        L.p.prof = dprof;
+        conv_tc_launch(L, 0); CK(cudaDeviceSynchronize());
+        long long hp[8 * 256]; CK(cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost));
+        double a[8] = {0};
+        for (int c = 0; c < L.grid; ++c) for (int q = 0; q < 8; ++q) a[q] += double(hp[c * 8 + q]) / L.grid;
+        const double tiles_per_cta = double(L.p.num_m_tiles) * L.p.num_n_tiles / L.grid;
+        printf("    prof(avg cycles/CTA, %.1f tiles x %d kb): producer total %.0f wait-empty %.0f | mma total %.0f wait-full %.0f wait-tmem %.0f | epi(g0) total %.0f wait-acc %.0f | per kb: %.0f cyc\n",
+               tiles_per_cta, L.p.num_k_blocks, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[2] / (tiles_per_cta * L.p.num_k_blocks));
+        L.p.prof = nullptr; cudaFree(dprof);
+    }
+    if (dres) cudaFree(dres);
+    printf("[time %-24s dbg=%d res=%d grid=%3d] bn=%3d tiles=%6d  %.3f ms  %.1f TFLOP/s (%.2f per CTA)  %.0f GB/s(min traffic)\n", name, debug, residual, L.grid, L.block_n,
+           L.p.num_m_tiles * L.p.num_n_tiles, ms, L.flops / ms * 1e-9, L.flops / ms * 1e-9 / L.grid, bytes / ms * 1e-6);
     cudaFree(dx); cudaFree(dw); cudaFree(dout); cudaFree(dbias);
 }
 
@@ -224,11 +241,53 @@ int main(int argc, char** argv) {
             {"3x3 64->32 pitch+32",     1, 19, 19, 64, 32, 3, 1, 1, 1, 1, 0, 0, 0, 32, 0},
             {"1x1 512->256 many tiles", 8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 0, 0, 0, 0, 64},
             {"3x3 tiny map 64->64",     1, 5, 5, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"2cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 512},
+            {"2cta 3x3 64->256 res s2", 3, 26, 26, 64, 256, 3, 2, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"2cta 1x1 256->255 fp32",  2, 13, 13, 256, 255, 1, 1, 0, 0, 0, 0, 1, 0, 0, 512},
+            {"2cta 1x1 512->256 many",  8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 1, 0, 0, 0, 512},
+            {"2cta 1x1 256->256 up",    2, 13, 13, 256, 256, 1, 1, 0, 0, 1, 0, 0, 1, 64, 512},
+            {"2cta 3x3 128->256 big",   16, 52, 52, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"1cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 257},
             {"3x3 16->32 s1 (bk16)",    2, 20, 20, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
             {"1x1 48->64 (bk16)",       1, 20, 20, 48, 64, 1, 1, 0, 0, 1, 0, 0, 0, 16, 0},
         };
         for (const Case& c : cases) fails += run_case(c, sms);
         printf("check: %d failing case(s)\n", fails);
+    }
+    if (!strcmp(mode, "mma")) {
+        for (int bn : {257, 512})
+            for (int dbg : {0, 1, 9, 25}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, bn, dbg);
+        for (int dbg : {0, 9, 25}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, dbg);
+        for (int dbg : {0, 9, 25}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, dbg);
+    }
+    if (!strcmp(mode, "two")) {
+        for (int bn : {257, 512}) {
+            time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, bn);
+            time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, bn, 0, 1);
+            time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, bn);
+            time_case("3x3 512->1024 @13 bs64", 64, 13, 512, 1024, 3, 1, sms, bn);
+            time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, bn);
+            time_case("1x1 1024->512 @13 bs64", 64, 13, 1024, 512, 1, 1, sms, bn);
+            time_case("3x3 256->512 s2 @52 bs64", 64, 52, 256, 512, 3, 2, sms, bn);
+        }
+    }
+    if (!strcmp(mode, "grid")) {
+        for (int g : {148, 111, 74, 37, 16}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, 0, 0, g);
+        for (int g : {148, 74, 37}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, 1, 0, g);
+        for (int g : {148, 74, 37}) time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, 0, 0, 0, g);
+        for (int g : {148, 74, 37}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, 0, 0, g);
+        for (int g : {148, 74, 37}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, 7, 0, g);
+        for (int g : {148, 74, 37}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, 0, 0, g);
+        for (int g : {148, 74, 37}) time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0, 0, 0, g);
+    }
+    if (!strcmp(mode, "probe")) {
+        for (int dbg : {0, 1, 2, 4, 3, 5, 6, 7}) time_case("3x3 32->64 s2 @416 bs64", 64, 416, 32, 64, 3, 2, sms, 0, dbg);
+        for (int dbg : {0, 1, 2, 4}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, dbg);
+        for (int dbg : {0, 1, 2, 4}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, dbg);
+        for (int dbg : {0, 1, 2, 4}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, dbg);
+        for (int dbg : {0, 1}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, dbg, 1);
+        for (int dbg : {0, 1, 2, 4}) time_case("1x1 1024->512 @13 bs64", 64, 13, 1024, 512, 1, 1, sms, 0, dbg);
+        for (int dbg : {0, 1, 2, 4}) time_case("1x1 64->32 @208 bs64", 64, 208, 64, 32, 1, 1, sms, 0, dbg);
     }
     if (!strcmp(mode, "time") || !strcmp(mode, "all")) {
         time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0);

@@ -14,6 +14,15 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
 
+// 16-byte read-only load that does not allocate in L1 (streamed once: residual tiles)
+__device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p));
+    return r;
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
@@ -43,17 +52,102 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
     return ok != 0;
 }
 // Bounded wait: a protocol bug must surface as a launch failure (trap), never as a hung GPU.
-#ifndef FD_MBAR_SPIN_LIMIT
-#define FD_MBAR_SPIN_LIMIT (1u << 26)
+#ifndef FD_MBAR_TIMEOUT_CYCLES
+#define FD_MBAR_TIMEOUT_CYCLES 4000000000LL  // ~2 s at 1.9 GHz
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > FD_MBAR_SPIN_LIMIT) __trap();
+        if (clock64() - t0 > FD_MBAR_TIMEOUT_CYCLES) __trap();
     }
 }
 
+// Variants taking raw shared-space addresses (no generic->shared conversion in single-thread hot loops).
+__device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait_addr(uint32_t bar, uint32_t parity) {
+    if (mbar_try_wait_addr(bar, parity)) return;
+    const long long t0 = clock64();
+    while (!mbar_try_wait_addr(bar, parity)) {
+        if (clock64() - t0 > FD_MBAR_TIMEOUT_CYCLES) __trap();
+    }
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx_addr(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+
+// true in exactly one lane of a fully active warp
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(pred));
+    return pred != 0;
+}
+
+// ---------------------------------------------------------------- clusters / CTA pairs
+// In the shared::cluster window of a CTA pair, bit 24 of a shared address selects the CTA; clearing it addresses
+// the same offset in the pair's leader (even) CTA.
+static constexpr uint32_t kPeerBitMask = 0xFEFFFFFFu;
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on an mbarrier given by a shared::cluster address (own CTA or the pair's leader)
+__device__ __forceinline__ void mbar_arrive_cluster_addr(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
+// CTA-pair loads: data lands in the issuing CTA's shared memory, the transaction bytes on `bar`, which may be the
+// leader CTA's barrier.
+__device__ __forceinline__ void tma2_load_2d_addr(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma2_load_im2col_4d_addr(uint32_t dst, uint64_t map, uint32_t bar, int c, int w, int h,
+                                                         int n, uint16_t ow, uint16_t oh) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.im2col.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_addr(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::
+            "r"(dst),
+        "l"(map), "r"(bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_addr(uint32_t dst, uint64_t map, uint32_t bar, int c, int w, int h,
+                                                        int n, uint16_t ow, uint16_t oh) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+        "l"(map), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n), "h"(ow), "h"(oh)
+        : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* m) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");
 }
@@ -121,6 +215,37 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                  : "memory");
+}
+// CTA-pair variants (cta_group::2): allocation is issued by the same warp of both CTAs; the MMA is issued by the
+// leader and spans both SMs; commit multicasts its arrive to the barrier at the same offset in the masked CTAs.
+__device__ __forceinline__ void tmem_alloc2(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish2() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                           uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mcast_addr(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+        "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 // Warp-collective: 32 lanes x 32 consecutive fp32 columns; lane i gets row (lane_base + i).
 __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&r)[32]) {
