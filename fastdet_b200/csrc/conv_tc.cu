@@ -21,6 +21,7 @@
 #include "ptx.cuh"
 
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 namespace fd {
@@ -211,7 +212,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint8_t* ring = smem + SMEM_RING_OFF;
     const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
     const uint32_t b_bytes = B_ROWS * p.block_k * 2;
-    const uint32_t stage_bytes = a_bytes + b_bytes;  // both multiples of 1024
+    const uint32_t sub_bytes = a_bytes + b_bytes;     // one K block: A then B, both multiples of 1024
+    const int kps = p.kb_per_stage;                   // K blocks sharing one ring stage / one barrier round
+    const uint32_t stage_bytes = sub_bytes * kps;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -280,40 +283,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 base_h = oy * cstride - pad;
             }
             int cb = 0, tap_s = 0, tap_r = 0, kcoord = 0;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; kb += kps) {
+                const int nsub = (nkb - kb < kps) ? nkb - kb : kps;
                 const uint32_t full_addr = bar_base + 8u * stage;
-                const uint32_t dst = ring_base + stage * stage_bytes;
+                const uint32_t lead_bar = TWO ? (full_addr & ptx::kPeerBitMask) : full_addr;
                 const long long tw0 = prof ? clock64() : 0;
                 ptx::mbar_wait_addr(full_addr + 8u * MAX_STAGES, phase ^ 1);
                 if (prof) t_wait += clock64() - tw0;
-                if (!issuer) {
-                } else if (TWO) {
-                    // transaction bytes of both CTAs land on the leader's barrier; only the leader arms it
-                    if (cta_rank == 0) ptx::mbar_arrive_expect_tx_addr(full_addr, tx_bytes);
-                    const uint32_t lead_bar = full_addr & ptx::kPeerBitMask;
-                    if (load_a) {
-                        if (im2col)
-                            ptx::tma2_load_im2col_4d_addr(dst, mapA, lead_bar, cb * block_k, base_w, base_h, img,
-                                                          static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
-                        else
-                            ptx::tma2_load_2d_addr(dst, mapA, lead_bar, cb * block_k, m0);
+                // transaction bytes of both CTAs of a pair land on the leader's barrier; only the leader arms it
+                if (issuer && cta_rank == 0) ptx::mbar_arrive_expect_tx_addr(full_addr, tx_bytes * nsub);
+                for (int sb = 0; sb < nsub; ++sb) {
+                    const uint32_t dst = ring_base + stage * stage_bytes + sb * sub_bytes;
+                    if (!issuer) {
+                    } else if (TWO) {
+                        if (load_a) {
+                            if (im2col)
+                                ptx::tma2_load_im2col_4d_addr(dst, mapA, lead_bar, cb * block_k, base_w, base_h, img,
+                                                              static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
+                            else
+                                ptx::tma2_load_2d_addr(dst, mapA, lead_bar, cb * block_k, m0);
+                        }
+                        ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
+                    } else {
+                        if (load_a) {
+                            if (im2col)
+                                ptx::tma_load_im2col_4d_addr(dst, mapA, full_addr, cb * block_k, base_w, base_h, img,
+                                                             static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
+                            else
+                                ptx::tma_load_2d_addr(dst, mapA, full_addr, cb * block_k, m0);
+                        }
+                        ptx::tma_load_2d_addr(dst + a_bytes, mapB, full_addr, kcoord, n0);
                     }
-                    ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
-                } else {
-                    ptx::mbar_arrive_expect_tx_addr(full_addr, tx_bytes);
-                    if (load_a) {
-                        if (im2col)
-                            ptx::tma_load_im2col_4d_addr(dst, mapA, full_addr, cb * block_k, base_w, base_h, img,
-                                                         static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
-                        else
-                            ptx::tma_load_2d_addr(dst, mapA, full_addr, cb * block_k, m0);
+                    kcoord += block_k;
+                    if (++cb == cin_blocks) {
+                        cb = 0;
+                        if (++tap_s == ksize) { tap_s = 0; ++tap_r; }
                     }
-                    ptx::tma_load_2d_addr(dst + a_bytes, mapB, full_addr, kcoord, n0);
-                }
-                kcoord += block_k;
-                if (++cb == cin_blocks) {
-                    cb = 0;
-                    if (++tap_s == ksize) { tap_s = 0; ++tap_r; }
                 }
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
@@ -327,7 +332,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t sbo = 16u * block_k;  // 8 rows x swizzle span
         const int k_steps = (p.debug & 4) ? 0 : block_k / 16;
         const uint64_t desc0 = ptx::make_kmajor_desc(ring_base, sbo, layout);  // stage 0, A operand
-        const uint32_t stage_units = stage_bytes >> 4, a_units = a_bytes >> 4;
+        const uint32_t stage_units = stage_bytes >> 4, sub_units = sub_bytes >> 4, a_units = a_bytes >> 4;
         const bool issuer = ptx::elect_one();
         int stage = 0;
         uint32_t phase = 0;
@@ -341,21 +346,25 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (prof) t_tmem += clock64() - tq0;
             ptx::tc_fence_after();
             const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-            for (int kb = 0; kb < nkb; ++kb) {
+            for (int kb = 0; kb < nkb; kb += kps) {
+                const int nsub = (nkb - kb < kps) ? nkb - kb : kps;
                 const uint32_t full_addr = bar_base + 8u * stage;
                 const long long tf0 = prof ? clock64() : 0;
                 if (!(p.debug & 8)) ptx::mbar_wait_addr(full_addr, phase);  // debug 8: MMA-only (operands = whatever is in smem)
                 if (prof) t_full += clock64() - tf0;
                 ptx::tc_fence_after();
-                const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * stage_units);
-                const uint64_t bdesc = adesc + a_units;
                 if (issuer) {
-                    // 16 elements (32 B) along K inside the swizzle span per MMA: +2 in 16-byte units.  Unrolled with
-                    // compile-time counts so the descriptor arithmetic of the four MMAs overlaps instead of forming a
-                    // serial chain in front of every tcgen05.mma (measured: ~200 cycles per MMA with a runtime loop).
-                    if (k_steps == 4) issue_mmas<4, TWO>(tmem_d, adesc, bdesc, idesc, kb != 0);
-                    else if (k_steps == 2) issue_mmas<2, TWO>(tmem_d, adesc, bdesc, idesc, kb != 0);
-                    else if (k_steps == 1) issue_mmas<1, TWO>(tmem_d, adesc, bdesc, idesc, kb != 0);
+                    for (int sb = 0; sb < nsub; ++sb) {
+                        const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * stage_units + sb * sub_units);
+                        const uint64_t bdesc = adesc + a_units;
+                        // 16 elements (32 B) along K inside the swizzle span per MMA: +2 in 16-byte units.  Unrolled
+                        // with compile-time counts so the descriptor arithmetic of the MMAs overlaps instead of forming
+                        // a serial chain in front of every tcgen05.mma (measured: ~200 cycles per MMA with a runtime loop).
+                        const bool acc0 = (kb | sb) != 0;
+                        if (k_steps == 4) issue_mmas<4, TWO>(tmem_d, adesc, bdesc, idesc, acc0);
+                        else if (k_steps == 2) issue_mmas<2, TWO>(tmem_d, adesc, bdesc, idesc, acc0);
+                        else if (k_steps == 1) issue_mmas<1, TWO>(tmem_d, adesc, bdesc, idesc, acc0);
+                    }
                     // smem slot free (in both CTAs) once these MMAs retire
                     if (p.debug & 16) {
                     } else if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
@@ -576,12 +585,25 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     } else {
         L->grid = static_cast<int>(tiles < num_sms ? tiles : num_sms);
     }
-    // operand ring: as many stages as fit (bytes in flight, not stage count, is what hides the ~1.5 us TMA latency)
-    const int stage_bytes = (BLOCK_M + (two ? bn / 2 : bn)) * block_k * 2;
+    // operand ring.  One K block of a narrow layer is only a few hundred tensor-core cycles of work but costs a
+    // full barrier round trip (~450 cycles of wait/fence/commit in the issuing warp), so narrow layers put several
+    // K blocks into one stage; then as many stages as fit (bytes in flight hide the ~1.5 us L2->SM fill latency).
+    const int sub_bytes = (BLOCK_M + (two ? bn / 2 : bn)) * block_k * 2;
+    int kps = 1;
+    if (!two && bn <= 128 && sub_bytes <= 16384) {
+        kps = 49152 / sub_bytes;  // stage of <= 48 KB
+        if (kps < 1) kps = 1;
+        if (kps > 4) kps = 4;
+        if (kps > p.num_k_blocks) kps = p.num_k_blocks;
+        if (k == 3 && p.num_k_blocks % 3 == 0 && kps == 4) kps = 3;  // keep whole filter rows together
+    }
+    if (getenv("FASTDET_KPS")) kps = atoi(getenv("FASTDET_KPS"));
+    const int stage_bytes = sub_bytes * kps;
     int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { set_err(err, errlen, "conv_tc: stage does not fit in shared memory"); return -1; }
     p.num_stages = stages;
+    p.kb_per_stage = kps;
     L->smem_bytes = 1024 + SMEM_RING_OFF + static_cast<size_t>(stages) * stage_bytes;
     L->flops = 2.0 * double(M) * d.cout * K;
     return 0;

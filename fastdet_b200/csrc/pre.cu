@@ -4,7 +4,10 @@
 //   letterbox_u8       : extension (the reference rejects non-net-sized frames, detector.py:131-132)
 //   conv0_u8           : the same normalisation fused into the first convolution (Cin = 3), so the f32
 //                        NCHW tensor the reference materialises never exists on the serving path.
+#include <stdlib.h>
+
 #include "kernels.h"
+#include "ptx.cuh"
 
 namespace fd {
 
@@ -214,6 +217,137 @@ conv0_u8_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wg
     }
 }
 
+// ------------------------------------------------------------------------------------ first conv on tensor cores
+// The same layer as conv0_u8_kernel as an implicit GEMM on tcgen05: M = 128 output pixels (a 32 x 4 patch),
+// K = 27 taps*channels padded to 32, N = Cout (16 or 32).  Each thread builds the bf16 im2col row of its pixel
+// from a u8 halo patch in shared memory through a 257-entry LUT (bf16(k/255); entry 256 = the zero padding),
+// writes it K-major with the 64-byte swizzle the UMMA descriptor expects, one thread issues two 128xNx16 MMAs,
+// and every warp drains its TMEM lane quarter: bias + LeakyReLU + bf16, 64 contiguous bytes per pixel, 2 KB per
+// warp.  HBM-bound by the 64 B/pixel it writes; several small CTAs per SM overlap build / MMA / drain.
+static constexpr int C0T_TW = 32, C0T_TH = 4, C0T_THREADS = 128;
+
+__global__ void __launch_bounds__(C0T_THREADS)
+conv0_tc_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wgt, const float* __restrict__ bias,
+                __nv_bfloat16* __restrict__ out, int n, int h, int wd, int cout, int out_pitch, int act, float alpha) {
+    __shared__ __align__(1024) uint8_t sA[128 * 64];   // 128 pixel rows x 32 bf16 (SWIZZLE_64B, K-major)
+    __shared__ __align__(1024) uint8_t sB[32 * 64];    // up to 32 filter rows x 32 bf16
+    __shared__ uint16_t lut[257];
+    __shared__ uint16_t patch[(C0T_TH + 2) * (C0T_TW + 2) * 3];
+    __shared__ float b_s[32];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 257; i += C0T_THREADS) {
+        const __nv_bfloat16 v = __float2bfloat16(i < 256 ? norm_u8(i) : 0.f);
+        lut[i] = *reinterpret_cast<const uint16_t*>(&v);
+    }
+    if (tid < 32) b_s[tid] = tid < cout ? __ldg(bias + tid) : 0.f;
+    // B: row = output channel, 32 K values (27 real: (r*3+s)*3+ci), chunk c of row m at slot c ^ ((m >> 1) & 3)
+    for (int i = tid; i < 32 * 4; i += C0T_THREADS) {
+        const int m = i >> 2, c = i & 3;
+        uint32_t w[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int k0 = c * 8 + 2 * e, k1 = k0 + 1;
+            const float f0 = (m < cout && k0 < 27) ? __ldg(wgt + k0 * cout + m) : 0.f;
+            const float f1 = (m < cout && k1 < 27) ? __ldg(wgt + k1 * cout + m) : 0.f;
+            w[e] = c0_pack(f0, f1);
+        }
+        *reinterpret_cast<uint4*>(sB + m * 64 + ((c ^ ((m >> 1) & 3)) << 4)) = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+    if (tid == 0) {
+        ptx::mbar_init(&mma_bar, 1);
+        ptx::fence_barrier_init();
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(&tmem_slot, 32);
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(128, cout);
+    const uint64_t adesc = ptx::make_kmajor_desc(ptx::smem_u32(sA), 512, 4);
+    const uint64_t bdesc = ptx::make_kmajor_desc(ptx::smem_u32(sB), 512, 4);
+
+    const int tiles_x = (wd + C0T_TW - 1) / C0T_TW, tiles_y = (h + C0T_TH - 1) / C0T_TH;
+    const long long total = 1LL * n * tiles_x * tiles_y;
+    constexpr int PROW = (C0T_TW + 2) * 3;
+    uint32_t phase = 0;
+    for (long long tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        const int f = static_cast<int>(tile / (tiles_x * tiles_y));
+        const int rem = static_cast<int>(tile - 1LL * f * tiles_x * tiles_y);
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const int x0 = tx * C0T_TW, y0 = ty * C0T_TH;
+        const uint8_t* fr = frames + 1LL * f * h * wd * 3;
+        for (int i = tid; i < (C0T_TH + 2) * PROW; i += C0T_THREADS) {
+            const int yy = i / PROW, off = i - yy * PROW;
+            const int gy = y0 - 1 + yy, gx = x0 - 1 + off / 3;
+            uint16_t v = 256;  // zero padding of the normalised input
+            if (gy >= 0 && gy < h && gx >= 0 && gx < wd) v = __ldg(fr + (1LL * gy * wd + x0 - 1) * 3 + off);
+            patch[i] = v;
+        }
+        __syncthreads();
+        {   // im2col row of pixel (px = lane, py = warp)
+            uint32_t kk[16];
+            uint16_t e[32];
+#pragma unroll
+            for (int r = 0; r < 3; ++r)
+#pragma unroll
+                for (int q = 0; q < 9; ++q) e[r * 9 + q] = lut[patch[(warp + r) * PROW + lane * 3 + q]];
+#pragma unroll
+            for (int q = 27; q < 32; ++q) e[q] = 0;
+#pragma unroll
+            for (int q = 0; q < 16; ++q) kk[q] = static_cast<uint32_t>(e[2 * q]) | (static_cast<uint32_t>(e[2 * q + 1]) << 16);
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(sA + tid * 64 + ((c ^ ((tid >> 1) & 3)) << 4)) =
+                    make_uint4(kk[4 * c], kk[4 * c + 1], kk[4 * c + 2], kk[4 * c + 3]);
+        }
+        ptx::fence_proxy_async();  // generic-proxy writes of sA -> visible to the tensor core (async proxy)
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            ptx::tc_fence_after();
+            ptx::umma_bf16(tmem, adesc, bdesc, idesc, 0u);
+            ptx::umma_bf16(tmem, adesc + 2, bdesc + 2, idesc, 1u);
+            ptx::umma_commit(&mma_bar);
+        }
+        ptx::mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        ptx::tc_fence_after();
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(tmem + (static_cast<uint32_t>(warp * 32) << 16), acc);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        const int gy = y0 + warp, gx = x0 + lane;
+        if (gy < h && gx < wd) {
+            __nv_bfloat16* op = out + ((1LL * f * h + gy) * wd + gx) * out_pitch;
+#pragma unroll
+            for (int c = 0; c < 32; c += 8) {
+                if (c >= cout) break;
+                float v[8];
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    float x = __uint_as_float(acc[c + q]) + b_s[c + q];
+                    v[q] = (act && x < 0.f) ? x * alpha : x;
+                }
+                *reinterpret_cast<uint4*>(op + c) =
+                    make_uint4(c0_pack(v[0], v[1]), c0_pack(v[2], v[3]), c0_pack(v[4], v[5]), c0_pack(v[6], v[7]));
+            }
+        }
+        // the next tile's __syncthreads (after the patch load) orders these TMEM reads and the patch/sA reuse
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, 32);
+    }
+}
+
 int kernels_init() {
     return cudaFuncSetAttribute(conv0_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) ==
                    cudaSuccess
@@ -223,6 +357,14 @@ int kernels_init() {
 
 int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __nv_bfloat16* out, int n, int h,
                     int wd, int cout, int out_pitch, int act, float alpha, cudaStream_t s) {
+    static const bool force_cuda_core = getenv("FASTDET_CONV0_FMA") != nullptr;
+    if (!force_cuda_core && (cout == 16 || cout == 32)) {
+        const long long tiles = 1LL * n * ((wd + C0T_TW - 1) / C0T_TW) * ((h + C0T_TH - 1) / C0T_TH);
+        static const int per_sm = getenv("FASTDET_C0_CTAS") ? atoi(getenv("FASTDET_C0_CTAS")) : 16;
+        const int blocks = static_cast<int>(tiles < 148LL * per_sm ? tiles : 148LL * per_sm);
+        conv0_tc_kernel<<<blocks, C0T_THREADS, 0, s>>>(frames, w, bias, out, n, h, wd, cout, out_pitch, act, alpha);
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
     const size_t smem = (256 + (C0_TH + 2) * (C0_TW + 2) * 3 + 4 + 27 * cout + cout) * sizeof(float) +
                         static_cast<size_t>(C0_TH) * C0_TW * cout * 2;
     dim3 grid((wd + C0_TW - 1) / C0_TW, (h + C0_TH - 1) / C0_TH, n);
