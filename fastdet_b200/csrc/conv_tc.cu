@@ -181,11 +181,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 }
 
 template <int KS, bool TWO>
-__device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc0) {
+__device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc0,
+                                           uint32_t alt = 0) {
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-        if (TWO) ptx::umma2_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
-        else ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
+        const uint32_t d = tmem_d ^ ((k & 1) ? alt : 0u);  // alt != 0 only in a timing experiment (debug 64)
+        if (TWO) ptx::umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
+        else ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
     }
 }
 
@@ -208,17 +210,22 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint64_t* empty_bar = full_bar + MAX_STAGES;
     uint64_t* tmem_full_bar = empty_bar + MAX_STAGES;
     uint64_t* tmem_empty_bar = tmem_full_bar + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
-    uint8_t* ring = smem + SMEM_RING_OFF;
+    uint64_t* bres_bar = tmem_empty_bar + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bres_bar + 1);
+    // "B resident": when the whole filter bank of the (single) N tile fits, it is loaded into shared memory once per
+    // CTA and the ring carries only A — narrow layers are bound by the TMA issue rate, and this halves it.
+    const bool b_res = !TWO && p.b_resident != 0;
     const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
     const uint32_t b_bytes = B_ROWS * p.block_k * 2;
-    const uint32_t sub_bytes = a_bytes + b_bytes;     // one K block: A then B, both multiples of 1024
+    uint8_t* bres = smem + SMEM_RING_OFF;
+    uint8_t* ring = bres + (b_res ? b_bytes * p.num_k_blocks : 0u);
+    const uint32_t sub_bytes = a_bytes + (b_res ? 0u : b_bytes);  // one K block: A then B, both multiples of 1024
     const int kps = p.kb_per_stage;                   // K blocks sharing one ring stage / one barrier round
     const uint32_t stage_bytes = sub_bytes * kps;
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = p.num_m_tiles * p.num_n_tiles;  // TWO: m tiles are 256 rows
+    const int num_tiles = (p.debug & 32) ? 0 : p.num_m_tiles * p.num_n_tiles;  // TWO: m tiles are 256 rows
     const uint32_t cta_rank = TWO ? ptx::cluster_ctarank() : 0u;
     const int unit = TWO ? (blockIdx.x >> 1) : blockIdx.x;          // tile-stream index of this CTA (pair)
     const int units = TWO ? (gridDim.x >> 1) : gridDim.x;
@@ -236,6 +243,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tmem_full_bar[i], 1);
             ptx::mbar_init(&tmem_empty_bar[i], TWO ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
         }
+        ptx::mbar_init(bres_bar, 1);
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -265,11 +273,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool issuer = ptx::elect_one();
         const bool im2col = p.a_im2col != 0, load_a = !(p.debug & 2);
         const int ho_wo = p.ho * p.wo, wo = p.wo, cstride = p.stride, pad = p.pad_lo;
-        const uint32_t tx_bytes = ((load_a ? a_bytes : 0u) + b_bytes) * (TWO ? 2u : 1u);
+        const uint32_t tx_bytes = ((load_a ? a_bytes : 0u) + (b_res ? 0u : b_bytes)) * (TWO ? 2u : 1u);
         const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
         int stage = 0;
         uint32_t phase = 0;
         long long t_wait = 0, t_start = clock64();
+        if (b_res && issuer && unit < num_tiles) {
+            const uint32_t bar = ptx::smem_u32(bres_bar);
+            ptx::mbar_arrive_expect_tx_addr(bar, b_bytes * nkb);
+            for (int kb = 0; kb < nkb; ++kb)
+                ptx::tma_load_2d_addr(ptx::smem_u32(bres) + kb * b_bytes, mapB, bar, kb * block_k, 0);
+        }
         for (int tile = unit; tile < num_tiles && !(p.debug & 8); tile += units) {
             const int m_tile = tile / n_tiles_n;
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS * (TWO ? 1 : 0);
@@ -312,7 +326,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             else
                                 ptx::tma_load_2d_addr(dst, mapA, full_addr, cb * block_k, m0);
                         }
-                        ptx::tma_load_2d_addr(dst + a_bytes, mapB, full_addr, kcoord, n0);
+                        if (!b_res) ptx::tma_load_2d_addr(dst + a_bytes, mapB, full_addr, kcoord, n0);
                     }
                     kcoord += block_k;
                     if (++cb == cin_blocks) {
@@ -334,6 +348,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t desc0 = ptx::make_kmajor_desc(ring_base, sbo, layout);  // stage 0, A operand
         const uint32_t stage_units = stage_bytes >> 4, sub_units = sub_bytes >> 4, a_units = a_bytes >> 4;
         const bool issuer = ptx::elect_one();
+        const uint64_t bres_desc0 = ptx::make_kmajor_desc(ptx::smem_u32(bres), sbo, layout);
+        const uint32_t b_units = b_bytes >> 4;
+        if (b_res && unit < num_tiles) {
+            ptx::mbar_wait(bres_bar, 0);
+            ptx::tc_fence_after();
+        }
         int stage = 0;
         uint32_t phase = 0;
         int it = 0;
@@ -356,14 +376,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (issuer) {
                     for (int sb = 0; sb < nsub; ++sb) {
                         const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * stage_units + sb * sub_units);
-                        const uint64_t bdesc = adesc + a_units;
+                        const uint64_t bdesc = b_res ? bres_desc0 + static_cast<uint64_t>((kb + sb) * b_units) : adesc + a_units;
                         // 16 elements (32 B) along K inside the swizzle span per MMA: +2 in 16-byte units.  Unrolled
                         // with compile-time counts so the descriptor arithmetic of the MMAs overlaps instead of forming
                         // a serial chain in front of every tcgen05.mma (measured: ~200 cycles per MMA with a runtime loop).
                         const bool acc0 = (kb | sb) != 0;
-                        if (k_steps == 4) issue_mmas<4, TWO>(tmem_d, adesc, bdesc, idesc, acc0);
-                        else if (k_steps == 2) issue_mmas<2, TWO>(tmem_d, adesc, bdesc, idesc, acc0);
-                        else if (k_steps == 1) issue_mmas<1, TWO>(tmem_d, adesc, bdesc, idesc, acc0);
+                        const uint32_t alt = (p.debug & 64) ? static_cast<uint32_t>(BLOCK_N) : 0u;
+                        if (k_steps == 4) issue_mmas<4, TWO>(tmem_d, adesc, bdesc, idesc, acc0, alt);
+                        else if (k_steps == 2) issue_mmas<2, TWO>(tmem_d, adesc, bdesc, idesc, acc0, alt);
+                        else if (k_steps == 1) issue_mmas<1, TWO>(tmem_d, adesc, bdesc, idesc, acc0, alt);
                     }
                     // smem slot free (in both CTAs) once these MMAs retire
                     if (p.debug & 16) {
@@ -588,10 +609,14 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     // operand ring.  One K block of a narrow layer is only a few hundred tensor-core cycles of work but costs a
     // full barrier round trip (~450 cycles of wait/fence/commit in the issuing warp), so narrow layers put several
     // K blocks into one stage; then as many stages as fit (bytes in flight hide the ~1.5 us L2->SM fill latency).
-    const int sub_bytes = (BLOCK_M + (two ? bn / 2 : bn)) * block_k * 2;
+    const int b_total = bn * K * 2;  // the whole filter bank of one N tile
+    const int b_res = (!two && p.num_n_tiles == 1 && b_total <= 65536 && !getenv("FASTDET_NO_BRES")) ? 1 : 0;
+    p.b_resident = b_res;
+    const int sub_bytes = (BLOCK_M + (b_res ? 0 : (two ? bn / 2 : bn))) * block_k * 2;
     int kps = 1;
+    const int ring_avail = SMEM_LIMIT - 1024 - SMEM_RING_OFF - (b_res ? b_total : 0);
     if (!two && bn <= 128 && sub_bytes <= 16384) {
-        kps = 49152 / sub_bytes;  // stage of <= 48 KB
+        kps = ring_avail / (4 * sub_bytes);  // keep at least 4 stages in flight
         if (kps < 1) kps = 1;
         if (kps > 4) kps = 4;
         if (kps > p.num_k_blocks) kps = p.num_k_blocks;
@@ -599,12 +624,12 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     }
     if (getenv("FASTDET_KPS")) kps = atoi(getenv("FASTDET_KPS"));
     const int stage_bytes = sub_bytes * kps;
-    int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF) / stage_bytes;
+    int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF - (b_res ? bn * block_k * 2 * p.num_k_blocks : 0)) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { set_err(err, errlen, "conv_tc: stage does not fit in shared memory"); return -1; }
     p.num_stages = stages;
     p.kb_per_stage = kps;
-    L->smem_bytes = 1024 + SMEM_RING_OFF + static_cast<size_t>(stages) * stage_bytes;
+    L->smem_bytes = 1024 + SMEM_RING_OFF + (b_res ? bn * block_k * 2 * p.num_k_blocks : 0) + static_cast<size_t>(stages) * stage_bytes;
     L->flops = 2.0 * double(M) * d.cout * K;
     return 0;
 }

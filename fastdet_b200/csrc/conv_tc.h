@@ -41,6 +41,7 @@ struct ConvParams {
     int a_im2col; // 0: A via 2D tiled map (1x1 s1), 1: via im2col map
     int num_m_tiles, num_n_tiles;
     int num_stages;  // depth of the shared-memory operand ring
+    int b_resident;    // 1: the N tile's whole filter bank stays in shared memory, the ring carries A only
     int kb_per_stage;  // K blocks per ring stage (one barrier round trip covers all of them)
     const float* bias;
     int act;

@@ -254,6 +254,31 @@ int main(int argc, char** argv) {
         for (const Case& c : cases) fails += run_case(c, sms);
         printf("check: %d failing case(s)\n", fails);
     }
+    if (!strcmp(mode, "alt")) {
+        for (int dbg : {9, 73}) {
+            time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, dbg);
+            time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, dbg);
+            time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 257, dbg);
+        }
+    }
+    if (!strcmp(mode, "narrow")) {
+        for (int dbg : {0, 1, 2, 4, 6, 7, 9}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, dbg);
+        for (int dbg : {0, 1, 9}) time_case("1x1 256->128 @52 bs64", 64, 52, 256, 128, 1, 1, sms, 0, dbg);
+        for (int dbg : {0, 1, 9}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, dbg);
+    }
+    if (!strcmp(mode, "empty")) {
+        for (int bn : {64, 128, 257, 512}) time_case("empty 1x1 512->256 @26", 64, 26, 512, 256, 1, 1, sms, bn, 32, 0);
+        time_case("1 tile/CTA 1x1 512->256", 4, 26, 512, 256, 1, 1, sms, 257, 0, 0);
+        time_case("1 tile/CTA 3x3 256->512", 28, 26, 256, 256, 3, 1, sms, 257, 0, 0);
+    }
+    if (!strcmp(mode, "one")) {
+        for (int bn : {64, 128, 257, 512}) {
+            time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, bn, 0, 0);
+            time_case("1x1 1024->512 @13 bs64", 64, 13, 1024, 512, 1, 1, sms, bn, 0, 0);
+            time_case("1x1 256->128 @52 bs64", 64, 52, 256, 128, 1, 1, sms, bn > 128 ? 128 : bn, 0, 0);
+            time_case("3x3 512->1024 @13 res", 64, 13, 512, 1024, 3, 1, sms, bn, 0, 1);
+        }
+    }
     if (!strcmp(mode, "mma")) {
         for (int bn : {257, 512})
             for (int dbg : {0, 1, 9, 25}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, bn, dbg);
