@@ -224,6 +224,7 @@ def run_b200(args):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = ClockSampler(local) if rank == 0 else None  # started early: nvidia-smi needs a moment to begin reporting
     for i in range(max(args.warmup, 3)):
         step_device(i)
     torch.cuda.synchronize()
@@ -234,7 +235,6 @@ def run_b200(args):
     fwd_events = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    sampler = ClockSampler(local) if rank == 0 else None
     t_wall0 = time.time()
     e0.record(stream)
     for i in range(args.steps):
@@ -337,7 +337,7 @@ def run_b200(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="time budget of the reported CPU baseline sample")

@@ -180,6 +180,92 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
     }
 }
 
+// Swapped mode (narrow layers, Cout <= 128): the accumulator holds channels on the TMEM lanes and 256 output pixels on
+// the columns (a tcgen05.mma costs ~150 cycles at M = 128 whatever its N, so N must be 256 to use the whole array and
+// a narrow Cout cannot be N).  Lane = channel: bias is a per-lane scalar; a 32-pixel column chunk is staged to shared
+// memory transposed ([pixel][32 channels] bf16) and re-read so that 4 lanes cover the 64 contiguous bytes this warp
+// owns of one pixel row.
+__device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint32_t taddr0, float* stage_buf, int ch_warp,
+                                                      long long pix0, int lane, uint32_t full_addr, uint32_t aphase,
+                                                      uint32_t empty_addr, long long* t_acc) {
+    const int hw = p.ho * p.wo;
+    const int sub = lane >> 2, j = lane & 3;
+    const bool warp_has_channels = ch_warp < p.cout;
+    const int ch_own = ch_warp + lane;                      // row-major phase: this lane's channel
+    const float bias_own = (ch_own < p.cout) ? __ldg(p.bias + ch_own) : 0.f;
+    const int ch = ch_warp + 8 * j;                         // transposed phase: this lane's 8 channels
+    const bool has_res = p.residual != nullptr;
+    uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_buf);
+
+    const long long ta0 = t_acc ? clock64() : 0;
+    ptx::mbar_wait_addr(full_addr, aphase);
+    if (t_acc) *t_acc += clock64() - ta0;
+    ptx::tc_fence_after();
+
+#pragma unroll 1
+    for (int c0 = 0; c0 < 256; c0 += 32) {
+        uint32_t acc[32];
+        if (warp_has_channels) ptx::tmem_ld_32x32(taddr0 + c0, acc);
+        // pixels of this chunk handled by this lane in the transposed phase, and their residual values
+        long long orow[4];
+        bool ok[4];
+        uint4 res[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const long long m = pix0 + c0 + 8 * i + sub;
+            ok[i] = warp_has_channels && m < p.M && ch < p.cout;
+            orow[i] = m;
+            res[i] = make_uint4(0u, 0u, 0u, 0u);
+            if (has_res && ok[i]) res[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + m * p.res_pitch + ch));
+            if (p.upsample2x && ok[i]) {
+                const int img = static_cast<int>(m / hw);
+                const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+                const int oy = rem / p.wo;
+                const int ox = rem - oy * p.wo;
+                orow[i] = (static_cast<long long>(img) * 2 * p.ho + 2 * oy) * (2LL * p.wo) + 2 * ox;
+            }
+        }
+        if (warp_has_channels) ptx::tmem_ld_wait();
+        if (c0 + 32 >= 256) {
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
+        }
+        if (!warp_has_channels || (p.debug & 1)) continue;
+        // channel-major phase: + bias, LeakyReLU, bf16; element (pixel q, channel lane) -> stage16[q][lane]
+#pragma unroll
+        for (int q = 0; q < 32; ++q) {
+            float x = __uint_as_float(acc[q]) + bias_own;
+            if (p.act) x = x > 0.f ? x : x * p.alpha;
+            const __nv_bfloat16 hb = __float2bfloat16(x);
+            stage16[q * 32 + lane] = *reinterpret_cast<const uint16_t*>(&hb);
+        }
+        __syncwarp();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int q = 8 * i + sub;
+            uint4 v = *reinterpret_cast<const uint4*>(stage16 + q * 32 + 8 * j);
+            if (has_res) {
+                const uint4 rr = res[i];
+                v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(rr.x), bf16_hi(v.x) + bf16_hi(rr.x));
+                v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(rr.y), bf16_hi(v.y) + bf16_hi(rr.y));
+                v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(rr.z), bf16_hi(v.z) + bf16_hi(rr.z));
+                v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(rr.w), bf16_hi(v.w) + bf16_hi(rr.w));
+            }
+            if (!ok[i]) continue;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.out_pitch + ch;
+            *reinterpret_cast<uint4*>(op) = v;
+            if (p.upsample2x) {
+                const long long w2p = 2LL * p.wo * p.out_pitch;
+                *reinterpret_cast<uint4*>(op + p.out_pitch) = v;
+                *reinterpret_cast<uint4*>(op + w2p) = v;
+                *reinterpret_cast<uint4*>(op + w2p + p.out_pitch) = v;
+            }
+        }
+        __syncwarp();
+    }
+}
+
 template <int KS, bool TWO>
 __device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc0,
                                            uint32_t alt = 0) {
@@ -215,6 +301,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // "B resident": when the whole filter bank of the (single) N tile fits, it is loaded into shared memory once per
     // CTA and the ring carries only A — narrow layers are bound by the TMA issue rate, and this halves it.
     const bool b_res = !TWO && p.b_resident != 0;
+    // swapped mode: slot 0 (the MMA's M side, 128 rows) holds filter rows, slot 1 (N side, 256 rows) holds pixels
+    const bool swap = !TWO && BLOCK_N == 256 && p.swap != 0;
     const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
     const uint32_t b_bytes = B_ROWS * p.block_k * 2;
     uint8_t* bres = smem + SMEM_RING_OFF;
@@ -286,8 +374,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int tile = unit; tile < num_tiles && !(p.debug & 8); tile += units) {
             const int m_tile = tile / n_tiles_n;
-            const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS * (TWO ? 1 : 0);
-            const int m0 = m_tile * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
+            // normal: m0 = first output pixel (M side), n0 = first output channel (N side)
+            // swapped: m0 = first output pixel (N side, 256 per tile), n0 = first output channel (M side, 128 per tile)
+            const int n0 = swap ? (tile - m_tile * n_tiles_n) * BLOCK_M
+                                : (tile - m_tile * n_tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS * (TWO ? 1 : 0);
+            const int m0 = swap ? m_tile * 256 : m_tile * TILE_M + static_cast<int>(cta_rank) * BLOCK_M;
             int img = 0, base_w = 0, base_h = 0;
             if (im2col) {
                 img = m0 / ho_wo;
@@ -319,14 +410,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         }
                         ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
                     } else {
+                        // pixels go to the slot of the side they occupy in the MMA (slot 0 = M side, slot 1 = N side)
+                        const uint32_t dst_x = swap ? dst + a_bytes : dst, dst_w = swap ? dst : dst + a_bytes;
                         if (load_a) {
                             if (im2col)
-                                ptx::tma_load_im2col_4d_addr(dst, mapA, full_addr, cb * block_k, base_w, base_h, img,
+                                ptx::tma_load_im2col_4d_addr(dst_x, mapA, full_addr, cb * block_k, base_w, base_h, img,
                                                              static_cast<uint16_t>(tap_s), static_cast<uint16_t>(tap_r));
                             else
-                                ptx::tma_load_2d_addr(dst, mapA, full_addr, cb * block_k, m0);
+                                ptx::tma_load_2d_addr(dst_x, mapA, full_addr, cb * block_k, m0);
                         }
-                        if (!b_res) ptx::tma_load_2d_addr(dst + a_bytes, mapB, full_addr, kcoord, n0);
+                        if (!b_res) ptx::tma_load_2d_addr(dst_w, mapB, full_addr, kcoord, n0);
                     }
                     kcoord += block_k;
                     if (++cb == cin_blocks) {
@@ -415,6 +508,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int tile = unit + group * units; tile < num_tiles; tile += 2 * units, it += 2) {
             const uint32_t aphase = (it >> 1) & 1;
             const int m_tile = tile / n_tiles_n;
+            if (swap) {
+                const int ch_warp = (tile - m_tile * n_tiles_n) * BLOCK_M + quarter * 32;
+                epilogue_tile_swapped(p, taddr0, stage_buf, ch_warp, static_cast<long long>(m_tile) * 256, lane,
+                                      tmem_full_addr + 8u * group, aphase, empty_addr, prof ? &t_acc : nullptr);
+                continue;
+            }
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
             const long long m_base = static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
             epilogue_tile<BLOCK_N>(p, taddr0, stage_buf, m_base, n0, lane, tmem_full_addr + 8u * group, aphase, empty_addr,
@@ -521,6 +620,12 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     const int cin_blocks = d.cin / block_k;
     const int K = k * k * d.cin;
     long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
+    // swapped mode for narrow layers: channels on the MMA's M side (128-row tiles), 256 pixels on its N side
+    // (only where Cout fills the 128 lanes: with fewer channels most epilogue warps idle and the normal mode wins)
+    int swap = (d.cout > 64 && d.cout <= 128 && !d.out_fp32 && M >= 256 && !getenv("FASTDET_NO_SWAP")) ? 1 : 0;
+    if (block_n_hint == 1024) { swap = 1; block_n_hint = 0; }
+    else if (block_n_hint) swap = 0;
+    if (swap) block_n_hint = 257;
     int two = -1;  // -1: decide below
     if (block_n_hint == 512) { two = 1; block_n_hint = 256; }
     if (block_n_hint == 257) { two = 0; block_n_hint = 256; }
@@ -530,6 +635,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     if (two < 0) two = (bn == 256 && block_k == 64 && m_tiles >= 2 && !getenv("FASTDET_NO_2CTA")) ? 1 : 0;
     if (two && (bn != 256 || block_k != 64)) { set_err(err, errlen, "conv_tc: the CTA-pair kernel needs Cout > 128 and Cin %% 64 == 0"); return -1; }
     if (two) m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    if (swap) m_tiles = (M + 255) / 256;
     ConvParams& p = L->p;
     p.M = static_cast<int>(M);
     p.cout = d.cout;
@@ -543,7 +649,8 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     p.block_k = block_k;
     p.a_im2col = !(k == 1 && d.stride == 1 && d.pad_lo == 0 && d.pad_hi == 0);
     p.num_m_tiles = static_cast<int>(m_tiles);
-    p.num_n_tiles = (d.cout + bn - 1) / bn;
+    p.num_n_tiles = swap ? (d.cout + BLOCK_M - 1) / BLOCK_M : (d.cout + bn - 1) / bn;
+    p.swap = swap;
     p.bias = d.bias;
     p.act = d.act;
     p.alpha = d.alpha;
@@ -563,7 +670,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     if (!p.a_im2col) {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.cin), static_cast<cuuint64_t>(M)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.in_pitch) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), BLOCK_M};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(swap ? 256 : BLOCK_M)};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.in), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -578,7 +685,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
         int upper[2] = {d.pad_hi - (k - 1), d.pad_hi - (k - 1)};
         cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
         r = g_encodeIm2col(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), dims,
-                           strides, lower, upper, static_cast<cuuint32_t>(block_k), BLOCK_M, estr,
+                           strides, lower, upper, static_cast<cuuint32_t>(block_k), swap ? 256u : BLOCK_M, estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         // Same driver quirk CUTLASS works around for im2col maps over small tensors (< 128 KiB).
@@ -590,7 +697,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.cout)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(two ? bn / 2 : bn)};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(swap ? BLOCK_M : (two ? bn / 2 : bn))};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -610,12 +717,16 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     // full barrier round trip (~450 cycles of wait/fence/commit in the issuing warp), so narrow layers put several
     // K blocks into one stage; then as many stages as fit (bytes in flight hide the ~1.5 us L2->SM fill latency).
     const int b_total = bn * K * 2;  // the whole filter bank of one N tile
-    const int b_res = (!two && p.num_n_tiles == 1 && b_total <= 65536 && !getenv("FASTDET_NO_BRES")) ? 1 : 0;
+    const int b_res = (!two && !swap && p.num_n_tiles == 1 && b_total <= 65536 && !getenv("FASTDET_NO_BRES")) ? 1 : 0;
     p.b_resident = b_res;
     const int sub_bytes = (BLOCK_M + (b_res ? 0 : (two ? bn / 2 : bn))) * block_k * 2;
     int kps = 1;
     const int ring_avail = SMEM_LIMIT - 1024 - SMEM_RING_OFF - (b_res ? b_total : 0);
-    if (!two && bn <= 128 && sub_bytes <= 16384) {
+    if (swap) {
+        kps = 49152 / sub_bytes;  // 48 KB stages, 4 of them
+        if (kps < 1) kps = 1;
+        if (kps > p.num_k_blocks) kps = p.num_k_blocks;
+    } else if (!two && bn <= 128 && sub_bytes <= 16384) {
         kps = ring_avail / (4 * sub_bytes);  // keep at least 4 stages in flight
         if (kps < 1) kps = 1;
         if (kps > 4) kps = 4;

@@ -41,6 +41,7 @@ struct ConvParams {
     int a_im2col; // 0: A via 2D tiled map (1x1 s1), 1: via im2col map
     int num_m_tiles, num_n_tiles;
     int num_stages;  // depth of the shared-memory operand ring
+    int swap;          // 1: channels on the MMA's M side (128 per tile), 256 output pixels on its N side
     int b_resident;    // 1: the N tile's whole filter bank stays in shared memory, the ring carries A only
     int kb_per_stage;  // K blocks per ring stage (one barrier round trip covers all of them)
     const float* bias;
@@ -67,7 +68,7 @@ struct ConvLaunch {
 };
 
 // Builds tensor maps + launch geometry.  block_n_hint: 0 = choose, else one of 32/64/128/256;
-// 512 = force the CTA-pair kernel, 257 = force the single-CTA 256-wide kernel.
+// 512 = force the CTA-pair kernel, 257 = force the single-CTA 256-wide kernel, 1024 = force the swapped mode.
 // Returns 0 on success; on failure writes a message to err (if non-null).
 int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* out, char* err, size_t errlen);
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);

@@ -144,8 +144,8 @@ static int run_case(const Case& c, int num_sms) {
             for (int ch = c.cout; ch < out_pitch; ++ch)
                 if (o[row * out_pitch + ch] != 0xFFFF) ++clobbered;
     }
-    printf("[%-28s] M=%lld N=%d K=%d bn=%d%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
-           c.name, M, c.cout, K, L.block_n, L.two_cta ? "x2" : "", L.grid, max_err, max_ref, bad, clobbered,
+    printf("[%-28s] M=%lld N=%d K=%d bn=%d%s%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
+           c.name, M, c.cout, K, L.block_n, L.two_cta ? "x2" : "", L.p.swap ? "swap" : "", L.grid, max_err, max_ref, bad, clobbered,
            (bad == 0 && clobbered == 0) ? "OK" : "FAIL");
     if (bad) printf("    first bad at m=%lld n=%d\n", first_bad_m, first_bad_n);
     cudaFree(dx); cudaFree(dw); cudaFree(dbias); cudaFree(dout);
@@ -241,6 +241,12 @@ int main(int argc, char** argv) {
             {"3x3 64->32 pitch+32",     1, 19, 19, 64, 32, 3, 1, 1, 1, 1, 0, 0, 0, 32, 0},
             {"1x1 512->256 many tiles", 8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 0, 0, 0, 0, 64},
             {"3x3 tiny map 64->64",     1, 5, 5, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"swap 3x3 64->128 res",    3, 13, 13, 64, 128, 3, 1, 1, 1, 1, 1, 0, 0, 0, 1024},
+            {"swap 3x3 32->64 s2",      2, 32, 32, 32, 64, 3, 2, 1, 1, 1, 0, 0, 0, 0, 1024},
+            {"swap 1x1 256->128 up",    2, 13, 13, 256, 128, 1, 1, 0, 0, 1, 0, 0, 1, 64, 1024},
+            {"swap 1x1 64->32 pitch",   2, 20, 20, 64, 32, 1, 1, 0, 0, 1, 1, 0, 0, 64, 1024},
+            {"swap 3x3 16->32 (bk16)",  2, 20, 20, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 1024},
+            {"swap 1x1 384->128 big",   8, 52, 52, 384, 128, 1, 1, 0, 0, 1, 0, 0, 0, 0, 1024},
             {"2cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 512},
             {"2cta 3x3 64->256 res s2", 3, 26, 26, 64, 256, 3, 2, 1, 1, 1, 1, 0, 0, 0, 512},
             {"2cta 1x1 256->255 fp32",  2, 13, 13, 256, 255, 1, 1, 0, 0, 0, 0, 1, 0, 0, 512},
