@@ -109,11 +109,23 @@ def make_frames(first_seed: int, n: int) -> np.ndarray:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
+def use_all_host_threads():
+    """torchrun exports OMP_NUM_THREADS=1; the CPU arm is meant to use every core the process may run on."""
+    import torch
+    try:
+        n = len(os.sched_getaffinity(0))
+    except AttributeError:
+        n = os.cpu_count() or 1
+    torch.set_num_threads(max(1, n))
+    return torch.get_num_threads()
+
+
 def cpu_reference_fps(onnx_bytes: bytes, frames: np.ndarray, budget_s: float, min_frames: int = 2):
     """The reference path on host cores: per frame normalise -> graph (torch-CPU fp32, all threads) -> decode ->
     Soft-NMS, one frame per call exactly like ONNXDetector.perform (batch 1).  Returns (fps, frames, seconds, split)."""
     import torch
     from oracle import ref_graph, ref_post
+    use_all_host_threads()
     sess = ref_graph.OrtSubstituteSession(onnx_bytes)
     split = {"normalise": 0.0, "model_run": 0.0, "decode_nms": 0.0}
     done = 0
@@ -145,6 +157,7 @@ def run_reference(args):
     per_step = 2  # bounded sample: 2 frames of the workload per step
     import torch
     from oracle import ref_graph, ref_post
+    use_all_host_threads()
     sess = ref_graph.OrtSubstituteSession(onnx_bytes)
 
     def step(i):
@@ -191,7 +204,19 @@ def run_b200(args):
     use_dist = world > 1
     if use_dist:
         import torch.distributed as dist
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        # NCCL announces its version on stdout when the communicator comes up; the contract is ONE JSON line on
+        # stdout, so stdout is pointed at stderr while the process group initialises and runs its first collective.
+        sys.stdout.flush()
+        saved = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+            dist.barrier()
+            torch.cuda.synchronize()
+        finally:
+            sys.stdout.flush()
+            os.dup2(saved, 1)
+            os.close(saved)
     peaks = load_peaks()
 
     onnx_bytes = modelgen.build_onnx(ARCH, CLASSES, SIZE, MODEL_SEED)
@@ -299,7 +324,7 @@ def run_b200(args):
                        "detections_per_frame": round(det_per_frame, 1), "parallelism": f"frame-sharded x{world}, no collective"},
             "e2e": {"value": round(e2e, 1), "unit": "frames/s", "h2d_bytes_per_step": int(n * SIZE * SIZE * 3),
                     "d2h_bytes_per_step": int(n * MAX_DET * 48 + 2 * 4 * n), "api": "fd_detect (C ABI), pinned host frames, synchronous"},
-            "gpu_launches": int(args.steps * info.launches_per_detect),
+            "gpu_launches": int(world * args.steps * info.launches_per_detect),
             "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16_sustained"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16_sustained"], 4), "traffic": traffic,
                          "kernel": "conv stack = 74 x conv_tc_kernel (tcgen05) + conv0_u8_kernel, timed as fd_forward inside the timed steps",

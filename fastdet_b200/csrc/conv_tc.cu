@@ -195,7 +195,6 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
     const float bias_own = (ch_own < p.cout) ? __ldg(p.bias + ch_own) : 0.f;
     const int ch = ch_warp + 8 * j;                         // transposed phase: this lane's 8 channels
     const bool has_res = p.residual != nullptr;
-    uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_buf);
 
     const long long ta0 = t_acc ? clock64() : 0;
     ptx::mbar_wait_addr(full_addr, aphase);
@@ -232,25 +231,29 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
             if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
         }
         if (!warp_has_channels || (p.debug & 1)) continue;
-        // channel-major phase: + bias, LeakyReLU, bf16; element (pixel q, channel lane) -> stage16[q][lane]
+        // channel-major phase: + bias, LeakyReLU; element (pixel q, channel lane) -> stage_buf[q][lane] (fp32: one
+        // conflict-free 128-byte row per store instruction)
 #pragma unroll
         for (int q = 0; q < 32; ++q) {
             float x = __uint_as_float(acc[q]) + bias_own;
             if (p.act) x = x > 0.f ? x : x * p.alpha;
-            const __nv_bfloat16 hb = __float2bfloat16(x);
-            stage16[q * 32 + lane] = *reinterpret_cast<const uint16_t*>(&hb);
+            stage_buf[q * 32 + lane] = x;
         }
         __syncwarp();
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int q = 8 * i + sub;
-            uint4 v = *reinterpret_cast<const uint4*>(stage16 + q * 32 + 8 * j);
+            const float4 lo = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j);
+            const float4 hi = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j + 4);
+            uint4 v;
             if (has_res) {
                 const uint4 rr = res[i];
-                v.x = pack_bf16(bf16_lo(v.x) + bf16_lo(rr.x), bf16_hi(v.x) + bf16_hi(rr.x));
-                v.y = pack_bf16(bf16_lo(v.y) + bf16_lo(rr.y), bf16_hi(v.y) + bf16_hi(rr.y));
-                v.z = pack_bf16(bf16_lo(v.z) + bf16_lo(rr.z), bf16_hi(v.z) + bf16_hi(rr.z));
-                v.w = pack_bf16(bf16_lo(v.w) + bf16_lo(rr.w), bf16_hi(v.w) + bf16_hi(rr.w));
+                v.x = pack_bf16(lo.x + bf16_lo(rr.x), lo.y + bf16_hi(rr.x));
+                v.y = pack_bf16(lo.z + bf16_lo(rr.y), lo.w + bf16_hi(rr.y));
+                v.z = pack_bf16(hi.x + bf16_lo(rr.z), hi.y + bf16_hi(rr.z));
+                v.w = pack_bf16(hi.z + bf16_lo(rr.w), hi.w + bf16_hi(rr.w));
+            } else {
+                v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
             }
             if (!ok[i]) continue;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.out_pitch + ch;
@@ -622,7 +625,8 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     // swapped mode for narrow layers: channels on the MMA's M side (128-row tiles), 256 pixels on its N side
     // (only where Cout fills the 128 lanes: with fewer channels most epilogue warps idle and the normal mode wins)
-    int swap = (d.cout > 64 && d.cout <= 128 && !d.out_fp32 && M >= 256 && !getenv("FASTDET_NO_SWAP")) ? 1 : 0;
+    static const int swap_min = getenv("FASTDET_SWAP_MIN") ? atoi(getenv("FASTDET_SWAP_MIN")) : 64;
+    int swap = (d.cout > swap_min && d.cout <= 128 && !d.out_fp32 && M >= 256 && !getenv("FASTDET_NO_SWAP")) ? 1 : 0;
     if (block_n_hint == 1024) { swap = 1; block_n_hint = 0; }
     else if (block_n_hint) swap = 0;
     if (swap) block_n_hint = 257;
