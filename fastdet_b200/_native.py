@@ -17,6 +17,7 @@ LIB_PATH = os.path.join(_HERE, "libfastdet_b200.so")
 
 FD_OK, FD_ERR_ARG, FD_ERR_MODEL, FD_ERR_HEADS, FD_ERR_CUDA, FD_ERR_SIZE = 0, -1, -2, -3, -4, -5
 FD_MAX_HEADS = 4
+FD_MAX_SLOTS = 2
 
 
 class FdDet(C.Structure):
@@ -61,6 +62,8 @@ _PROTOS = {
     "fd_fetch": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_detect": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int,
                             C.c_void_p, C.c_void_p]),
+    "fd_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
+    "fd_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_set_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_layer_output_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -176,6 +179,31 @@ class Model:
         _check(lib().fd_detect(self._h, _ptr(frames), n, w, h, 0, int(allow_resize), float(threshold), max_det,
                                _ptr(dets), _ptr(counts)))
         return dets, counts
+
+    # -- pipelined serving: two batches in flight, the H2D copy of one overlaps the compute of the other
+    def submit(self, slot: int, frames, threshold: float, allow_resize=False, max_det: int = 2048, n=None, src_wh=None,
+               on_device=False):
+        """frames: [n, h, w, 3] u8 numpy array (ideally backed by pinned memory) or a raw pointer (then give n and
+        src_wh).  The caller keeps `frames` alive and unmodified until collect(slot) returns."""
+        if isinstance(frames, int):
+            p, (w, h) = C.c_void_p(frames), src_wh
+        else:
+            if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3 or not frames.flags.c_contiguous:
+                raise ValueError("invalid image size")
+            n, h, w, _ = frames.shape
+            p = _ptr(frames)
+        _check(lib().fd_submit(self._h, slot, p, n, w, h, int(on_device), int(allow_resize), float(threshold), max_det))
+        if not hasattr(self, "_slot_shape"):
+            self._slot_shape = {}
+        self._slot_shape[slot] = (n, max_det, frames)
+
+    def collect(self, slot: int):
+        n, max_det, _keepalive = self._slot_shape.pop(slot)
+        dets = np.zeros((n, max_det), DET_DTYPE)
+        counts = np.zeros(n, np.int32)
+        total = np.zeros(n, np.int32)
+        _check(lib().fd_collect(self._h, slot, _ptr(dets), _ptr(counts), _ptr(total)))
+        return dets, counts, total
 
     # -- parity / profiling hooks
     def heads(self, n: int) -> List[np.ndarray]:

@@ -67,9 +67,23 @@ struct Exec {  // everything that depends on the batch size
 
 }  // namespace
 
+struct Slot {  // one in-flight fd_submit: staged input + pinned results + the events that order them
+    uint8_t* stage = nullptr;   // device staging for the H2D copy (copy stream)
+    size_t stage_cap = 0;
+    Detection* h_dets = nullptr;  // pinned
+    size_t h_dets_cap = 0;
+    int* h_count = nullptr;       // pinned [2n]
+    size_t h_count_cap = 0;
+    cudaEvent_t staged = nullptr, stage_free = nullptr, done = nullptr;
+    int n = 0, max_det = 0;
+    bool busy = false;
+};
+
 struct fd_model {
     int device = 0;
     int num_sms = 148;
+    cudaStream_t copy_stream = nullptr;
+    Slot slots[FD_MAX_SLOTS];
     ModelPlan plan;
     __nv_bfloat16* d_w = nullptr;
     float* d_bias = nullptr;
@@ -132,7 +146,7 @@ int get_exec(fd_model* m, int n, Exec** out) {
         d.n = n; d.hi = L.in.h; d.wi = L.in.w; d.cin = L.cin; d.in_pitch = L.in.pitch;
         d.in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false));
         d.cout = L.cout; d.ksize = L.ksize; d.stride = L.stride; d.pad_lo = L.pad_lo; d.pad_hi = L.pad_hi;
-        d.w = m->d_w + L.w_off; d.bias = m->d_bias + L.b_off; d.act = L.act; d.alpha = L.alpha;
+        d.w = m->d_w + L.w_off; d.bias = m->d_bias + L.b_off; d.bias_host = P.bias_f32.data() + L.b_off; d.act = L.act; d.alpha = L.alpha;
         if (L.res.buf >= 0) { d.residual = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.res, false)); d.res_pitch = L.res.pitch; }
         d.out = loc_ptr(*e, L.out, L.out_fp32 != 0); d.out_pitch = L.out.pitch; d.out_fp32 = L.out_fp32; d.upsample2x = L.upsample2x;
         char err[256] = "";
@@ -278,6 +292,13 @@ void fd_model_destroy(fd_model* m) {
     cudaDeviceSynchronize();
     for (auto& kv : m->execs) free_exec(kv.second.get());
     cudaFree(m->d_w); cudaFree(m->d_bias); cudaFree(m->d_conv0);
+    for (Slot& S : m->slots) {
+        cudaFree(S.stage);
+        if (S.h_dets) cudaFreeHost(S.h_dets);
+        if (S.h_count) cudaFreeHost(S.h_count);
+        if (S.staged) { cudaEventDestroy(S.staged); cudaEventDestroy(S.stage_free); cudaEventDestroy(S.done); }
+    }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
 }
@@ -362,24 +383,10 @@ int fd_forward(fd_model* m, int n, void* stream) {
     return launch_layers(m, e, s);
 }
 
-int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stream) {
-    if (!m) return fail(FD_ERR_ARG, "fd_postprocess: null model");
+// decode + Soft-NMS on the head tensors, then the records to pinned host memory (h_dets / h_count) on stream s
+static int postprocess_on(fd_model* m, Exec* e, int n, double threshold, int max_det, cudaStream_t s, Detection* h_dets,
+                          int* h_count) {
     const fd_info& I = m->info;
-    if (I.n_heads != 2 && I.n_heads != 3) return fail(FD_ERR_HEADS, "%d", I.n_heads);  // KeyError(len(outputs)) in the reference
-    if (max_det < 1) return fail(FD_ERR_ARG, "max_det must be >= 1");
-    NEED_DEVICE(m);
-    CU(cudaSetDevice(m->device));
-    Exec* e;
-    if (int rc = get_exec(m, n, &e)) return rc;
-    cudaStream_t s = pick(m, stream);
-    if (e->max_det < max_det) {
-        CU(cudaStreamSynchronize(s));
-        cudaFree(e->dets); e->dets = nullptr;
-        if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
-        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
-        CU(cudaMallocHost(&e->h_dets, sizeof(Detection) * size_t(n) * max_det));
-        e->max_det = max_det;
-    }
     HeadDesc heads[FD_MAX_HEADS];
     int first = 0;
     for (int h = 0; h < I.n_heads; ++h) {
@@ -395,9 +402,31 @@ int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stre
     if (launch_soft_nms(e->cand, e->cand_count, e->scores, I.boxes_per_frame, n, I.net_w, I.net_h, threshold, e->dets,
                         e->det_count, e->det_count + n, max_det, s))
         return fail(FD_ERR_CUDA, "soft-nms launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    CU(cudaMemcpyAsync(h_count, e->det_count, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s));
+    CU(cudaMemcpyAsync(h_dets, e->dets, sizeof(Detection) * size_t(n) * max_det, cudaMemcpyDeviceToHost, s));
+    return FD_OK;
+}
+
+int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stream) {
+    if (!m) return fail(FD_ERR_ARG, "fd_postprocess: null model");
+    const fd_info& I = m->info;
+    if (I.n_heads != 2 && I.n_heads != 3) return fail(FD_ERR_HEADS, "%d", I.n_heads);  // KeyError(len(outputs)) in the reference
+    if (max_det < 1) return fail(FD_ERR_ARG, "max_det must be >= 1");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    cudaStream_t s = pick(m, stream);
+    if (e->max_det != max_det || !e->h_dets) {
+        CU(cudaStreamSynchronize(s));
+        cudaFree(e->dets); e->dets = nullptr;
+        if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
+        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
+        CU(cudaMallocHost(&e->h_dets, sizeof(Detection) * size_t(n) * max_det));
+        e->max_det = max_det;
+    }
     // results to pinned host memory on the same stream; fd_fetch synchronises
-    CU(cudaMemcpyAsync(e->h_count, e->det_count, sizeof(int) * 2 * n, cudaMemcpyDeviceToHost, s));
-    CU(cudaMemcpyAsync(e->h_dets, e->dets, sizeof(Detection) * size_t(n) * max_det, cudaMemcpyDeviceToHost, s));
+    if (int rc = postprocess_on(m, e, n, threshold, max_det, s, e->h_dets, e->h_count)) return rc;
     m->last_n = n;
     m->last_max_det = max_det;
     return FD_OK;
@@ -426,6 +455,97 @@ int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, i
     if (int rc = fd_forward(m, n, nullptr)) return rc;
     if (int rc = fd_postprocess(m, n, threshold, max_det, nullptr)) return rc;
     return fd_fetch(m, n, out, counts, nullptr, nullptr);
+}
+
+// ------------------------------------------------------------------ pipelined serving: fd_submit / fd_collect
+// Two (FD_MAX_SLOTS) batches can be in flight: the host->device copy of a slot runs on the model's copy stream while
+// the compute stream works on the other slot, so a caller that alternates slots keeps the conv stack busy
+// back to back (the synchronous fd_detect pays the PCIe copy in front of every batch).
+int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
+              double threshold, int max_det) {
+    if (!m || !frames) return fail(FD_ERR_ARG, "fd_submit: null argument");
+    if (slot < 0 || slot >= FD_MAX_SLOTS) return fail(FD_ERR_ARG, "fd_submit: slot %d out of range [0, %d)", slot, FD_MAX_SLOTS);
+    const ModelPlan& P = m->plan;
+    const fd_info& I = m->info;
+    const bool same = src_w == P.net_w && src_h == P.net_h;
+    if (!same && !allow_resize) return fail(FD_ERR_SIZE, "invalid image size");  // reference detector.py:132
+    if (src_w < 1 || src_h < 1) return fail(FD_ERR_SIZE, "invalid image size");
+    if (I.n_heads != 2 && I.n_heads != 3) return fail(FD_ERR_HEADS, "%d", I.n_heads);
+    if (max_det < 1) return fail(FD_ERR_ARG, "max_det must be >= 1");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Slot& S = m->slots[slot];
+    if (S.busy) return fail(FD_ERR_ARG, "fd_submit: slot %d still holds uncollected results", slot);
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    if (!S.staged) {
+        CU(cudaEventCreateWithFlags(&S.staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&S.stage_free, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    }
+    const size_t bytes = size_t(n) * src_w * src_h * 3;
+    if (S.stage_cap < bytes) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(S.stage); S.stage = nullptr; S.stage_cap = 0;
+        CU(cudaMalloc(&S.stage, bytes));
+        S.stage_cap = bytes;
+    }
+    const size_t det_bytes = sizeof(Detection) * size_t(n) * max_det, cnt_bytes = sizeof(int) * 2 * size_t(n);
+    if (S.h_dets_cap < det_bytes) {
+        if (S.h_dets) cudaFreeHost(S.h_dets);
+        S.h_dets = nullptr; S.h_dets_cap = 0;
+        CU(cudaMallocHost(&S.h_dets, det_bytes));
+        S.h_dets_cap = det_bytes;
+    }
+    if (S.h_count_cap < cnt_bytes) {
+        if (S.h_count) cudaFreeHost(S.h_count);
+        S.h_count = nullptr; S.h_count_cap = 0;
+        CU(cudaMallocHost(&S.h_count, cnt_bytes));
+        S.h_count_cap = cnt_bytes;
+    }
+    if (e->max_det != max_det) {
+        CU(cudaStreamSynchronize(m->stream));
+        cudaFree(e->dets); e->dets = nullptr;
+        if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
+        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
+        e->max_det = max_det;
+    }
+    cudaStream_t cs = m->copy_stream, s = m->stream;
+    // copy stream: wait until the compute stream has consumed this slot's previous contents, then stage the frames
+    CU(cudaStreamWaitEvent(cs, S.stage_free, 0));
+    CU(cudaMemcpyAsync(S.stage, frames, bytes, on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(S.staged, cs));
+    // compute stream: staged frames -> the Exec's input tensor (33 MB device copy at bs64, ~10 us), then the batch
+    CU(cudaStreamWaitEvent(s, S.staged, 0));
+    if (same) {
+        CU(cudaMemcpyAsync(e->frames, S.stage, bytes, cudaMemcpyDeviceToDevice, s));
+    } else if (launch_letterbox_u8(S.stage, e->frames, n, src_h, src_w, P.net_h, P.net_w, 128, s)) {
+        return fail(FD_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    }
+    CU(cudaEventRecord(S.stage_free, s));
+    if (int rc = fd_forward(m, n, nullptr)) return rc;
+    if (int rc = postprocess_on(m, e, n, threshold, max_det, s, S.h_dets, S.h_count)) return rc;
+    CU(cudaEventRecord(S.done, s));
+    S.n = n; S.max_det = max_det; S.busy = true;
+    return FD_OK;
+}
+
+int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* total) {
+    if (!m || !out || !counts) return fail(FD_ERR_ARG, "fd_collect: null argument");
+    if (slot < 0 || slot >= FD_MAX_SLOTS) return fail(FD_ERR_ARG, "fd_collect: slot %d out of range [0, %d)", slot, FD_MAX_SLOTS);
+    NEED_DEVICE(m);
+    Slot& S = m->slots[slot];
+    if (!S.busy) return fail(FD_ERR_ARG, "fd_collect: nothing was submitted to slot %d", slot);
+    CU(cudaSetDevice(m->device));
+    S.busy = false;
+    CU(cudaEventSynchronize(S.done));
+    for (int f = 0; f < S.n; ++f) {
+        counts[f] = S.h_count[f];
+        if (total) total[f] = S.h_count[S.n + f];
+        memcpy(out + size_t(f) * S.max_det, S.h_dets + size_t(f) * S.max_det, sizeof(fd_det) * size_t(S.h_count[f]));
+    }
+    return FD_OK;
 }
 
 // ------------------------------------------------------------------ parity / profiling hooks

@@ -31,7 +31,7 @@ static constexpr int NUM_THREADS = 384;
 static constexpr int MAX_STAGES = 32;
 // dynamic shared memory map (after aligning the base to 1024 B):
 //   [0, 1024)       full[32] + empty[32] + tmem_full[2] + tmem_empty[2] mbarriers, TMEM base slot
-//   [1024, 33792)   epilogue staging: 8 warps x (32 rows x 32 fp32) = 8 x 4 KB
+//   [1024, 33792)   epilogue staging: 8 warps x 4 KB (two 32-row x 64-byte bf16 chunk buffers each)
 //   [33792, ...)    operand ring: num_stages x (A stage | B stage), every stage 1024-byte aligned
 static constexpr int SMEM_STAGING_OFF = 1024;
 static constexpr int SMEM_RING_OFF = 1024 + 8 * 4096;
@@ -49,134 +49,194 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
+// bf16x2 add with one rounding (HADD2.BF16): residual + branch value, both already bf16
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
+// bias + activation on two accumulator columns at once (FADD2 / FMUL2 are two fp32 lanes per instruction).
+// Branch-free for the two cases YOLO has: LeakyReLU with 0 <= alpha <= 1 is max(x, alpha*x), and a linear layer is
+// the same expression with alpha = 1 (x*1 = x exactly).  GENERIC (alpha outside [0,1]) uses the select form.
+template <bool GENERIC>
+__device__ __forceinline__ float2 bias_act2(uint32_t a0, uint32_t a1, float b0, float b1, float2 alpha2) {
+    float2 x = __fadd2_rn(make_float2(__uint_as_float(a0), __uint_as_float(a1)), make_float2(b0, b1));
+    if (GENERIC) {
+        x.x = x.x > 0.f ? x.x : x.x * alpha2.x;
+        x.y = x.y > 0.f ? x.y : x.y * alpha2.x;
+    } else {
+        const float2 m = __fmul2_rn(x, alpha2);
+        x.x = fmaxf(x.x, m.x);
+        x.y = fmaxf(x.y, m.y);
+    }
+    return x;
+}
+
 // One accumulator tile (128 rows x BLOCK_N columns of this CTA's TMEM) -> global memory.
 //   taddr0     TMEM address of the warp's lane quarter at the accumulator stage's first column
 //   m_base     global output-pixel index of the warp's first row
 //   empty_addr shared address of the tmem_empty barrier to arrive on once the accumulator is drained
 //              (for a CTA pair: the leader's barrier, reached through the shared::cluster window)
+// Shared-memory LOADS cost ~500 cycles here (the LSU queues behind the TMA fills and the tensor core's operand
+// reads — measured), and two epilogue warps per scheduler cannot hide that, so the path has none: the bias comes
+// from the constant bank (kernel parameter), the residual is read row-major straight from global memory one chunk
+// ahead, the bf16 rows are staged with fire-and-forget stores and leave through a TMA store, and the TMEM load of
+// chunk c+1 is in flight while chunk c is processed.
+//   p.epi_mode 0: bf16 NHWC slice via TMA store (+ residual)   1: fp32 head rows, direct stores
+//              2: bf16 with x2 nearest upsampling (2 layers): staged, re-read transposed, 4 coalesced stores per row
 template <int BLOCK_N>
-__device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t taddr0, float* stage_buf, long long m_base,
-                                              int n0, int lane, uint32_t full_addr, uint32_t aphase,
-                                              uint32_t empty_addr, long long* t_acc) {
-    const int hw = p.ho * p.wo;
-    const int sub = lane >> 2;  // row within an 8-row pass of the transposed phase
-    const int j = lane & 3;     // which 8 of the chunk's 32 channels this lane owns there
-    // destination rows of the 4 pixel rows this lane touches in the transposed phase
-    long long orow[4];
-    bool ok[4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        const long long m = m_base + 8 * i + sub;
-        ok[i] = m < p.M;
-        orow[i] = m;
-        if (p.upsample2x && ok[i]) {
-            const int img = static_cast<int>(m / hw);
-            const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
-            const int oy = rem / p.wo;
-            const int ox = rem - oy * p.wo;
-            orow[i] = (static_cast<long long>(img) * 2 * p.ho + 2 * oy) * (2LL * p.wo) + 2 * ox;
-        }
-    }
-    const bool has_res = p.residual != nullptr;
-    uint4 rnext[4];
+__device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtensorMap* tm_out, uint32_t taddr0,
+                                              uint8_t* stage, int& sbuf, long long m_base, int n0, int lane, int half,
+                                              uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc) {
+    // the two warps that share a TMEM lane quarter split the tile's columns: all 8 epilogue warps work on the same
+    // tile, which halves the time the last tile of a launch (nothing left to overlap with) spends here
+    constexpr int HALF_N = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
+    // (a 32-column tile is one chunk: there the two warps take alternate tiles instead, see the kernel)
+    const int c_begin = (BLOCK_N >= 64) ? half * HALF_N : 0;
+    const int c_end = c_begin + HALF_N;
+    const int mode = p.epi_mode;
+    const bool generic_act = p.act == 2;
+    const float alpha_eff = p.act ? p.alpha : 1.0f;
+    const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
+    const long long m_own = m_base + lane;  // the pixel row this lane holds
+    const bool own_ok = m_own < p.M;
+    const bool has_res = mode == 0 && p.residual != nullptr;
+    const __nv_bfloat16* res_row = p.residual + m_own * p.res_pitch + n0;
+    ptx::U32x8 rnext[2];
+    // this lane's 64 bytes of the residual row for chunk c0, as two 32-byte loads: every L2 sector is requested once
+    // (16-byte loads would fetch each sector twice, and this kernel is bound by L2 -> SM traffic)
     auto fetch_res = [&](int c0) {
-        const int ch = n0 + c0 + 8 * j;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            rnext[i] = make_uint4(0u, 0u, 0u, 0u);
-            if (has_res && ok[i] && ch < p.cout)
-                rnext[i] = __ldg(reinterpret_cast<const uint4*>(p.residual + (m_base + 8 * i + sub) * p.res_pitch + ch));
+        for (int i = 0; i < 2; ++i) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rnext[i].v[e] = 0u;
+            if (!(has_res && own_ok && n0 + c0 + 16 * i < p.cout)) continue;
+            if (p.res_v8) {
+                rnext[i] = ptx::ld_nc_v8(res_row + c0 + 16 * i);
+            } else {  // slices that are only 16-byte aligned
+                const uint4 lo = ptx::ld_nc_v4(reinterpret_cast<const uint4*>(res_row + c0 + 16 * i));
+                const uint4 hi = ptx::ld_nc_v4(reinterpret_cast<const uint4*>(res_row + c0 + 16 * i + 8));
+                rnext[i].v[0] = lo.x; rnext[i].v[1] = lo.y; rnext[i].v[2] = lo.z; rnext[i].v[3] = lo.w;
+                rnext[i].v[4] = hi.x; rnext[i].v[5] = hi.y; rnext[i].v[6] = hi.z; rnext[i].v[7] = hi.w;
+            }
         }
     };
-    fetch_res(0);  // independent of the accumulator: in flight while the MMAs finish
+    fetch_res(c_begin);  // independent of the accumulator: in flight while the MMAs finish
 
     const long long ta0 = t_acc ? clock64() : 0;
     ptx::mbar_wait_addr(full_addr, aphase);
     if (t_acc) *t_acc += clock64() - ta0;
     ptx::tc_fence_after();
+    long long tp = t_acc ? clock64() : 0;  // developer phase timers: t_acc[1] TMEM load, [2] math, [3] staging + stores
+    auto lap = [&](int slot) {
+        if (t_acc) { const long long now = clock64(); t_acc[slot] += now - tp; tp = now; }
+    };
 
-    const long long m_own = m_base + lane;  // the pixel row this lane holds in the row-major phase
-    const bool own_ok = m_own < p.M;
-    uint16_t* stage16 = reinterpret_cast<uint16_t*>(stage_buf);
-
-#pragma unroll 1
-    for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-        uint32_t acc[32];
-        ptx::tmem_ld_32x32(taddr0 + c0, acc);
-        uint4 rcur[4];
+    // one 32-column chunk held in `acc` (its TMEM load already waited for)
+    auto chunk = [&](const uint32_t (&acc)[32], int c0) {
+        ptx::U32x8 rcur[2];
+        rcur[0] = rnext[0];
+        rcur[1] = rnext[1];
+        if (c0 + 32 < c_end) fetch_res(c0 + 32);
+        const float* bias = p.bias_c + n0 + c0;  // constant bank, warp-uniform index
+        float2 x[16];
+        if (!generic_act) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) rcur[i] = rnext[i];
-        if (c0 + 32 < BLOCK_N) fetch_res(c0 + 32);
-        const float4* bias4 = reinterpret_cast<const float4*>(p.bias + n0 + c0);  // same address in every lane: L1 broadcast
-        float4 bv[8];
+            for (int g = 0; g < 16; ++g) x[g] = bias_act2<false>(acc[2 * g], acc[2 * g + 1], bias[2 * g], bias[2 * g + 1], alpha2);
+        } else {
 #pragma unroll
-        for (int g = 0; g < 8; ++g) bv[g] = __ldg(bias4 + g);
-        ptx::tmem_ld_wait();
-        if (c0 + 32 >= BLOCK_N) {
-            // last TMEM read of this accumulator stage: hand it back to the MMA warp early
-            ptx::tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
+            for (int g = 0; g < 16; ++g) x[g] = bias_act2<true>(acc[2 * g], acc[2 * g + 1], bias[2 * g], bias[2 * g + 1], alpha2);
         }
-        if (p.debug & 1) continue;
-        // row-major phase (lane = pixel row): bias + LeakyReLU in fp32
-        float v[32];
-#pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            v[4 * g + 0] = __uint_as_float(acc[4 * g + 0]) + bv[g].x;
-            v[4 * g + 1] = __uint_as_float(acc[4 * g + 1]) + bv[g].y;
-            v[4 * g + 2] = __uint_as_float(acc[4 * g + 2]) + bv[g].z;
-            v[4 * g + 3] = __uint_as_float(acc[4 * g + 3]) + bv[g].w;
-        }
-        if (p.act) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * p.alpha;
-        }
-        if (p.out_fp32) {
-            // head tensors (3 small layers): fp32 rows straight from the row-major phase
+        if (mode == 1) {
+            // head tensors (3 small layers): fp32 rows straight from the registers
             if (own_ok) {
                 float* op = reinterpret_cast<float*>(p.out) + m_own * p.out_pitch + n0 + c0;
 #pragma unroll
                 for (int g = 0; g < 8; ++g)
                     if (n0 + c0 + 4 * g < p.n_store_limit)
-                        *reinterpret_cast<float4*>(op + 4 * g) = make_float4(v[4 * g], v[4 * g + 1], v[4 * g + 2], v[4 * g + 3]);
+                        *reinterpret_cast<float4*>(op + 4 * g) = make_float4(x[2 * g].x, x[2 * g].y, x[2 * g + 1].x, x[2 * g + 1].y);
             }
-            continue;
+            lap(2);
+            return;
         }
-        // stage the bf16 row (64 B = 4 x 16 B) swizzled: chunk c of row r sits at slot c ^ ((r >> 1) & 3), which makes
-        // both this write (8 consecutive rows per quarter-warp) and the transposed read below bank-conflict free
+        uint32_t pk[16];
+#pragma unroll
+        for (int g = 0; g < 16; ++g) pk[g] = pack_bf16(x[g].x, x[g].y);
+        if (has_res) {  // ONNX Add after LeakyRelu; both terms are bf16, the sum is rounded once
+#pragma unroll
+            for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
+        }
+        lap(2);
+        // stage the bf16 row (64 B = 4 x 16 B) with the 64-byte swizzle (chunk c of row r at slot c ^ ((r >> 1) & 3)):
+        // conflict-free for these stores, and the layout a SWIZZLE_64B tensor map reads back
+        uint8_t* buf = stage + (sbuf & 1) * 2048;
+        if (mode == 0) {
+            // the TMA store that last read this buffer (two chunks ago) must have finished reading it
+            if (lane == 0) ptx::tma_store_wait_read<1>();
+            __syncwarp();
+        }
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            *reinterpret_cast<uint4*>(stage16 + lane * 32 + ((c ^ ((lane >> 1) & 3)) << 3)) =
-                make_uint4(pack_bf16(v[8 * c + 0], v[8 * c + 1]), pack_bf16(v[8 * c + 2], v[8 * c + 3]),
-                           pack_bf16(v[8 * c + 4], v[8 * c + 5]), pack_bf16(v[8 * c + 6], v[8 * c + 7]));
+            *reinterpret_cast<uint4*>(buf + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) =
+                make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        if (mode == 0) {
+            ptx::fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_2d(tm_out, buf, n0 + c0, static_cast<int>(m_base));  // rows >= M are clipped by the map
+                ptx::tma_store_commit();
+            }
+            ++sbuf;
+            lap(3);
+            return;
+        }
+        // mode 2 (x2 upsampling): re-read transposed so that 4 lanes cover the 64 contiguous bytes of one pixel row
         __syncwarp();
-        // transposed phase: 4 lanes cover the 64 contiguous bytes of one pixel row -> coalesced residual add + store
+        const int hw = p.ho * p.wo;
+        const int sub = lane >> 2, j = lane & 3;
         const int ch = n0 + c0 + 8 * j;
+        const long long w2p = 2LL * p.wo * p.out_pitch;
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int r = 8 * i + sub;
-            uint4 q = *reinterpret_cast<const uint4*>(stage16 + r * 32 + ((j ^ ((r >> 1) & 3)) << 3));
-            if (has_res) {
-                // (the branch value was rounded to bf16 once above; it is ~0.3x the stream it is added to, so the
-                // extra rounding is well below the rounding of the sum)
-                const uint4 rr = rcur[i];
-                q.x = pack_bf16(bf16_lo(q.x) + bf16_lo(rr.x), bf16_hi(q.x) + bf16_hi(rr.x));
-                q.y = pack_bf16(bf16_lo(q.y) + bf16_lo(rr.y), bf16_hi(q.y) + bf16_hi(rr.y));
-                q.z = pack_bf16(bf16_lo(q.z) + bf16_lo(rr.z), bf16_hi(q.z) + bf16_hi(rr.z));
-                q.w = pack_bf16(bf16_lo(q.w) + bf16_lo(rr.w), bf16_hi(q.w) + bf16_hi(rr.w));
-            }
-            if (!ok[i] || ch >= p.n_store_limit) continue;
-            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.out_pitch + ch;
-            *reinterpret_cast<uint4*>(op) = q;
-            if (p.upsample2x) {  // the other three pixels of the 2x2 nearest-neighbour block
-                const long long w2p = 2LL * p.wo * p.out_pitch;
-                *reinterpret_cast<uint4*>(op + p.out_pitch) = q;
-                *reinterpret_cast<uint4*>(op + w2p) = q;
-                *reinterpret_cast<uint4*>(op + w2p + p.out_pitch) = q;
-            }
+            const long long m = m_base + r;
+            const uint4 q = *reinterpret_cast<const uint4*>(buf + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+            if (m >= p.M || ch >= p.n_store_limit) continue;
+            const int img = static_cast<int>(m / hw);
+            const int rem = static_cast<int>(m - static_cast<long long>(img) * hw);
+            const int oy = rem / p.wo;
+            const int ox = rem - oy * p.wo;
+            const long long orow = (static_cast<long long>(img) * 2 * p.ho + 2 * oy) * (2LL * p.wo) + 2 * ox;
+            __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow * p.out_pitch + ch;
+            *reinterpret_cast<uint4*>(op) = q;  // the 2x2 nearest-neighbour block
+            *reinterpret_cast<uint4*>(op + p.out_pitch) = q;
+            *reinterpret_cast<uint4*>(op + w2p) = q;
+            *reinterpret_cast<uint4*>(op + w2p + p.out_pitch) = q;
         }
         __syncwarp();  // staging tile is rewritten by the next chunk
+        lap(3);
+    };
+    auto release_tmem = [&]() {  // all TMEM reads of this accumulator stage done: hand it back to the MMA warp
+        ptx::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
+    };
+
+    uint32_t acc_a[32], acc_b[32];
+    ptx::tmem_ld_32x32(taddr0 + c_begin, acc_a);
+#pragma unroll 1
+    for (int c0 = c_begin; c0 < c_end; c0 += 64) {
+        ptx::tmem_ld_wait();
+        if (HALF_N > 32) ptx::tmem_ld_32x32(taddr0 + c0 + 32, acc_b);  // in flight during chunk c0
+        else release_tmem();
+        lap(1);
+        if (!(p.debug & 1)) chunk(acc_a, c0);
+        if (HALF_N > 32) {
+            ptx::tmem_ld_wait();
+            if (c0 + 64 < c_end) ptx::tmem_ld_32x32(taddr0 + c0 + 64, acc_a);
+            else release_tmem();
+            lap(1);
+            if (!(p.debug & 1)) chunk(acc_b, c0 + 32);
+        }
     }
 }
 
@@ -186,7 +246,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, uint32_t tadd
 // memory transposed ([pixel][32 channels] bf16) and re-read so that 4 lanes cover the 64 contiguous bytes this warp
 // owns of one pixel row.
 __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint32_t taddr0, float* stage_buf, int ch_warp,
-                                                      long long pix0, int lane, uint32_t full_addr, uint32_t aphase,
+                                                      long long pix0, int lane, int half, uint32_t full_addr, uint32_t aphase,
                                                       uint32_t empty_addr, long long* t_acc) {
     const int hw = p.ho * p.wo;
     const int sub = lane >> 2, j = lane & 3;
@@ -195,14 +255,22 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
     const float bias_own = (ch_own < p.cout) ? __ldg(p.bias + ch_own) : 0.f;
     const int ch = ch_warp + 8 * j;                         // transposed phase: this lane's 8 channels
     const bool has_res = p.residual != nullptr;
+    const bool generic_act = p.act == 2;
+    const float alpha_eff = p.act ? p.alpha : 1.0f;
+    const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
 
     const long long ta0 = t_acc ? clock64() : 0;
     ptx::mbar_wait_addr(full_addr, aphase);
     if (t_acc) *t_acc += clock64() - ta0;
     ptx::tc_fence_after();
+    long long tp = t_acc ? clock64() : 0;
+    auto lap = [&](int slot) {
+        if (t_acc) { const long long now = clock64(); t_acc[slot] += now - tp; tp = now; }
+    };
 
+    const int c_end = half * 128 + 128;  // the two warps of a lane quarter take 128 of the tile's 256 pixels each
 #pragma unroll 1
-    for (int c0 = 0; c0 < 256; c0 += 32) {
+    for (int c0 = half * 128; c0 < c_end; c0 += 32) {
         uint32_t acc[32];
         if (warp_has_channels) ptx::tmem_ld_32x32(taddr0 + c0, acc);
         // pixels of this chunk handled by this lane in the transposed phase, and their residual values
@@ -225,35 +293,44 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
             }
         }
         if (warp_has_channels) ptx::tmem_ld_wait();
-        if (c0 + 32 >= 256) {
+        if (c0 + 32 >= c_end) {
             ptx::tc_fence_before();
             __syncwarp();
             if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
         }
+        lap(1);
         if (!warp_has_channels || (p.debug & 1)) continue;
         // channel-major phase: + bias, LeakyReLU; element (pixel q, channel lane) -> stage_buf[q][lane] (fp32: one
         // conflict-free 128-byte row per store instruction)
+        if (!generic_act) {
 #pragma unroll
-        for (int q = 0; q < 32; ++q) {
-            float x = __uint_as_float(acc[q]) + bias_own;
-            if (p.act) x = x > 0.f ? x : x * p.alpha;
-            stage_buf[q * 32 + lane] = x;
+            for (int q = 0; q < 32; q += 2) {
+                const float2 x = bias_act2<false>(acc[q], acc[q + 1], bias_own, bias_own, alpha2);
+                stage_buf[q * 32 + lane] = x.x;
+                stage_buf[(q + 1) * 32 + lane] = x.y;
+            }
+        } else {
+#pragma unroll
+            for (int q = 0; q < 32; q += 2) {
+                const float2 x = bias_act2<true>(acc[q], acc[q + 1], bias_own, bias_own, alpha2);
+                stage_buf[q * 32 + lane] = x.x;
+                stage_buf[(q + 1) * 32 + lane] = x.y;
+            }
         }
         __syncwarp();
+        lap(2);
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int q = 8 * i + sub;
             const float4 lo = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j);
             const float4 hi = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j + 4);
-            uint4 v;
-            if (has_res) {
+            uint4 v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+            if (has_res) {  // same arithmetic as the normal mode: branch value rounded to bf16, bf16x2 add rounded once
                 const uint4 rr = res[i];
-                v.x = pack_bf16(lo.x + bf16_lo(rr.x), lo.y + bf16_hi(rr.x));
-                v.y = pack_bf16(lo.z + bf16_lo(rr.y), lo.w + bf16_hi(rr.y));
-                v.z = pack_bf16(hi.x + bf16_lo(rr.z), hi.y + bf16_hi(rr.z));
-                v.w = pack_bf16(hi.z + bf16_lo(rr.w), hi.w + bf16_hi(rr.w));
-            } else {
-                v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
+                v.x = add_bf16x2(v.x, rr.x);
+                v.y = add_bf16x2(v.y, rr.y);
+                v.z = add_bf16x2(v.z, rr.z);
+                v.w = add_bf16x2(v.w, rr.w);
             }
             if (!ok[i]) continue;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.out_pitch + ch;
@@ -266,6 +343,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
             }
         }
         __syncwarp();
+        lap(3);
     }
 }
 
@@ -285,11 +363,13 @@ __device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint
 //              [128r, 128r+128) and stages B rows [128r, 128r+128); the leader (rank 0) issues the MMAs, which
 //              read both CTAs' shared memory.  Per SM and K block this needs 16 KB of A + 16 KB of B instead of
 //              16 + 32 KB, which is what the L2->SM fill latency x shared-memory capacity product can sustain.
-template <int BLOCK_N, bool TWO>
+template <int BLOCK_N, bool TWO, bool SWAP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const ConvParams p) {
+conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
     using Cfg = TileCfg<BLOCK_N>;
     static_assert(!TWO || BLOCK_N == 256, "the CTA-pair kernel is built for 256-wide tiles");
+    static_assert(!SWAP || (BLOCK_N == 256 && !TWO), "the swapped mode is a single-CTA 128 x 256 kernel");
     constexpr int B_ROWS = TWO ? BLOCK_N / 2 : BLOCK_N;  // B rows this CTA stages per K block
     const int STAGES = p.num_stages;
 
@@ -305,7 +385,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // CTA and the ring carries only A — narrow layers are bound by the TMA issue rate, and this halves it.
     const bool b_res = !TWO && p.b_resident != 0;
     // swapped mode: slot 0 (the MMA's M side, 128 rows) holds filter rows, slot 1 (N side, 256 rows) holds pixels
-    const bool swap = !TWO && BLOCK_N == 256 && p.swap != 0;
+    constexpr bool swap = SWAP;
     const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
     const uint32_t b_bytes = B_ROWS * p.block_k * 2;
     uint8_t* bres = smem + SMEM_RING_OFF;
@@ -325,6 +405,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tma_prefetch_desc(&tmA);
         ptx::tma_prefetch_desc(&tmB);
     }
+    if (warp == 4 && lane == 0 && p.epi_mode == 0) ptx::tma_prefetch_desc(&tmOut);
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
@@ -332,7 +413,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
-            ptx::mbar_init(&tmem_empty_bar[i], TWO ? 8 : 4);  // one arrive per epilogue warp (of both CTAs)
+            ptx::mbar_init(&tmem_empty_bar[i], TWO ? 16 : (BLOCK_N < 64 ? 4 : 8));  // one arrive per epilogue warp (of both CTAs) draining the stage
         }
         ptx::mbar_init(bres_bar, 1);
         ptx::fence_barrier_init();
@@ -345,6 +426,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (TWO) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    // Programmatic dependent launch: the next layer's CTAs may be scheduled from here on (they take an SM as soon as
+    // this kernel's CTA leaves it and run their own set-up above while the rest of this grid finishes).  Warps that
+    // touch activations call grid_dep_wait() first: the previous layer is complete and visible after it.
+    ptx::grid_dep_launch();
 
     // Everything the single-thread producer / MMA loops need is copied into registers first: the inline-asm
     // "memory" clobbers would otherwise make the compiler re-read every p.* field from the constant bank on each
@@ -368,13 +453,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
         int stage = 0;
         uint32_t phase = 0;
-        long long t_wait = 0, t_start = clock64();
+        long long t_wait = 0;
         if (b_res && issuer && unit < num_tiles) {
             const uint32_t bar = ptx::smem_u32(bres_bar);
             ptx::mbar_arrive_expect_tx_addr(bar, b_bytes * nkb);
             for (int kb = 0; kb < nkb; ++kb)
                 ptx::tma_load_2d_addr(ptx::smem_u32(bres) + kb * b_bytes, mapB, bar, kb * block_k, 0);
         }
+        ptx::grid_dep_wait();  // weights above are constants; everything below reads the previous layer's output
+        const long long t_start = clock64();
         for (int tile = unit; tile < num_tiles && !(p.debug & 8); tile += units) {
             const int m_tile = tile / n_tiles_n;
             // normal: m0 = first output pixel (M side), n0 = first output channel (N side)
@@ -433,7 +520,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
         }
-        if (prof && lane == 0) { p.prof[blockIdx.x * 8 + 0] = clock64() - t_start; p.prof[blockIdx.x * 8 + 1] = t_wait; }
+        if (prof && lane == 0) { p.prof[blockIdx.x * 16 + 0] = clock64() - t_start; p.prof[blockIdx.x * 16 + 1] = t_wait; }
     } else if (warp == 1 && cta_rank == 0) {
         // ------------------------------------------------------------------ MMA issuer (leader CTA only)
         const uint32_t idesc = ptx::make_idesc_bf16_f32(TILE_M, BLOCK_N);
@@ -497,32 +584,42 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             __syncwarp();
         }
-        if (prof && lane == 0) { p.prof[blockIdx.x * 8 + 2] = clock64() - t_start; p.prof[blockIdx.x * 8 + 3] = t_full; p.prof[blockIdx.x * 8 + 4] = t_tmem; }
+        if (prof && lane == 0) { p.prof[blockIdx.x * 16 + 2] = clock64() - t_start; p.prof[blockIdx.x * 16 + 3] = t_full; p.prof[blockIdx.x * 16 + 4] = t_tmem; }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
-        const int group = (warp - 4) >> 2;  // which accumulator stage / tile parity this warp serves
+        const int half = (warp - 4) >> 2;   // which half of the tile's columns this warp drains
         const int quarter = warp & 3;       // TMEM lanes [32*quarter, 32*quarter + 32)
-        float* stage_buf = reinterpret_cast<float*>(smem + SMEM_STAGING_OFF + (warp - 4) * 4096);
-        const uint32_t taddr0 = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16) + group * BLOCK_N;
+        uint8_t* stage = smem + SMEM_STAGING_OFF + (warp - 4) * 4096;  // two 2 KB chunk buffers (swapped mode: one 4 KB)
+        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
         // the MMA issuer that waits for "accumulator drained" lives in the leader CTA
-        const uint32_t empty_addr = (tmem_empty_addr + 8u * group) & (TWO ? ptx::kPeerBitMask : 0xFFFFFFFFu);
-        int it = group;
-        long long t_acc = 0, t_start = clock64();
-        for (int tile = unit + group * units; tile < num_tiles; tile += 2 * units, it += 2) {
+        const uint32_t empty_mask = TWO ? ptx::kPeerBitMask : 0xFFFFFFFFu;
+        int it = 0;
+        int sbuf = 0;
+        ptx::grid_dep_wait();  // residual reads / output writes must not overtake the previous layer
+        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_start = clock64();
+        for (int tile = unit; tile < num_tiles; tile += units, ++it) {
+            const int as = it & 1;  // accumulator stage
+            if (BLOCK_N < 64 && as != half) continue;  // one-chunk tiles: the two warps of a lane quarter alternate tiles
             const uint32_t aphase = (it >> 1) & 1;
+            const uint32_t taddr0 = tlane + as * BLOCK_N;
+            const uint32_t full_addr = tmem_full_addr + 8u * as, empty_addr = (tmem_empty_addr + 8u * as) & empty_mask;
             const int m_tile = tile / n_tiles_n;
             if (swap) {
                 const int ch_warp = (tile - m_tile * n_tiles_n) * BLOCK_M + quarter * 32;
-                epilogue_tile_swapped(p, taddr0, stage_buf, ch_warp, static_cast<long long>(m_tile) * 256, lane,
-                                      tmem_full_addr + 8u * group, aphase, empty_addr, prof ? &t_acc : nullptr);
+                epilogue_tile_swapped(p, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256, lane,
+                                      half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
                 continue;
             }
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
             const long long m_base = static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
-            epilogue_tile<BLOCK_N>(p, taddr0, stage_buf, m_base, n0, lane, tmem_full_addr + 8u * group, aphase, empty_addr,
-                                   prof ? &t_acc : nullptr);
+            epilogue_tile<BLOCK_N>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
+                                   prof ? t_acc : nullptr);
         }
-        if (prof && warp == 4 && lane == 0) { p.prof[blockIdx.x * 8 + 5] = clock64() - t_start; p.prof[blockIdx.x * 8 + 6] = t_acc; }
+        if (lane == 0) ptx::tma_store_wait<0>();  // outstanding TMA stores read this CTA's shared memory
+        if (prof && warp == 4 && lane == 0) {
+            long long* o = p.prof + blockIdx.x * 16;
+            o[5] = clock64() - t_start; o[6] = t_acc[0]; o[7] = t_acc[1]; o[8] = t_acc[2]; o[9] = t_acc[3]; o[10] = t_acc[4]; o[11] = t_acc[5];
+        }
     }
 
     ptx::tc_fence_before();
@@ -553,9 +650,9 @@ void set_err(char* err, size_t n, const char* fmt, long long a = 0, long long b 
     if (err && n) snprintf(err, n, fmt, a, b, c);
 }
 
-template <int BN, bool TWO>
+template <int BN, bool TWO, bool SWAP = false>
 int set_smem_attr() {
-    return cudaFuncSetAttribute(conv_tc_kernel<BN, TWO>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess
+    return cudaFuncSetAttribute(conv_tc_kernel<BN, TWO, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess
                ? 0
                : -1;
 }
@@ -580,7 +677,7 @@ int conv_tc_init(char* err, size_t errlen) {
         cudaDriverGetVersion(&g_driver_version);
     }
     if (set_smem_attr<32, false>() || set_smem_attr<64, false>() || set_smem_attr<128, false>() ||
-        set_smem_attr<256, false>() || set_smem_attr<256, true>()) {
+        set_smem_attr<256, false>() || set_smem_attr<256, true>() || set_smem_attr<256, false, true>()) {
         set_err(err, errlen, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %lld",
                 static_cast<long long>(cudaGetLastError()));
         return -1;
@@ -655,8 +752,15 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     p.num_m_tiles = static_cast<int>(m_tiles);
     p.num_n_tiles = swap ? (d.cout + BLOCK_M - 1) / BLOCK_M : (d.cout + bn - 1) / bn;
     p.swap = swap;
+    if (d.cout > 1024) { set_err(err, errlen, "conv_tc: Cout=%lld exceeds the 1024-entry bias block", d.cout); return -1; }
+    if (!d.bias_host) { set_err(err, errlen, "conv_tc: bias_host is required"); return -1; }
+    memset(p.bias_c, 0, sizeof(p.bias_c));
+    memcpy(p.bias_c, d.bias_host, sizeof(float) * d.cout);
+    p.epi_mode = d.out_fp32 ? 1 : (d.upsample2x ? 2 : 0);
+    p.res_v8 = (d.residual && (reinterpret_cast<uintptr_t>(d.residual) & 31) == 0 && d.res_pitch % 16 == 0 && d.cout % 16 == 0) ? 1 : 0;
+    if (d.residual && p.epi_mode != 0 && !swap) { set_err(err, errlen, "conv_tc: a residual needs a plain bf16 output"); return -1; }
     p.bias = d.bias;
-    p.act = d.act;
+    p.act = d.act ? ((d.alpha >= 0.f && d.alpha <= 1.f) ? 1 : 2) : 0;  // 1: max(x, alpha x); 2: select form
     p.alpha = d.alpha;
     p.residual = d.residual;
     p.res_pitch = d.res_pitch;
@@ -708,8 +812,21 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map B encode failed (CUresult %lld)", r); return -1; }
     }
+    if (p.epi_mode == 0 && !swap) {
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.cout), static_cast<cuuint64_t>(M)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_pitch) * 2};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        r = g_encodeTiled(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map OUT encode failed (CUresult %lld)", r); return -1; }
+    } else {
+        L->tmOut = L->tmB;  // unused by these modes; any valid map
+    }
     L->block_n = bn;
     L->two_cta = two;
+    L->pdl = 1;
     const long long tiles = m_tiles * p.num_n_tiles;
     if (two) {
         const long long pairs = num_sms / 2;
@@ -750,30 +867,40 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
 }
 
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
-    dim3 grid(L.grid), block(NUM_THREADS);
+    static const bool no_pdl = getenv("FASTDET_NO_PDL") != nullptr;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(L.grid);
+    cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = L.smem_bytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    int na = 0;
     if (L.two_cta) {
-        cudaLaunchConfig_t cfg = {};
-        cfg.gridDim = grid;
-        cfg.blockDim = block;
-        cfg.dynamicSmemBytes = L.smem_bytes;
-        cfg.stream = stream;
-        cudaLaunchAttribute attr[1];
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2;
-        attr[0].val.clusterDim.y = 1;
-        attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr;
-        cfg.numAttrs = 1;
-        return cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, L.tmA, L.tmB, L.p) == cudaSuccess ? 0 : -1;
+        attr[na].id = cudaLaunchAttributeClusterDimension;
+        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.y = 1;
+        attr[na].val.clusterDim.z = 1;
+        ++na;
     }
-    switch (L.block_n) {
-        case 32: conv_tc_kernel<32, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
-        case 64: conv_tc_kernel<64, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
-        case 128: conv_tc_kernel<128, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
-        case 256: conv_tc_kernel<256, false><<<grid, block, L.smem_bytes, stream>>>(L.tmA, L.tmB, L.p); break;
+    if (L.pdl && !no_pdl) {
+        // programmatic dependent launch: this kernel may start while its predecessor in the stream drains
+        attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[na].val.programmaticStreamSerializationAllowed = 1;
+        ++na;
+    }
+    cfg.attrs = attr;
+    cfg.numAttrs = na;
+    cudaError_t e;
+    if (L.two_cta) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, L.tmA, L.tmB, L.tmOut, L.p);
+    else if (L.p.swap) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, false, true>, L.tmA, L.tmB, L.tmOut, L.p);
+    else switch (L.block_n) {
+        case 32: e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false>, L.tmA, L.tmB, L.tmOut, L.p); break;
+        case 64: e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<64, false>, L.tmA, L.tmB, L.tmOut, L.p); break;
+        case 128: e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<128, false>, L.tmA, L.tmB, L.tmOut, L.p); break;
+        case 256: e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, false>, L.tmA, L.tmB, L.tmOut, L.p); break;
         default: return -1;
     }
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return e == cudaSuccess ? 0 : -1;
 }
 
 }  // namespace fd

@@ -21,7 +21,8 @@ struct ConvDesc {
     int cout, ksize, stride;
     int pad_lo, pad_hi;  // begin / end padding (same for h and w)
     const __nv_bfloat16* w;  // [cout][ksize*ksize*cin], tap-major then channel
-    const float* bias;       // [>= round_up(cout, 256)] fp32 (BatchNorm folded in)
+    const float* bias;       // device, [>= round_up(cout, 256)] fp32 (BatchNorm folded in)
+    const float* bias_host;  // the same values on the host (they travel in the kernel's parameter block)
     int act;                 // 0 = linear, 1 = LeakyReLU(alpha)
     float alpha;
     // optional residual (added after the activation, like ONNX Add after LeakyRelu)
@@ -53,16 +54,22 @@ struct ConvParams {
     long long out_pitch;
     int out_fp32, upsample2x;
     int n_store_limit;
-    long long* prof;  // developer: per-CTA cycle counters [grid][8] (null in production)
+    long long* prof;  // developer: per-CTA cycle counters [grid][16] (null in production)
     int debug;  // developer switches (0 in production): 1 skip epilogue stores, 2 skip A loads, 4 skip MMA issue
+    int res_v8;    // 1: residual rows are 32-byte aligned -> 256-bit loads
+    int epi_mode;  // 0 bf16 slice through a TMA store (+ residual), 1 fp32 head rows, 2 bf16 with x2 upsampling
+    // the layer's bias, read by the epilogue from the constant bank with a warp-uniform index (shared-memory and
+    // L1 loads queue behind the operand traffic in this kernel; the constant cache does not)
+    float bias_c[1024];
 };
 
 struct ConvLaunch {
-    CUtensorMap tmA, tmB;
+    CUtensorMap tmA, tmB, tmOut;  // tmOut: {channels, pixel rows} of the output slice, 32 x 32 boxes, SWIZZLE_64B
     ConvParams p;
     int block_n;
     int two_cta;  // 1: CTA-pair kernel (cta_group::2, 256 x 256 tiles)
     int grid;
+    int pdl;      // 1: launched with programmatic stream serialisation (overlaps the previous kernel's drain)
     size_t smem_bytes;
     double flops;  // algorithmic: 2*M*cout*K
 };

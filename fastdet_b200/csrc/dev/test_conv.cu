@@ -76,7 +76,7 @@ static int run_case(const Case& c, int num_sms) {
     memset(&d, 0, sizeof(d));
     d.n = c.n; d.hi = c.h; d.wi = c.w; d.cin = c.cin; d.in_pitch = in_pitch; d.in = dx;
     d.cout = c.cout; d.ksize = c.k; d.stride = c.stride; d.pad_lo = c.pad_lo; d.pad_hi = c.pad_hi;
-    d.w = dw; d.bias = dbias; d.act = c.act; d.alpha = 0.1f;
+    d.w = dw; d.bias = dbias; d.bias_host = bias.data(); d.act = c.act; d.alpha = 0.1f;
     d.residual = dr; d.res_pitch = c.cout;
     d.out = dout; d.out_pitch = out_pitch; d.out_fp32 = c.fp32; d.upsample2x = c.upsample;
     ConvLaunch L;
@@ -171,7 +171,7 @@ static void time_case(const char* name, int n, int h, int cin, int cout, int k, 
     CK(cudaMemset(dbias, 0, 1024 * 4));
     d.n = n; d.hi = h; d.wi = h; d.cin = cin; d.in_pitch = cin; d.in = dx;
     d.cout = cout; d.ksize = k; d.stride = stride; d.pad_lo = pad; d.pad_hi = pad;
-    d.w = dw; d.bias = dbias; d.act = 1; d.alpha = 0.1f;
+    static float zero_bias[1024]; d.w = dw; d.bias = dbias; d.bias_host = zero_bias; d.act = 1; d.alpha = 0.1f;
     d.out = dout; d.out_pitch = cout;
     ConvLaunch L;
     char err[256] = {0};
@@ -194,12 +194,14 @@ static void time_case(const char* name, int n, int h, int cin, int cout, int k, 
     ms /= iters;
     const double bytes = (in_e + out_e + w_e) * 2.0;
     if (getenv("FD_PROF")) {
-        long long* dprof; CK(cudaMalloc(&dprof, 8 * 8 * 256)); CK(cudaMemset(dprof, 0, 8 * 8 * 256));
+        long long* dprof; CK(cudaMalloc(&dprof, 8 * 16 * 256)); CK(cudaMemset(dprof, 0, 8 * 16 * 256));
         L.p.prof = dprof;
         conv_tc_launch(L, 0); CK(cudaDeviceSynchronize());
-        long long hp[8 * 256]; CK(cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost));
-        double a[8] = {0};
-        for (int c = 0; c < L.grid; ++c) for (int q = 0; q < 8; ++q) a[q] += double(hp[c * 8 + q]) / L.grid;
+        static long long hp[16 * 256]; CK(cudaMemcpy(hp, dprof, sizeof(hp), cudaMemcpyDeviceToHost));
+        double a[16] = {0}, mx[16] = {0};
+        for (int c = 0; c < L.grid; ++c) for (int q = 0; q < 16; ++q) { a[q] += double(hp[c * 16 + q]) / L.grid; if (hp[c * 16 + q] > mx[q]) mx[q] = double(hp[c * 16 + q]); }
+        printf("    epilogue phases (avg cycles/CTA, group 0 warp 0): wait-acc %.0f | tmem-ld %.0f | res-fetch+bias loads %.0f | math %.0f | stage(STS+sync) %.0f | transposed read+stores %.0f\n", a[6], a[7], a[11], a[10], a[8], a[9]);
+        printf("    prof max over CTAs: producer %.0f mma %.0f epi %.0f cycles; launch %.1f us -> %.0f cycles at 1.9 GHz\n", mx[0], mx[2], mx[5], ms * 1e3, ms * 1e-3 * 1.9e9);
         const double tiles_per_cta = double(L.p.num_m_tiles) * L.p.num_n_tiles / L.grid;
         printf("    prof(avg cycles/CTA, %.1f tiles x %d kb): producer total %.0f wait-empty %.0f | mma total %.0f wait-full %.0f wait-tmem %.0f | epi(g0) total %.0f wait-acc %.0f | per kb: %.0f cyc\n",
                tiles_per_cta, L.p.num_k_blocks, a[0], a[1], a[2], a[3], a[4], a[5], a[6], a[2] / (tiles_per_cta * L.p.num_k_blocks));
@@ -310,6 +312,11 @@ int main(int argc, char** argv) {
         for (int g : {148, 74, 37}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, 7, 0, g);
         for (int g : {148, 74, 37}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, 0, 0, g);
         for (int g : {148, 74, 37}) time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0, 0, 0, g);
+    }
+    if (!strcmp(mode, "epi")) {
+        for (int dbg : {0, 1, 2, 4, 6, 8}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, dbg);
+        for (int dbg : {0, 1, 2, 4, 6}) time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0, dbg);
+        for (int dbg : {0, 4}) time_case("1x1 256->128 @52 bs64", 64, 52, 256, 128, 1, 1, sms, 0, dbg);
     }
     if (!strcmp(mode, "probe")) {
         for (int dbg : {0, 1, 2, 4, 3, 5, 6, 7}) time_case("3x3 32->64 s2 @416 bs64", 64, 416, 32, 64, 3, 2, sms, 0, dbg);

@@ -268,6 +268,7 @@ conv0_tc_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wg
     __syncthreads();
     ptx::tc_fence_after();
     const uint32_t tmem = tmem_slot;
+    ptx::grid_dep_launch();  // the next layer may start its set-up on SMs as they drain (it waits before reading)
     const uint32_t idesc = ptx::make_idesc_bf16_f32(128, cout);
     const uint64_t adesc = ptx::make_kmajor_desc(ptx::smem_u32(sA), 512, 4);
     const uint64_t bdesc = ptx::make_kmajor_desc(ptx::smem_u32(sB), 512, 4);

@@ -23,6 +23,23 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
     return r;
 }
 
+// 32-byte read-only load (one full L2 sector per lane), no L1 allocation
+struct U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ U32x8 ld_nc_v8(const void* p) {
+    U32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p));
+    return r;
+}
+
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: returns once every grid this launch depends on has completed and its writes are visible (no-op for a
+// launch without the programmatic-serialisation attribute).  launch_dependents: lets the next kernel in the
+// stream start its prologue (barrier init, TMEM allocation, weight prefetch) on SMs as they drain.
+__device__ __forceinline__ void grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

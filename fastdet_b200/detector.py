@@ -11,7 +11,8 @@ Soft-NMS order; same exception types (``ValueError('invalid image size')`` :132,
 named ``detector`` (:17) and needs nothing else.
 
 Additive extras (not in the reference): ``image_size=`` and ``device=`` keyword arguments,
-``perform_batch`` / ``perform_frames`` for decoded RGB frames, ``forward_raw`` for parity tests.
+``perform_batch`` / ``perform_frames`` for decoded RGB frames, ``perform_stream`` (pipelined batches),
+``forward_raw`` for parity tests.
 ``mode`` is accepted and stored like the reference does; every mode runs on the B200 — there is no
 CPU execution provider here and no fallback.
 """
@@ -113,6 +114,34 @@ class ONNXDetector(Detector):
         return out
 
     perform_batch = perform_frames
+
+    @staticmethod
+    def _tuples(dets, counts):
+        out = []
+        for f in range(dets.shape[0]):
+            d = dets[f, :counts[f]]
+            out.append([(int(k), float(c), float(x), float(y), float(w), float(h))
+                        for k, c, x, y, w, h in zip(d['klass'], d['conf'], d['x'], d['y'], d['w'], d['h'])])
+        return out
+
+    def perform_stream(self, batches, threshold=0.1, allow_resize=False):
+        """Generator over an iterable of [n, h, w, 3] u8 batches: yields one list of per-frame result lists per
+        batch, in order, with two batches in flight (fd_submit / fd_collect) so the host->device copy of batch
+        i+1 overlaps the compute of batch i.  Same results as perform_frames on each batch."""
+        self.ANCHORS[self.model.n_heads]
+        pending = []  # slots in submission order
+        slot = 0
+        for frames in batches:
+            frames = np.ascontiguousarray(frames, np.uint8)
+            if len(pending) == _native.FD_MAX_SLOTS:
+                dets, counts, _ = self.model.collect(pending.pop(0))
+                yield self._tuples(dets, counts)
+            self.model.submit(slot, frames, threshold, allow_resize=allow_resize, max_det=self.max_det)
+            pending.append(slot)
+            slot = (slot + 1) % _native.FD_MAX_SLOTS
+        for s in pending:
+            dets, counts, _ = self.model.collect(s)
+            yield self._tuples(dets, counts)
 
     def forward_raw(self, frames):
         """Raw head tensors (what ``model.run`` returns in the reference): list of f32 [n, C, H, W]."""

@@ -34,7 +34,8 @@ extern "C" {
 #define FD_ERR_SIZE (-5)     /* frame size not accepted (reference: ValueError('invalid image size'), detector.py:132) */
 
 #define FD_MAX_HEADS 4
-#define FD_ABI_VERSION 1
+#define FD_MAX_SLOTS 2 /* batches in flight through fd_submit / fd_collect */
+#define FD_ABI_VERSION 2
 
 typedef struct fd_model fd_model;
 
@@ -100,6 +101,17 @@ int fd_fetch(fd_model* m, int n, fd_det* out, int32_t* counts, int32_t* total, v
 /* preprocess -> forward -> postprocess -> fetch; synchronous; frames in host (or device) memory. */
 int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
               double threshold, int max_det, fd_det* out, int32_t* counts);
+
+/* Pipelined form of fd_detect for callers that serve a stream of batches (the reference's server loop calls
+ * perform() once per UDP payload, server/server.py:225-241; a batching front end calls these instead).
+ * fd_submit enqueues copy -> forward -> postprocess -> result copy for ring slot `slot` (0 .. FD_MAX_SLOTS-1) and
+ * returns without waiting; the host->device copy runs on its own stream, so it overlaps the previous slot's
+ * compute.  `frames` must stay valid (and should be pinned) until fd_collect(slot) returns.  fd_collect blocks
+ * until the slot's results are on the host and copies out counts[n] and out[n][max_det]; total may be NULL.
+ * Results are identical to fd_detect on the same frames. */
+int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, int src_h, int on_device,
+              int allow_resize, double threshold, int max_det);
+int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* total);
 
 /* ---- parity / profiling hooks (synchronous; host pointers) ---- */
 /* Raw head tensor `head` of the last forward as f32 NCHW [n, C, H, W] — what model.run returns. */

@@ -274,6 +274,23 @@ def _class_gap(heads, box, nc):
     raise IndexError(box)
 
 
+def _kept_after_nudge(heads, nc, thr, box, delta):
+    """Oracle Soft-NMS re-run with candidate `box`'s score moved by `delta`: its decayed score if it is selected,
+    else None.  Soft-NMS is order-sensitive: two overlapping boxes whose scores are closer than the bf16 noise swap
+    roles (the one picked first suppresses the other), which is the 'near-threshold tie' the spec allows."""
+    cands, first = [], 0
+    for anchors, out in zip(ref_post.ANCHORS[len(heads)], heads):
+        m = np.ascontiguousarray(out[0].transpose(1, 2, 0))
+        cands.extend(ref_post.decode_head_fast(anchors, m, nc, (416, 416), thr - abs(delta), first))
+        first += m.shape[0] * m.shape[1] * 3
+    cands = [(c[0], c[1], c[2] + (delta if c[0] == box else 0.0)) + tuple(c[3:]) for c in cands]
+    cands = [c for c in cands if c[2] >= thr or c[0] == box]
+    for score, c in ref_post.soft_nms(cands, thr - abs(delta)):
+        if c[0] == box:
+            return score
+    return None
+
+
 @pytest.mark.parametrize("arch,nc,seed", [("tiny", 80, 1), ("rsu", 9, 3), ("full", 80, 2)])
 def test_detections_match_oracle(arch, nc, seed):
     """ONNXDetector.perform (PNG bytes in, tuples out) against the oracle's restatement of the reference's perform
@@ -307,7 +324,9 @@ def test_detections_match_oracle(arch, nc, seed):
             solid = min(w[1], dec) >= thr + margin
             g = gpu.get(box)
             if g is None:
-                assert not solid, ("reference detection lost", w, dec)
+                # lost on the GPU: allowed when the reference's own decision flips under a score nudge of the margin
+                nudged = _kept_after_nudge(heads, nc, thr, box, -margin) if solid else None
+                assert not solid or nudged is None or nudged < thr + margin, ("reference detection lost", w, dec, nudged)
                 n_soft += 1
                 continue
             if int(g["klass"]) != w[0]:
@@ -322,8 +341,11 @@ def test_detections_match_oracle(arch, nc, seed):
                 continue
             # not kept by the reference: either it never cleared the threshold there, or Soft-NMS decayed it away
             final = left.get(box)
-            assert float(g["conf"]) <= thr + margin or (final is not None and final >= thr - margin), \
-                ("spurious detection", dict(zip(g.dtype.names, g.tolist())), final)
+            ok = float(g["conf"]) <= thr + margin or (final is not None and final >= thr - margin)
+            if not ok:  # Soft-NMS order flip between near-equal overlapping boxes?
+                nudged = _kept_after_nudge(heads, nc, thr, box, margin)
+                ok = nudged is not None and nudged >= thr - margin
+            assert ok, ("spurious detection", dict(zip(g.dtype.names, g.tolist())), final)
             n_soft += 1
     assert n_solid >= 5
     ious, dconfs = np.array(ious), np.array(dconfs)
@@ -374,3 +396,32 @@ def test_full_size_batch64_properties():
     assert np.array_equal(c4, counts[:4])
     for f in range(4):
         assert np.array_equal(d4[f, :c4[f]], dets[f, :counts[f]])
+
+
+def test_pipelined_submit_collect_equals_detect():
+    """fd_submit / fd_collect (two batches in flight, H2D overlapped with compute) return exactly what the
+    synchronous fd_detect returns for the same frames, in submission order, including after slot reuse."""
+    data, m = get_model("tiny", 80, 416, 1)
+    batches = [frames_for(3, 416, 400 + 10 * k) for k in range(5)]
+    want = [m.detect(b, 0.1, max_det=128) for b in batches]
+    got = []
+    m.submit(0, batches[0], 0.1, max_det=128)
+    for k in range(1, 5):
+        m.submit(k % 2, batches[k], 0.1, max_det=128)
+        got.append(m.collect((k - 1) % 2))
+    got.append(m.collect(0))
+    for (wd, wc), (gd, gc, gt) in zip(want, got):
+        assert np.array_equal(wc, gc) and (gt >= gc).all()
+        for f in range(3):
+            assert np.array_equal(wd[f, :wc[f]], gd[f, :gc[f]])
+    # protocol errors are reported, not fatal
+    m.submit(0, batches[0], 0.1, max_det=128)
+    with pytest.raises(_native.NativeError):
+        m.submit(0, batches[1], 0.1, max_det=128)  # slot busy
+    m.collect(0)
+    with pytest.raises(ValueError, match="invalid image size"):
+        m.submit(1, np.zeros((1, 300, 300, 3), np.uint8), 0.1)
+    # the detector-level generator: same per-frame tuples as perform_frames
+    det = fdet.ONNXDetector(data, num_classes=80, max_det=128)
+    streamed = list(det.perform_stream(batches, threshold=0.1))
+    assert streamed == [det.perform_frames(b, threshold=0.1) for b in batches]
