@@ -24,6 +24,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <type_traits>
+
 namespace fd {
 
 static constexpr int BLOCK_M = 128;
@@ -348,13 +350,11 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
 }
 
 template <int KS, bool TWO>
-__device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc0,
-                                           uint32_t alt = 0) {
+__device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, bool acc0) {
 #pragma unroll
     for (int k = 0; k < KS; ++k) {
-        const uint32_t d = tmem_d ^ ((k & 1) ? alt : 0u);  // alt != 0 only in a timing experiment (debug 64)
-        if (TWO) ptx::umma2_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
-        else ptx::umma_bf16(d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
+        if (TWO) ptx::umma2_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
+        else ptx::umma_bf16(tmem_d, adesc + 2 * k, bdesc + 2 * k, idesc, (acc0 || k > 0) ? 1u : 0u);
     }
 }
 
@@ -425,7 +425,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     ptx::tc_fence_before();
     if (TWO) ptx::cluster_sync(); else __syncthreads();
     ptx::tc_fence_after();
-    const uint32_t tmem_base = *tmem_slot;
+    const uint32_t tmem_base_v = *tmem_slot;
     // Programmatic dependent launch: the next layer's CTAs may be scheduled from here on (they take an SM as soon as
     // this kernel's CTA leaves it and run their own set-up above while the rest of this grid finishes).  Warps that
     // touch activations call grid_dep_wait() first: the previous layer is complete and visible after it.
@@ -434,9 +434,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // Everything the single-thread producer / MMA loops need is copied into registers first: the inline-asm
     // "memory" clobbers would otherwise make the compiler re-read every p.* field from the constant bank on each
     // k-block, and integer divisions per k-block put ~700 dependent cycles in the producer's way (measured).
-    const uint32_t bar_base = ptx::smem_u32(full_bar);       // full[i] at +8i, empty[i] at +8(MAX_STAGES+i)
-    const uint32_t ring_base = ptx::smem_u32(ring);
-    const uint32_t tmem_full_addr = ptx::smem_u32(tmem_full_bar), tmem_empty_addr = ptx::smem_u32(tmem_empty_bar);
+    const uint32_t bar_base_v = ptx::smem_u32(full_bar);       // full[i] at +8i, empty[i] at +8(MAX_STAGES+i)
+    const uint32_t ring_base_v = ptx::smem_u32(ring);
+    const uint32_t tmem_full_addr_v = ptx::smem_u32(tmem_full_bar), tmem_empty_addr_v = ptx::smem_u32(tmem_empty_bar);
     const int nkb = p.num_k_blocks, cin_blocks = p.cin_blocks, ksize = p.ksize, block_k = p.block_k;
     const int n_tiles_n = p.num_n_tiles;
     const bool prof = p.prof != nullptr;
@@ -447,6 +447,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // The whole warp walks the loop (warp-uniform control flow keeps addresses and coordinates in uniform
         // registers); one elected lane issues.
         const bool issuer = ptx::elect_one();
+        const uint32_t ring_base = __shfl_sync(0xffffffffu, ring_base_v, 0);  // warp-uniform for the compiler (see the MMA warp)
+        const uint32_t bar_base = __shfl_sync(0xffffffffu, bar_base_v, 0);
         const bool im2col = p.a_im2col != 0, load_a = !(p.debug & 2);
         const int ho_wo = p.ho * p.wo, wo = p.wo, cstride = p.stride, pad = p.pad_lo;
         const uint32_t tx_bytes = ((load_a ? a_bytes : 0u) + (b_res ? 0u : b_bytes)) * (TWO ? 2u : 1u);
@@ -528,69 +530,85 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t layout = (block_k == 64) ? 2u : (block_k == 32 ? 4u : 6u);
         const uint32_t sbo = 16u * block_k;  // 8 rows x swizzle span
         const int k_steps = (p.debug & 4) ? 0 : block_k / 16;
+        // shared-memory / TMEM base addresses are the same in every lane, but the compiler cannot see that (they come
+        // from a cvta and a shared-memory load): a broadcast shuffle marks them warp-uniform
+        const uint32_t ring_base = __shfl_sync(0xffffffffu, ring_base_v, 0);
+        const uint32_t bar_base = __shfl_sync(0xffffffffu, bar_base_v, 0);
+        const uint32_t tmem_base = __shfl_sync(0xffffffffu, tmem_base_v, 0);
+        const uint32_t tmem_full_addr = __shfl_sync(0xffffffffu, tmem_full_addr_v, 0);
+        const uint32_t tmem_empty_addr = __shfl_sync(0xffffffffu, tmem_empty_addr_v, 0);
         const uint64_t desc0 = ptx::make_kmajor_desc(ring_base, sbo, layout);  // stage 0, A operand
         const uint32_t stage_units = stage_bytes >> 4, sub_units = sub_bytes >> 4, a_units = a_bytes >> 4;
         const bool issuer = ptx::elect_one();
-        const uint64_t bres_desc0 = ptx::make_kmajor_desc(ptx::smem_u32(bres), sbo, layout);
+        const uint64_t bres_desc0 = ptx::make_kmajor_desc(__shfl_sync(0xffffffffu, ptx::smem_u32(bres), 0), sbo, layout);
         const uint32_t b_units = b_bytes >> 4;
         if (b_res && unit < num_tiles) {
             ptx::mbar_wait(bres_bar, 0);
             ptx::tc_fence_after();
         }
-        int stage = 0;
-        uint32_t phase = 0;
-        int it = 0;
         long long t_full = 0, t_tmem = 0, t_start = clock64();
-        for (int tile = unit; tile < num_tiles; tile += units, ++it) {
-            const int as = it & 1;
-            const uint32_t aphase = (it >> 1) & 1;
-            const long long tq0 = prof ? clock64() : 0;
-            ptx::mbar_wait_addr(tmem_empty_addr + 8u * as, aphase ^ 1);
-            if (prof) t_tmem += clock64() - tq0;
-            ptx::tc_fence_after();
-            const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-            for (int kb = 0; kb < nkb; kb += kps) {
-                const int nsub = (nkb - kb < kps) ? nkb - kb : kps;
-                const uint32_t full_addr = bar_base + 8u * stage;
-                const long long tf0 = prof ? clock64() : 0;
-                if (!(p.debug & 8)) ptx::mbar_wait_addr(full_addr, phase);  // debug 8: MMA-only (operands = whatever is in smem)
-                if (prof) t_full += clock64() - tf0;
+        const bool skip_full_wait = (p.debug & 8) != 0;  // developer: MMA-only run (operands = whatever is in smem)
+        // The loop is walked by the whole warp with every address / descriptor a warp-uniform value computed OUTSIDE the
+        // elected lane's branch: that keeps them in uniform registers, so a tcgen05.mma costs one UIADD3.64 per operand
+        // instead of a chain of R2UR moves (the narrow layers are bound by this warp's issue rate: ~150 cycles per MMA
+        // before, against 48 the tensor core needs at N = 64 — dev/mma_rate.cu).
+        auto run = [&](auto ks_tag) {
+            constexpr int KS = decltype(ks_tag)::value;  // MMAs (16-wide K steps) per K block
+            int stage = 0, it = 0;
+            uint32_t phase = 0, stage_off = 0;
+            for (int tile = unit; tile < num_tiles; tile += units, ++it) {
+                const int as = it & 1;
+                const uint32_t aphase = (it >> 1) & 1;
+                const long long tq0 = prof ? clock64() : 0;
+                ptx::mbar_wait_addr(tmem_empty_addr + 8u * as, aphase ^ 1);
+                if (prof) t_tmem += clock64() - tq0;
                 ptx::tc_fence_after();
-                if (issuer) {
+                const uint32_t tmem_d = tmem_base + as * BLOCK_N;
+                uint32_t accumulate = 0, bres_off = 0;
+                for (int kb = 0; kb < nkb; kb += kps) {
+                    const int nsub = (nkb - kb < kps) ? nkb - kb : kps;
+                    const uint32_t full_addr = bar_base + 8u * stage;
+                    const long long tf0 = prof ? clock64() : 0;
+                    if (!skip_full_wait) ptx::mbar_wait_addr(full_addr, phase);
+                    if (prof) t_full += clock64() - tf0;
+                    ptx::tc_fence_after();
+                    uint64_t adesc = desc0 + stage_off;
                     for (int sb = 0; sb < nsub; ++sb) {
-                        const uint64_t adesc = desc0 + static_cast<uint64_t>(stage * stage_units + sb * sub_units);
-                        const uint64_t bdesc = b_res ? bres_desc0 + static_cast<uint64_t>((kb + sb) * b_units) : adesc + a_units;
-                        // 16 elements (32 B) along K inside the swizzle span per MMA: +2 in 16-byte units.  Unrolled
-                        // with compile-time counts so the descriptor arithmetic of the MMAs overlaps instead of forming
-                        // a serial chain in front of every tcgen05.mma (measured: ~200 cycles per MMA with a runtime loop).
-                        const bool acc0 = (kb | sb) != 0;
-                        const uint32_t alt = (p.debug & 64) ? static_cast<uint32_t>(BLOCK_N) : 0u;
-                        if (k_steps == 4) issue_mmas<4, TWO>(tmem_d, adesc, bdesc, idesc, acc0, alt);
-                        else if (k_steps == 2) issue_mmas<2, TWO>(tmem_d, adesc, bdesc, idesc, acc0, alt);
-                        else if (k_steps == 1) issue_mmas<1, TWO>(tmem_d, adesc, bdesc, idesc, acc0, alt);
+                        const uint64_t bdesc = b_res ? bres_desc0 + bres_off : adesc + a_units;
+                        // 16 elements (32 B) along K inside the swizzle span per MMA: +2 in 16-byte units
+                        if (issuer) issue_mmas<KS, TWO>(tmem_d, adesc, bdesc, idesc, accumulate != 0);
+                        accumulate = 1;
+                        adesc += sub_units;
+                        bres_off += b_units;
                     }
-                    // smem slot free (in both CTAs) once these MMAs retire
-                    if (p.debug & 16) {
-                    } else if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
-                    else ptx::umma_commit_addr(full_addr + 8u * MAX_STAGES);
+                    if (issuer) {  // smem slot free (in both CTAs) once these MMAs retire
+                        if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
+                        else ptx::umma_commit_addr(full_addr + 8u * MAX_STAGES);
+                    }
+                    __syncwarp();
+                    stage_off += stage_units;
+                    if (++stage == STAGES) { stage = 0; stage_off = 0; phase ^= 1; }
+                }
+                // accumulator complete (each CTA of a pair drains its own 128 rows)
+                if (issuer) {
+                    if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, 3);
+                    else ptx::umma_commit_addr(tmem_full_addr + 8u * as);
                 }
                 __syncwarp();
-                if (++stage == STAGES) { stage = 0; phase ^= 1; }
             }
-            // accumulator complete (each CTA of a pair drains its own 128 rows)
-            if (issuer) {
-                if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, 3);
-                else ptx::umma_commit_addr(tmem_full_addr + 8u * as);
-            }
-            __syncwarp();
-        }
+        };
+        if (k_steps == 4) run(std::integral_constant<int, 4>{});
+        else if (k_steps == 2) run(std::integral_constant<int, 2>{});
+        else if (k_steps == 1) run(std::integral_constant<int, 1>{});
+        else run(std::integral_constant<int, 0>{});
         if (prof && lane == 0) { p.prof[blockIdx.x * 16 + 2] = clock64() - t_start; p.prof[blockIdx.x * 16 + 3] = t_full; p.prof[blockIdx.x * 16 + 4] = t_tmem; }
     } else if (warp >= 4) {
         // ------------------------------------------------------------------ epilogue
         const int half = (warp - 4) >> 2;   // which half of the tile's columns this warp drains
         const int quarter = warp & 3;       // TMEM lanes [32*quarter, 32*quarter + 32)
         uint8_t* stage = smem + SMEM_STAGING_OFF + (warp - 4) * 4096;  // two 2 KB chunk buffers (swapped mode: one 4 KB)
-        const uint32_t tlane = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+        const uint32_t tmem_full_addr = tmem_full_addr_v, tmem_empty_addr = tmem_empty_addr_v;
+        const uint32_t tlane = tmem_base_v + (static_cast<uint32_t>(quarter * 32) << 16);
         // the MMA issuer that waits for "accumulator drained" lives in the leader CTA
         const uint32_t empty_mask = TWO ? ptx::kPeerBitMask : 0xFFFFFFFFu;
         int it = 0;
@@ -626,8 +644,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (TWO) ptx::cluster_sync(); else __syncthreads();
     if (warp == 2) {
         ptx::tc_fence_after();
-        if (TWO) ptx::tmem_dealloc2(tmem_base, Cfg::TMEM_COLS);
-        else ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (TWO) ptx::tmem_dealloc2(tmem_base_v, Cfg::TMEM_COLS);
+        else ptx::tmem_dealloc(tmem_base_v, Cfg::TMEM_COLS);
     }
 }
 
