@@ -703,6 +703,19 @@ int conv_tc_init(char* err, size_t errlen) {
     return 0;
 }
 
+int encode_tiled_bf16(CUtensorMap* out, void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides_bytes, const unsigned* box, int swizzle) {
+    if (!g_encodeTiled && conv_tc_init(nullptr, 0)) return -1;
+    cuuint64_t d[5], st[4];
+    cuuint32_t b[5], es[5];
+    for (int i = 0; i < rank; ++i) { d[i] = dims[i]; b[i] = box[i]; es[i] = 1; }
+    for (int i = 0; i + 1 < rank; ++i) st[i] = strides_bytes[i];
+    const CUtensorMapSwizzle sw = swizzle == 3 ? CU_TENSOR_MAP_SWIZZLE_128B : swizzle == 2 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                  : swizzle == 1 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE;
+    return g_encodeTiled(out, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, rank, base, d, st, b, es, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
+                         CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS ? 0 : -1;
+}
+
 static int choose_block_n(int cout, long long m_tiles, int num_sms) {
     (void)m_tiles; (void)num_sms;
     // One 128 x N x 16 MMA reads A (4 KB) + B (N*32 B) from shared memory; at N = 128 that is exactly the

@@ -79,6 +79,10 @@ struct ConvLaunch {
 // Returns 0 on success; on failure writes a message to err (if non-null).
 int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* out, char* err, size_t errlen);
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);
+// Tiled bf16 tensor map (rank 2..5) through the driver entry point this library resolves at run time.
+// swizzle: 0 none, 1 32 B, 2 64 B, 3 128 B.  Returns 0 on success.
+int encode_tiled_bf16(CUtensorMap* out, void* base, int rank, const unsigned long long* dims,
+                      const unsigned long long* strides_bytes, const unsigned* box, int swizzle);
 // One-time per device: opt in to the large dynamic shared memory the kernels need.
 int conv_tc_init(char* err, size_t errlen);
 

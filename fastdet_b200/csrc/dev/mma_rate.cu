@@ -14,7 +14,7 @@ __device__ __forceinline__ void umma_ts(uint32_t d, uint32_t a_tmem, uint64_t bd
 }
 
 template <bool TS>
-__global__ void __launch_bounds__(128, 1) rate_kernel(int m, int n, int iters, int two_acc, long long* out) {
+__global__ void __launch_bounds__(128, 1) rate_kernel(int m, int n, int iters, int two_acc, long long* out, int noswz_sbo = 0) {
     extern __shared__ uint8_t raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(raw) + 1023) & ~uintptr_t(1023));
     __shared__ uint64_t bar;
@@ -29,8 +29,12 @@ __global__ void __launch_bounds__(128, 1) rate_kernel(int m, int n, int iters, i
     const uint32_t tmem = slot;
     if (threadIdx.x == 0) {
         const uint32_t idesc = ptx::make_idesc_bf16_f32(m, n);
-        const uint64_t adesc = ptx::make_kmajor_desc(ptx::smem_u32(smem), 1024, 2);
-        const uint64_t bdesc = ptx::make_kmajor_desc(ptx::smem_u32(smem) + 32768, 1024, 2);
+        uint64_t adesc = ptx::make_kmajor_desc(ptx::smem_u32(smem), 1024, 2);
+        uint64_t bdesc = ptx::make_kmajor_desc(ptx::smem_u32(smem) + 32768, 1024, 2);
+        if (noswz_sbo) {  // un-swizzled K-major: LBO = 16 B (next K chunk), SBO = noswz_sbo (next 8-row group); B: LBO 512, SBO 128
+            adesc = static_cast<uint64_t>((ptx::smem_u32(smem) >> 4) & 0x3FFF) | (1ull << 16) | (static_cast<uint64_t>(noswz_sbo >> 4) << 32) | (1ull << 46);
+            bdesc = static_cast<uint64_t>(((ptx::smem_u32(smem) + 32768) >> 4) & 0x3FFF) | (32ull << 16) | (8ull << 32) | (1ull << 46);
+        }
         const long long t0 = clock64();
         for (int i = 0; i < iters; i += 8) {
 #pragma unroll
@@ -75,5 +79,16 @@ int main() {
                     for (int i = 0; i < 148; ++i) s += double(h[i]);
                     printf("%-4s %-4d %-5d %-8d %.1f\n", ts ? "TS" : "SS", m, n, two, s / 148 / iters);
                 }
+    for (int sbo : {160, 256, 128, 1024})
+        for (int n : {32, 64}) {
+            for (int rep = 0; rep < 2; ++rep) rate_kernel<false><<<148, 128, 100 * 1024>>>(128, n, iters, 0, d, sbo);
+            cudaError_t e = cudaDeviceSynchronize();
+            if (e != cudaSuccess) { printf("noswz sbo=%d: %s\n", sbo, cudaGetErrorString(e)); return 1; }
+            long long h[148];
+            cudaMemcpy(h, d, sizeof(h), cudaMemcpyDeviceToHost);
+            double s = 0;
+            for (int i = 0; i < 148; ++i) s += double(h[i]);
+            printf("un-swizzled A (LBO 16, SBO %4d), N=%d: %.1f cycles/MMA\n", sbo, n, s / 148 / iters);
+        }
     return 0;
 }

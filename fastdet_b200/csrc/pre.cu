@@ -6,6 +6,7 @@
 //                        NCHW tensor the reference materialises never exists on the serving path.
 #include <stdlib.h>
 
+#include "conv_tc.h"
 #include "kernels.h"
 #include "ptx.cuh"
 
@@ -349,17 +350,486 @@ conv0_tc_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wg
     }
 }
 
+// ------------------------------------------------------------------------------------ first conv, im2col by descriptor
+// Same layer again, with the im2col done by the tensor core's operand addressing instead of by threads.
+//   * The CTA keeps a bf16 halo patch of the input in shared memory, one 16-byte unit per pixel
+//     (R, G, B, 0, 0, 0, 0, 0): patch[18 rows][10 pixels] for a tile of 16 rows x 8 columns of output pixels.
+//   * In the un-swizzled K-major operand layout a "core matrix" is 8 rows x 16 bytes with the rows 16 bytes apart,
+//     the next 8-row group SBO bytes further, the next 16-byte K chunk LBO bytes further.  With the patch above,
+//     8 consecutive pixels ARE a core matrix; SBO = one patch row (160 B) walks down the tile's 16 image rows, and
+//     LBO = 16 B steps to the next pixel, i.e. the next filter tap of the same filter row.  So the A operand of the
+//     MMA for filter row r, taps (s, s+1) is just the patch viewed from pixel (r, s): no per-pixel gather at all
+//     (the thread-built version spent ~54 shared-memory loads per output pixel on it).
+//   * K per filter row = 4 taps x 8 channels (tap 3 and channels 3..7 meet zero weights): 6 MMAs of 128 x Cout x 16
+//     per tile, ~45 cycles each (dev/mma_rate.cu), against the 64 B/pixel the layer has to write to HBM.
+//   * Epilogue: each warp drains its TMEM lane quarter (lane = pixel), bias + LeakyReLU in registers, bf16 rows staged
+//     in shared memory and written by one TMA store per warp (box = Cout x 8 pixels x 4 rows).
+static constexpr int C0D_TW = 8, C0D_TH = 16, C0D_THREADS = 128;
+static constexpr int C0D_PW = C0D_TW + 2, C0D_PH = C0D_TH + 2;   // halo patch, pixels
+static constexpr int C0D_PATCH_BYTES = (C0D_PH * C0D_PW + 8) * 16;  // + slack: tap 3 of the last pixels reads past the end
+
+__global__ void __launch_bounds__(C0D_THREADS)
+conv0_desc_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wgt, const float* __restrict__ bias,
+                  const __grid_constant__ CUtensorMap tm_out, int n, int h, int wd, int cout, int act, float alpha) {
+    __shared__ __align__(1024) uint8_t s_patch[2][C0D_PATCH_BYTES];  // double-buffered halo patch
+    __shared__ __align__(1024) uint8_t s_w[12 * 32 * 16];            // B: [K chunk 0..11][32 filters][16 B]
+    __shared__ __align__(1024) uint8_t s_out[4][2048];               // per warp: 32 pixels x 64 B (SWIZZLE_64B layout)
+    __shared__ uint16_t lut[256];
+    __shared__ __align__(8) uint64_t mma_bar;
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 256; i += C0D_THREADS) {
+        const __nv_bfloat16 v = __float2bfloat16(norm_u8(i));
+        lut[i] = *reinterpret_cast<const uint16_t*>(&v);
+    }
+    // weights: chunk c = filter row r * 4 + tap s; 8 bf16 = channels (R, G, B, 0...); tap 3 and filters >= cout are zero
+    for (int i = tid; i < 12 * 32; i += C0D_THREADS) {
+        const int c = i >> 5, f = i & 31, r = c >> 2, sx = c & 3;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (sx < 3 && f < cout) {
+            const float* wp = wgt + ((r * 3 + sx) * 3) * cout + f;
+            w0 = __ldg(wp); w1 = __ldg(wp + cout); w2 = __ldg(wp + 2 * cout);
+        }
+        *reinterpret_cast<uint4*>(s_w + i * 16) = make_uint4(c0_pack(w0, w1), c0_pack(w2, 0.f), 0u, 0u);
+    }
+    for (int i = tid; i < 2 * C0D_PATCH_BYTES / 16; i += C0D_THREADS) reinterpret_cast<uint4*>(&s_patch[0][0])[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        ptx::mbar_init(&mma_bar, 1);
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tm_out);
+    }
+    if (warp == 0) {
+        ptx::tmem_alloc(&tmem_slot, 64);  // two accumulator stages of up to 32 columns
+        ptx::tmem_relinquish();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    ptx::grid_dep_launch();  // the next layer may start its set-up on SMs as they drain (it waits before reading)
+
+    float bv[32];
+#pragma unroll
+    for (int c = 0; c < 32; ++c) bv[c] = (c < cout) ? __ldg(bias + c) : 0.f;
+    const float alpha_eff = act ? alpha : 1.0f;
+    const uint32_t idesc = ptx::make_idesc_bf16_f32(128, cout);
+    // un-swizzled K-major descriptors: LBO (K chunk stride) and SBO (8-row group stride), both in 16-byte units
+    auto desc = [](uint32_t addr, uint32_t lbo, uint32_t sbo) -> uint64_t {
+        return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+               (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (static_cast<uint64_t>(1) << 46);
+    };
+    const uint32_t w_addr = ptx::smem_u32(s_w);
+
+    const int tiles_x = (wd + C0D_TW - 1) / C0D_TW, tiles_y = (h + C0D_TH - 1) / C0D_TH;
+    const int total = n * tiles_x * tiles_y;  // < 2^31 by far (host checks)
+    // raw bytes of the next tile's patch are fetched into registers while the current tile is in the tensor core
+    // (the three bytes stay in separate registers until build(): any arithmetic on them here would wait for the loads)
+    auto fetch = [&](int tile, uint32_t (&raw)[6], uint32_t& inside) {
+        const int f = tile / (tiles_x * tiles_y);
+        const int rem = tile - f * tiles_x * tiles_y;
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        const uint8_t* fr = frames + 1LL * f * h * wd * 3;
+        inside = 0;
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = tid + k * C0D_THREADS;  // patch pixel
+            if (q < C0D_PH * C0D_PW) {
+                const int py = q / C0D_PW, px = q - py * C0D_PW;
+                const int gy = ty * C0D_TH - 1 + py, gx = tx * C0D_TW - 1 + px;
+                if (gy >= 0 && gy < h && gx >= 0 && gx < wd) {  // outside: zero padding of the normalised input
+                    const uint8_t* sp = fr + (1LL * gy * wd + gx) * 3;
+                    inside |= 1u << k;
+                    raw[3 * k] = __ldg(sp);
+                    raw[3 * k + 1] = __ldg(sp + 1);
+                    raw[3 * k + 2] = __ldg(sp + 2);
+                }
+            }
+        }
+    };
+    auto build = [&](int buf, const uint32_t (&raw)[6], uint32_t inside) {
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+            const int q = tid + k * C0D_THREADS;
+            if (q < C0D_PH * C0D_PW) {
+                uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                if (inside & (1u << k)) {
+                    v.x = static_cast<uint32_t>(lut[raw[3 * k]]) | (static_cast<uint32_t>(lut[raw[3 * k + 1]]) << 16);
+                    v.y = static_cast<uint32_t>(lut[raw[3 * k + 2]]);
+                }
+                *reinterpret_cast<uint4*>(&s_patch[buf][q * 16]) = v;
+            }
+        }
+    };
+
+    uint32_t raw[6] = {0, 0, 0, 0, 0, 0}, inside = 0;
+    uint32_t phase = 0;
+    int buf = 0;
+    if (blockIdx.x < total) fetch(blockIdx.x, raw, inside);
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, buf ^= 1) {
+        build(buf, raw, inside);
+        ptx::fence_proxy_async();  // generic-proxy writes of the patch -> visible to the tensor core
+        ptx::tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            ptx::tc_fence_after();
+            const uint32_t p_addr = ptx::smem_u32(&s_patch[buf][0]);
+            const uint32_t d = tmem + buf * 32;
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                const int r = j >> 1, s0 = (j & 1) * 2;  // filter row, first of the two taps of this K step
+                ptx::umma_bf16(d, desc(p_addr + (r * C0D_PW + s0) * 16, 16, C0D_PW * 16),
+                               desc(w_addr + (r * 4 + s0) * 512, 512, 128), idesc, j ? 1u : 0u);
+            }
+            ptx::umma_commit(&mma_bar);
+        }
+        const int next = tile + gridDim.x;
+        if (next < total) fetch(next, raw, inside);  // global loads in flight while the MMAs run
+        const int f = tile / (tiles_x * tiles_y);
+        const int rem = tile - f * tiles_x * tiles_y;
+        const int ty = rem / tiles_x, tx = rem - ty * tiles_x;
+        ptx::mbar_wait(&mma_bar, phase);
+        phase ^= 1;
+        ptx::tc_fence_after();
+        uint32_t acc[32];
+        ptx::tmem_ld_32x32(tmem + buf * 32 + (static_cast<uint32_t>(warp * 32) << 16), acc);
+        ptx::tmem_ld_wait();
+        ptx::tc_fence_before();
+        // lane = pixel (warp w: tile rows 4w .. 4w+3, 8 pixels each); bias + LeakyReLU as max(x, alpha x)
+        uint32_t pk[16];
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            float x0 = __uint_as_float(acc[2 * c]) + bv[2 * c], x1 = __uint_as_float(acc[2 * c + 1]) + bv[2 * c + 1];
+            if (act != 2) { x0 = fmaxf(x0, x0 * alpha_eff); x1 = fmaxf(x1, x1 * alpha_eff); }
+            else { x0 = x0 > 0.f ? x0 : x0 * alpha; x1 = x1 > 0.f ? x1 : x1 * alpha; }
+            pk[c] = c0_pack(x0, x1);
+        }
+        uint8_t* so = s_out[warp];
+        if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous tile's store has finished reading the staging rows
+        __syncwarp();
+        if (cout == 32) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(so + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        } else {  // cout == 16: 32-byte rows, SWIZZLE_32B (16-byte chunk index ^ bit 2 of the row)
+#pragma unroll
+            for (int c = 0; c < 2; ++c)
+                *reinterpret_cast<uint4*>(so + lane * 32 + ((c ^ ((lane >> 2) & 1)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+        }
+        ptx::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) {
+            ptx::tma_store_4d(&tm_out, so, 0, tx * C0D_TW, ty * C0D_TH + 4 * warp, f);  // clipped at the frame edges
+            ptx::tma_store_commit();
+        }
+        // the next tile's __syncthreads orders these TMEM reads before the accumulator stage is reused two tiles on
+    }
+    if (lane == 0) ptx::tma_store_wait<0>();
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == 0) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, 64);
+    }
+}
+
+// Warp-specialised form of conv0_desc_kernel (same arithmetic, same operand layouts): the lock-step version spends
+// most of a tile's ~5000 cycles waiting at its barriers (ncu: barrier + load-use stalls), so here the three stages run
+// decoupled over rings:
+//   warps 9..12  builders: warp b owns patch slot b and every 4th tile; it gathers the 180 halo pixels of a tile (6 per
+//                lane, the next tile's bytes already in registers), converts through the LUT and publishes the patch
+//   warp 8       issues the 6 MMAs of a tile into a ring of 4 TMEM accumulators
+//   warps 0..7   two epilogue groups (even / odd tiles; TMEM lane quarter = warp % 4): bias + LeakyReLU, bf16 rows
+//                staged in shared memory, one TMA store per warp and tile
+static constexpr int C0W_GROUPS = 3;                       // epilogue groups of 4 warps
+static constexpr int C0W_EPI_WARPS = 4 * C0W_GROUPS;       // warps 0 .. 11
+static constexpr int C0W_MMA_WARP = C0W_EPI_WARPS;         // warp 12
+static constexpr int C0W_BUILD_WARPS = 8;                  // one per patch slot
+static constexpr int C0W_THREADS = (C0W_EPI_WARPS + 1 + C0W_BUILD_WARPS) * 32, C0W_PATCHES = 8, C0W_ACCS = 8;  // ring depth: the
+// publish -> MMA -> drain -> release round trip is ~3000 cycles, so 4 slots capped the kernel at ~800 cycles per tile
+// q = x / d for 0 <= x < 2^24 and d < 2^12 as one 64-bit multiply: m = ceil(2^40 / d)
+__device__ __forceinline__ int div_magic(int x, unsigned long long m) { return static_cast<int>((static_cast<unsigned long long>(x) * m) >> 40); }
+static constexpr int C0W_PPL = (C0D_PH * C0D_PW + 31) / 32;  // patch pixels per builder lane
+
+__global__ void __launch_bounds__(C0W_THREADS)
+conv0_ws_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wgt, const float* __restrict__ bias,
+                const __grid_constant__ CUtensorMap tm_out, int n, int h, int wd, int cout, int act, float alpha,
+                unsigned long long m_per_frame, unsigned long long m_tiles_x) {
+    extern __shared__ __align__(1024) uint8_t c0w_dyn[];        // patch ring
+    uint8_t (*s_patch)[C0D_PATCH_BYTES] = reinterpret_cast<uint8_t (*)[C0D_PATCH_BYTES]>(c0w_dyn);
+    __shared__ __align__(1024) uint8_t s_w[12 * 32 * 16];       // B: [K chunk 0..11][32 filters][16 B]
+    __shared__ __align__(1024) uint8_t s_out[C0W_EPI_WARPS][2048];  // per epilogue warp: one staging tile of 32 pixels x 64 B
+    __shared__ uint16_t lut[256];
+    __shared__ __align__(8) uint64_t patch_full[C0W_PATCHES], patch_empty[C0W_PATCHES], acc_full[C0W_ACCS], acc_empty[C0W_ACCS];
+    __shared__ uint32_t tmem_slot;
+
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < 256; i += C0W_THREADS) {
+        const __nv_bfloat16 v = __float2bfloat16(norm_u8(i));
+        lut[i] = *reinterpret_cast<const uint16_t*>(&v);
+    }
+    for (int i = tid; i < 12 * 32; i += C0W_THREADS) {
+        const int c = i >> 5, f = i & 31, r = c >> 2, sx = c & 3;
+        float w0 = 0.f, w1 = 0.f, w2 = 0.f;
+        if (sx < 3 && f < cout) {
+            const float* wp = wgt + ((r * 3 + sx) * 3) * cout + f;
+            w0 = __ldg(wp); w1 = __ldg(wp + cout); w2 = __ldg(wp + 2 * cout);
+        }
+        *reinterpret_cast<uint4*>(s_w + i * 16) = make_uint4(c0_pack(w0, w1), c0_pack(w2, 0.f), 0u, 0u);
+    }
+    for (int i = tid; i < C0W_PATCHES * C0D_PATCH_BYTES / 16; i += C0W_THREADS) reinterpret_cast<uint4*>(c0w_dyn)[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (tid == 0) {
+        for (int i = 0; i < C0W_PATCHES; ++i) { ptx::mbar_init(&patch_full[i], 1); ptx::mbar_init(&patch_empty[i], 1); }
+        for (int i = 0; i < C0W_ACCS; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
+        ptx::fence_barrier_init();
+        ptx::tma_prefetch_desc(&tm_out);
+    }
+    if (warp == C0W_MMA_WARP) {
+        ptx::tmem_alloc(&tmem_slot, 32 * C0W_ACCS);
+        ptx::tmem_relinquish();
+    }
+    ptx::fence_proxy_async();  // the weight tile and the zeroed patch slack are read by the tensor core
+    ptx::tc_fence_before();
+    __syncthreads();
+    ptx::tc_fence_after();
+    const uint32_t tmem = tmem_slot;
+    ptx::grid_dep_launch();  // the next layer may start its set-up on SMs as they drain (it waits before reading)
+
+    const int tiles_x = (wd + C0D_TW - 1) / C0D_TW, tiles_y = (h + C0D_TH - 1) / C0D_TH;
+    const int per_frame = tiles_x * tiles_y;
+    const int total = n * per_frame;  // < 2^31 by far
+    const int my_tiles = (total > static_cast<int>(blockIdx.x)) ? (total - 1 - static_cast<int>(blockIdx.x)) / static_cast<int>(gridDim.x) + 1 : 0;
+
+    if (warp > C0W_MMA_WARP) {
+        // ---------------------------------------------------------------- builders: u8 halo patch -> bf16, 16 B per pixel
+        // warp s of this role owns patch slot s and every 8th tile; a lane handles 6 fixed patch pixels, whose
+        // offsets inside a tile are computed once (one warp's dependent-instruction latency per tile is what bounds
+        // this role, so the per-tile work is kept to the loads, the LUT and the stores)
+        const int slot = warp - C0W_MMA_WARP - 1;
+        int pq[C0W_PPL], ppy[C0W_PPL], ppx[C0W_PPL], poff[C0W_PPL];
+#pragma unroll
+        for (int k = 0; k < C0W_PPL; ++k) {
+            const int q = lane + 32 * k;  // patch pixel
+            pq[k] = q < C0D_PH * C0D_PW ? q : -1;
+            ppy[k] = q / C0D_PW;
+            ppx[k] = q - ppy[k] * C0D_PW;
+            poff[k] = (ppy[k] * wd + ppx[k]) * 3;
+        }
+        // two register sets: the bytes of this warp's next TWO tiles are in flight while it converts the current one
+        // (the loads come from DRAM: one tile of look-ahead left the warp waiting on them)
+        uint32_t raw_a[3 * C0W_PPL], raw_b[3 * C0W_PPL], inside_a = 0, inside_b = 0;
+#pragma unroll
+        for (int i = 0; i < 3 * C0W_PPL; ++i) raw_a[i] = raw_b[i] = 0;
+        auto fetch = [&](int it, uint32_t (&raw)[3 * C0W_PPL], uint32_t& inside) {  // no arithmetic on the bytes here: it would wait for the loads
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int f = div_magic(tile, m_per_frame);
+            const int rem = tile - f * per_frame;
+            const int ty = div_magic(rem, m_tiles_x), tx = rem - ty * tiles_x;
+            const int y0 = ty * C0D_TH - 1, x0 = tx * C0D_TW - 1;
+            const uint8_t* origin = frames + (1LL * f * h * wd + 1LL * y0 * wd + x0) * 3;  // may point before the frame: only used when inside
+            inside = 0;
+#pragma unroll
+            for (int k = 0; k < C0W_PPL; ++k) {
+                const int gy = y0 + ppy[k], gx = x0 + ppx[k];
+                if (pq[k] >= 0 && gy >= 0 && gy < h && gx >= 0 && gx < wd) {  // outside: zero padding of the normalised input
+                    const uint8_t* sp = origin + poff[k];
+                    inside |= 1u << k;
+                    raw[3 * k] = __ldg(sp);
+                    raw[3 * k + 1] = __ldg(sp + 1);
+                    raw[3 * k + 2] = __ldg(sp + 2);
+                }
+            }
+        };
+        auto publish = [&](const uint32_t (&raw)[3 * C0W_PPL], uint32_t inside, uint32_t phase) {
+            ptx::mbar_wait(&patch_empty[slot], phase ^ 1);
+#pragma unroll
+            for (int k = 0; k < C0W_PPL; ++k) {
+                if (pq[k] >= 0) {
+                    uint4 v = make_uint4(0u, 0u, 0u, 0u);
+                    if (inside & (1u << k)) {
+                        v.x = static_cast<uint32_t>(lut[raw[3 * k]]) | (static_cast<uint32_t>(lut[raw[3 * k + 1]]) << 16);
+                        v.y = static_cast<uint32_t>(lut[raw[3 * k + 2]]);
+                    }
+                    *reinterpret_cast<uint4*>(&s_patch[slot][pq[k] * 16]) = v;
+                }
+            }
+        };
+        auto signal = [&]() {
+            ptx::fence_proxy_async();  // generic-proxy writes of the patch -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&patch_full[slot]);
+        };
+        uint32_t phase = 0;
+        if (slot < my_tiles) fetch(slot, raw_a, inside_a);
+        if (slot + C0W_PATCHES < my_tiles) fetch(slot + C0W_PATCHES, raw_b, inside_b);
+        for (int it = slot; it < my_tiles; it += 2 * C0W_PATCHES) {
+            publish(raw_a, inside_a, phase);
+            if (it + 2 * C0W_PATCHES < my_tiles) fetch(it + 2 * C0W_PATCHES, raw_a, inside_a);
+            signal();
+            phase ^= 1;
+            if (it + C0W_PATCHES >= my_tiles) break;
+            publish(raw_b, inside_b, phase);
+            if (it + 3 * C0W_PATCHES < my_tiles) fetch(it + 3 * C0W_PATCHES, raw_b, inside_b);
+            signal();
+            phase ^= 1;
+        }
+    } else if (warp == C0W_MMA_WARP) {
+        // ---------------------------------------------------------------- MMA issuer
+        // This warp's issue rate bounds the kernel (6 MMAs + 2 commits per 128 pixels), so everything it needs is a
+        // warp-uniform value prepared outside the loop and the elected lane only issues (an `if (lane == 0)` body made
+        // the compiler wrap every tcgen05.mma in an ELECT loop: ~950 cycles per tile).
+        const uint32_t idesc = ptx::make_idesc_bf16_f32(128, cout);
+        // un-swizzled K-major descriptors: LBO (K chunk stride) and SBO (8-row group stride), in 16-byte units
+        auto desc = [](uint32_t addr, uint32_t lbo, uint32_t sbo) -> uint64_t {
+            return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+                   (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (static_cast<uint64_t>(1) << 46);
+        };
+        const uint32_t w_addr = __shfl_sync(0xffffffffu, ptx::smem_u32(s_w), 0);
+        const uint32_t p_addr0 = __shfl_sync(0xffffffffu, ptx::smem_u32(&s_patch[0][0]), 0);
+        const uint32_t bar_pe = __shfl_sync(0xffffffffu, ptx::smem_u32(&patch_empty[0]), 0);
+        const uint32_t bar_pf = __shfl_sync(0xffffffffu, ptx::smem_u32(&patch_full[0]), 0);
+        const uint32_t bar_af = __shfl_sync(0xffffffffu, ptx::smem_u32(&acc_full[0]), 0);
+        const uint32_t bar_ae = __shfl_sync(0xffffffffu, ptx::smem_u32(&acc_empty[0]), 0);
+        const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+        const uint64_t a0 = desc(p_addr0, 16, C0D_PW * 16);
+        uint64_t bd[6], aoff[6];
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int r = j >> 1, s0 = (j & 1) * 2;  // filter row, first of the two taps of this K step
+            bd[j] = desc(w_addr + (r * 4 + s0) * 512, 512, 128);
+            aoff[j] = static_cast<uint64_t>(r * C0D_PW + s0);  // 16-byte units
+        }
+        const bool issuer = ptx::elect_one();
+        uint32_t slot = 0, phase = 0;
+        for (int it = 0; it < my_tiles; ++it) {
+            ptx::mbar_wait_addr(bar_ae + 8u * slot, phase ^ 1);
+            ptx::mbar_wait_addr(bar_pf + 8u * slot, phase);
+            ptx::tc_fence_after();
+            const uint64_t ad = a0 + slot * (C0D_PATCH_BYTES / 16);
+            const uint32_t d = tmem_u + slot * 32;
+            if (issuer) {
+#pragma unroll
+                for (int j = 0; j < 6; ++j) ptx::umma_bf16(d, ad + aoff[j], bd[j], idesc, j ? 1u : 0u);
+                ptx::umma_commit_addr(bar_pe + 8u * slot);
+                ptx::umma_commit_addr(bar_af + 8u * slot);
+            }
+            __syncwarp();
+            if (++slot == C0W_ACCS) { slot = 0; phase ^= 1; }  // C0W_PATCHES == C0W_ACCS: one index walks both rings
+        }
+    } else {
+        // ---------------------------------------------------------------- epilogue group g: tiles it = g, g + groups, ...
+        static_assert(C0W_PATCHES == C0W_ACCS && C0W_ACCS == 8 && C0W_BUILD_WARPS == C0W_PATCHES, "ring indexing below assumes 8 + 8");
+        const int group = warp >> 2, quarter = warp & 3;  // TMEM lane quarter = warp % 4
+        float bv[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) bv[c] = (c < cout) ? __ldg(bias + c) : 0.f;
+        const float alpha_eff = act ? alpha : 1.0f;
+        for (int it = group; it < my_tiles; it += C0W_GROUPS) {
+            const int as = it & 7;
+            const uint32_t aphase = (it >> 3) & 1;
+            const int tile = blockIdx.x + it * gridDim.x;
+            const int f = div_magic(tile, m_per_frame);
+            const int rem = tile - f * per_frame;
+            const int ty = div_magic(rem, m_tiles_x), tx = rem - ty * tiles_x;
+            ptx::mbar_wait(&acc_full[as], aphase);
+            ptx::tc_fence_after();
+            uint32_t acc[32];
+            ptx::tmem_ld_32x32(tmem + as * 32 + (static_cast<uint32_t>(quarter * 32) << 16), acc);
+            ptx::tmem_ld_wait();
+            ptx::tc_fence_before();
+            __syncwarp();
+            if (lane == 0) ptx::mbar_arrive(&acc_empty[as]);
+            // lane = pixel (tile rows 4q .. 4q+3, 8 pixels each); bias + LeakyReLU as max(x, alpha x)
+            uint32_t pk[16];
+            const float2 a2 = make_float2(alpha_eff, alpha_eff);
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {  // two columns per FADD2 / FMUL2
+                float2 x = __fadd2_rn(make_float2(__uint_as_float(acc[2 * c]), __uint_as_float(acc[2 * c + 1])), make_float2(bv[2 * c], bv[2 * c + 1]));
+                if (act != 2) {
+                    const float2 m = __fmul2_rn(x, a2);
+                    x.x = fmaxf(x.x, m.x);
+                    x.y = fmaxf(x.y, m.y);
+                } else {
+                    x.x = x.x > 0.f ? x.x : x.x * alpha;
+                    x.y = x.y > 0.f ? x.y : x.y * alpha;
+                }
+                pk[c] = c0_pack(x.x, x.y);
+            }
+            uint8_t* so = s_out[warp];
+            if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store (two tiles ago) has finished reading the buffer
+            __syncwarp();
+            // dense rows [4 image rows][8 pixels][cout]: with pitch == cout the 8 pixels of an image row are one contiguous
+            // 8*cout*2-byte run in global memory, so the TMA store moves 4 wide rows instead of 32 narrow ones (the L2
+            // takes ~1 request per 3 cycles per SM whatever its size; 64-byte rows made this kernel request-bound)
+            if (cout == 32) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c)  // (un-swizzled: 4-way bank conflicts on 4 stores per tile, noise)
+                    *reinterpret_cast<uint4*>(so + lane * 64 + (c << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            } else {
+#pragma unroll
+                for (int c = 0; c < 2; ++c)
+                    *reinterpret_cast<uint4*>(so + lane * 32 + (c << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_3d(&tm_out, so, tx * C0D_TW * cout, ty * C0D_TH + 4 * quarter, f);  // clipped at the frame edges
+                ptx::tma_store_commit();
+            }
+        }
+        if (lane == 0) ptx::tma_store_wait<0>();
+    }
+    ptx::tc_fence_before();
+    __syncthreads();
+    if (warp == C0W_MMA_WARP) {
+        ptx::tc_fence_after();
+        ptx::tmem_dealloc(tmem, 32 * C0W_ACCS);
+    }
+}
+
 int kernels_init() {
-    return cudaFuncSetAttribute(conv0_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) ==
-                   cudaSuccess
+    return (cudaFuncSetAttribute(conv0_u8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024) == cudaSuccess &&
+            cudaFuncSetAttribute(conv0_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, C0W_PATCHES * C0D_PATCH_BYTES) == cudaSuccess)
                ? 0
                : -1;
 }
 
 int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __nv_bfloat16* out, int n, int h,
                     int wd, int cout, int out_pitch, int act, float alpha, cudaStream_t s) {
-    static const bool force_cuda_core = getenv("FASTDET_CONV0_FMA") != nullptr;
-    if (!force_cuda_core && (cout == 16 || cout == 32)) {
+    static const int variant = getenv("FASTDET_CONV0") ? atoi(getenv("FASTDET_CONV0")) : 0;  // 0 descriptor im2col, 1 thread-built im2col, 2 CUDA cores
+    const int act_mode = act ? ((alpha >= 0.f && alpha <= 1.f) ? 1 : 2) : 0;
+    if (variant == 0 && (cout == 16 || cout == 32) && out_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
+        static const bool lockstep = getenv("FASTDET_C0_LOCKSTEP") != nullptr;
+        CUtensorMap tm;
+        if (lockstep || out_pitch != cout) {
+            if (!lockstep) return -1;  // (the planner gives the first layer a dense output)
+            const unsigned long long dims[4] = {static_cast<unsigned long long>(cout), static_cast<unsigned long long>(wd),
+                                                static_cast<unsigned long long>(h), static_cast<unsigned long long>(n)};
+            const unsigned long long strides[3] = {2ULL * out_pitch, 2ULL * out_pitch * wd, 2ULL * out_pitch * wd * h};
+            const unsigned box[4] = {static_cast<unsigned>(cout), C0D_TW, 4, 1};
+            if (encode_tiled_bf16(&tm, out, 4, dims, strides, box, cout == 32 ? 2 : 1)) return -1;
+        } else {
+            // dense NHWC: an image row is one run of W*C elements; box = 8 pixels x 4 rows
+            const unsigned long long dims[3] = {static_cast<unsigned long long>(cout) * wd, static_cast<unsigned long long>(h),
+                                                static_cast<unsigned long long>(n)};
+            const unsigned long long strides[2] = {2ULL * cout * wd, 2ULL * cout * wd * h};
+            const unsigned box[3] = {static_cast<unsigned>(cout) * C0D_TW, 4, 1};
+            if (encode_tiled_bf16(&tm, out, 3, dims, strides, box, 0)) return -1;
+        }
+        const long long tiles = 1LL * n * ((wd + C0D_TW - 1) / C0D_TW) * ((h + C0D_TH - 1) / C0D_TH);
+        static const int per_sm = getenv("FASTDET_C0_CTAS") ? atoi(getenv("FASTDET_C0_CTAS")) : 1;
+        const int blocks = static_cast<int>(tiles < 148LL * per_sm ? tiles : 148LL * per_sm);
+        if (lockstep) conv0_desc_kernel<<<blocks, C0D_THREADS, 0, s>>>(frames, w, bias, tm, n, h, wd, cout, act_mode, alpha);
+        else {
+            const int tx = (wd + C0D_TW - 1) / C0D_TW, per_frame = tx * ((h + C0D_TH - 1) / C0D_TH);
+            if (tiles >= (1LL << 24) || per_frame >= 4096 * 16) return -1;  // range of the multiply-shift division
+            const unsigned long long one40 = 1ULL << 40;
+            conv0_ws_kernel<<<blocks, C0W_THREADS, C0W_PATCHES * C0D_PATCH_BYTES, s>>>(frames, w, bias, tm, n, h, wd, cout, act_mode, alpha,
+                                                          (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx);
+        }
+        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    }
+    if (variant <= 1 && (cout == 16 || cout == 32)) {
         const long long tiles = 1LL * n * ((wd + C0T_TW - 1) / C0T_TW) * ((h + C0T_TH - 1) / C0T_TH);
         static const int per_sm = getenv("FASTDET_C0_CTAS") ? atoi(getenv("FASTDET_C0_CTAS")) : 16;
         const int blocks = static_cast<int>(tiles < 148LL * per_sm ? tiles : 148LL * per_sm);
