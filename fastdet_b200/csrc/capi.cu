@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/fastdet_b200.h"
+#include "conv_halo.h"
 #include "conv_tc.h"
 #include "kernels.h"
 #include "onnx_reader.h"
@@ -48,6 +49,8 @@ struct Exec {  // everything that depends on the batch size
     int n = 0;
     std::vector<void*> bufs;
     std::vector<ConvLaunch> conv;  // indexed by layer
+    std::vector<HaloLaunch> halo;  // indexed by layer; used where use_halo[layer]
+    std::vector<char> use_halo;
     uint8_t* frames = nullptr;     // [n, net_h, net_w, 3]
     uint8_t* src = nullptr;        // staging for frames that need the letterbox
     size_t src_cap = 0;
@@ -138,9 +141,23 @@ int get_exec(fd_model* m, int n, Exec** out) {
         return fail(FD_ERR_CUDA, "cudaMalloc(per-batch state, batch %d) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
     }
     e->conv.resize(P.layers.size());
+    e->halo.resize(P.layers.size());
+    e->use_halo.assign(P.layers.size(), 0);
     for (size_t i = 0; i < P.layers.size(); ++i) {
         const LayerPlan& L = P.layers[i];
         if (L.kind != LAYER_CONV) continue;
+        {   // narrow 3x3 layers on large maps: halo-patch kernel (conv_halo.cu)
+            HaloDesc h;
+            memset(&h, 0, sizeof(h));
+            h.n = n; h.hi = L.in.h; h.wi = L.in.w; h.cin = L.cin; h.in_pitch = L.in.pitch;
+            h.in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false));
+            h.cout = L.cout; h.ksize = L.ksize; h.stride = L.stride; h.pad_lo = L.pad_lo; h.pad_hi = L.pad_hi;
+            h.w = m->d_w + L.w_off; h.bias_host = P.bias_f32.data() + L.b_off; h.act = L.act; h.alpha = L.alpha;
+            if (L.res.buf >= 0) { h.residual = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.res, false)); h.res_pitch = L.res.pitch; }
+            h.out = loc_ptr(*e, L.out, L.out_fp32 != 0); h.out_pitch = L.out.pitch; h.out_fp32 = L.out_fp32; h.upsample2x = L.upsample2x;
+            char herr[256] = "";
+            if (conv_halo_supported(h) && conv_halo_prepare(h, m->num_sms, &e->halo[i], herr, sizeof(herr)) == 0) { e->use_halo[i] = 1; continue; }
+        }
         ConvDesc d;
         memset(&d, 0, sizeof(d));
         d.n = n; d.hi = L.in.h; d.wi = L.in.w; d.cin = L.cin; d.in_pitch = L.in.pitch;
@@ -169,7 +186,7 @@ int launch_layers(fd_model* m, Exec* e, cudaStream_t s, int only_layer = -1) {
                                      static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), e->n, L.in.h, L.in.w, L.cout,
                                      L.out.pitch, L.act, L.alpha, s);
                 break;
-            case LAYER_CONV: rc = conv_tc_launch(e->conv[i], s); break;
+            case LAYER_CONV: rc = e->use_halo[i] ? conv_halo_launch(e->halo[i], s) : conv_tc_launch(e->conv[i], s); break;
             case LAYER_MAXPOOL:
                 rc = launch_maxpool(static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false)), L.in.pitch,
                                     static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), L.out.pitch, e->n, L.in.h, L.in.w,
@@ -317,7 +334,10 @@ int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out) {
     out->cin = L.cin; out->ksize = L.ksize; out->stride = L.stride; out->act = L.act;
     out->has_residual = L.res.buf >= 0; out->upsample2x = L.upsample2x; out->out_fp32 = L.out_fp32;
     out->flops = L.flops;
-    if (L.kind == LAYER_CONV && !m->execs.empty()) out->block_n = m->execs.begin()->second->conv[layer].block_n;
+    if (L.kind == LAYER_CONV && !m->execs.empty()) {
+        const Exec& e0 = *m->execs.begin()->second;
+        out->block_n = e0.use_halo[layer] ? -1 : e0.conv[layer].block_n;  // -1: halo-patch kernel
+    }
     snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
     snprintf(out->out_name, sizeof(out->out_name), "%s", L.out_name.c_str());
     return FD_OK;

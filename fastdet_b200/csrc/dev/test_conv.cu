@@ -8,6 +8,7 @@
 
 #include <vector>
 
+#include "../conv_halo.h"
 #include "../conv_tc.h"
 
 using namespace fd;
@@ -80,7 +81,20 @@ static int run_case(const Case& c, int num_sms) {
     d.residual = dr; d.res_pitch = c.cout;
     d.out = dout; d.out_pitch = out_pitch; d.out_fp32 = c.fp32; d.upsample2x = c.upsample;
     ConvLaunch L;
+    memset(&L, 0, sizeof(L));
     char err[256] = {0};
+    if (c.block_n == 2048) {  // the halo-patch kernel (conv_halo.cu) on the same problem
+        HaloDesc hd;
+        memset(&hd, 0, sizeof(hd));
+        hd.n = d.n; hd.hi = d.hi; hd.wi = d.wi; hd.cin = d.cin; hd.in_pitch = d.in_pitch; hd.in = d.in;
+        hd.cout = d.cout; hd.ksize = d.ksize; hd.stride = d.stride; hd.pad_lo = d.pad_lo; hd.pad_hi = d.pad_hi;
+        hd.w = d.w; hd.bias_host = d.bias_host; hd.act = d.act; hd.alpha = d.alpha;
+        hd.residual = d.residual; hd.res_pitch = d.res_pitch; hd.out = d.out; hd.out_pitch = d.out_pitch;
+        static HaloLaunch H;
+        if (conv_halo_prepare(hd, num_sms, &H, err, sizeof(err))) { printf("[%s] halo prepare failed: %s\n", c.name, err); return 1; }
+        if (conv_halo_launch(H, 0)) { printf("[%s] halo launch failed: %s\n", c.name, cudaGetErrorString(cudaGetLastError())); return 1; }
+        L.grid = H.grid;
+    } else {
     if (conv_tc_prepare(d, num_sms, c.block_n, &L, err, sizeof(err))) {
         printf("[%s] prepare failed: %s\n", c.name, err);
         return 1;
@@ -88,6 +102,7 @@ static int run_case(const Case& c, int num_sms) {
     if (conv_tc_launch(L, 0)) {
         printf("[%s] launch failed: %s\n", c.name, cudaGetErrorString(cudaGetLastError()));
         return 1;
+    }
     }
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) {
@@ -257,6 +272,10 @@ int main(int argc, char** argv) {
             {"2cta 3x3 128->256 big",   16, 52, 52, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
             {"1cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 257},
             {"3x3 16->32 s1 (bk16)",    2, 20, 20, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
+            {"halo 3x3 32->64 s1 res",  2, 72, 76, 32, 64, 3, 1, 1, 1, 1, 1, 0, 0, 0, 2048},
+            {"halo 3x3 32->64 s2",      2, 130, 134, 32, 64, 3, 2, 1, 1, 1, 0, 0, 0, 0, 2048},
+            {"halo 3x3 32->32 s1 pitch",1, 64, 64, 32, 32, 3, 1, 1, 1, 0, 0, 0, 0, 32, 2048},
+            {"halo 3x3 32->64 s2 (1,0)",1, 128, 128, 32, 64, 3, 2, 1, 0, 1, 0, 0, 0, 0, 2048},
             {"1x1 48->64 (bk16)",       1, 20, 20, 48, 64, 1, 1, 0, 0, 1, 0, 0, 0, 16, 0},
         };
         for (const Case& c : cases) fails += run_case(c, sms);

@@ -80,6 +80,16 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// 16-byte asynchronous copy global -> shared (LDGSTS), L1-allocating; src_bytes = 0 writes zeros (padding)
+__device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // Variants taking raw shared-space addresses (no generic->shared conversion in single-thread hot loops).
 __device__ __forceinline__ bool mbar_try_wait_addr(uint32_t bar, uint32_t parity) {
     uint32_t ok;
