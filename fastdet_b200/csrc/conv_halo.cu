@@ -17,7 +17,8 @@
 //     2*ox + s for consecutive ox are again 16 bytes apart.
 //
 // Roles (17 warps): 8 epilogue warps in two groups (even / odd tiles; TMEM lane quarter = warp % 4), 1 MMA warp, 8
-// builder warps in two teams (team t owns patch slots 2t, 2t+1 and keeps two tiles' copies in flight).
+// builder warps in two teams (even / odd tiles) that never wait for a copy: the copies of every free patch slot (8 at
+// stride 1, 4 at stride 2) are in flight at once and arrive on the slot's barrier asynchronously.
 // Replaces the same Conv+BatchNormalization+LeakyRelu(+Add) node groups as conv_tc.cu (reference server/detector.py:135).
 #include "conv_halo.h"
 
@@ -35,7 +36,7 @@ namespace {
 constexpr int TW = 8, TH = 16;           // output tile (pixels): 16 rows x 8 columns = the 128 rows of one MMA
 constexpr int EPI_WARPS = 8, MMA_WARP = 8, BUILD_WARPS = 8;
 constexpr int THREADS = (EPI_WARPS + 1 + BUILD_WARPS) * 32;
-constexpr int SLOTS = 4, ACCS = 4;
+constexpr int ACCS = 4;
 constexpr int SMEM_LIMIT = 227 * 1024;
 
 template <int STRIDE>
@@ -49,6 +50,9 @@ struct Geo {
     static constexpr int PLANE_PIX = (STRIDE == 1 ? 1 : 4) * SPH * SPW;
     static constexpr int PLANE_BYTES = ((PLANE_PIX * 16 + 127) / 128) * 128;
     static constexpr int SBO = SPW * 16;
+    // patch ring depth: the copies of SLOTS tiles are in flight at once (the ~3 us DRAM/L2 round trip of a patch is what
+    // has to be covered); stride-2 patches are 39 KB each, more than 4 do not fit
+    static constexpr int SLOTS = STRIDE == 1 ? 8 : 4;
 };
 
 __device__ __forceinline__ int div_magic(int x, unsigned long long m) {
@@ -75,6 +79,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
     constexpr int NCH = CIN / 8;                    // 16-byte channel chunks per pixel
     constexpr int PATCH_BYTES = NCH * G::PLANE_BYTES;
     constexpr int KSTEPS = CIN / 16;                // MMAs per filter tap
+    constexpr int SLOTS = G::SLOTS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [0, 1024) barriers | staging 8 warps x 4 KB | weights 9*NCH*cout*16 | patch ring SLOTS x PATCH_BYTES
@@ -95,7 +100,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
         *reinterpret_cast<uint4*>(s_w + i * 16) = __ldg(reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(f) * 9 * CIN + kc * 8));
     }
     if (tid == 0) {
-        for (int i = 0; i < SLOTS; ++i) { ptx::mbar_init(&patch_full[i], 4); ptx::mbar_init(&patch_empty[i], 1); }
+        for (int i = 0; i < SLOTS; ++i) { ptx::mbar_init(&patch_full[i], 128); ptx::mbar_init(&patch_empty[i], 1); }  // full: one asynchronous arrive per thread of a builder team
         for (int i = 0; i < ACCS; ++i) { ptx::mbar_init(&acc_full[i], 1); ptx::mbar_init(&acc_empty[i], 4); }
         ptx::fence_barrier_init();
         ptx::tma_prefetch_desc(&tm_out);
@@ -117,16 +122,16 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
 
     if (warp > MMA_WARP) {
         // ---------------------------------------------------------------- builders
-        // team t = 4 warps owns patch slots 2t and 2t+1 (tiles it % 4 == 2t, 2t+1); a lane copies items q = pixel * NCH +
-        // chunk, q = ltid, ltid + 128, ...: consecutive lanes take consecutive 16-byte chunks, i.e. whole pixels, i.e.
-        // 512-byte runs of an image row.  A tile's copies are published (wait_group + proxy fence + arrive) one tile
-        // late, so two tiles' loads are always in flight per team.
+        // team t = 4 warps takes the tiles of parity t; a lane copies items q = pixel * NCH + chunk, q = ltid, ltid + 128,
+        // ...: consecutive lanes take consecutive 16-byte chunks, i.e. whole pixels, i.e. 512-byte runs of an image row.
+        // Nothing here waits for a copy: each thread's arrival on the slot's barrier is itself asynchronous
+        // (cp.async.mbarrier.arrive), so the copies of every free slot are in flight at once.
         const int bw = warp - MMA_WARP - 1, team = bw >> 2, ltid = (bw & 3) * 32 + lane;
         constexpr int ITEMS = G::PH * G::PW * NCH;
         const uint32_t patch_base = ptx::smem_u32(s_patch);
         ptx::grid_dep_wait();
-        auto issue = [&](int it) {
-            const int slot = it & 3;
+        for (int it = team; it < my_tiles; it += 2) {
+            const int slot = it % SLOTS;
             const int tile = blockIdx.x + it * gridDim.x;
             const int f = div_magic(tile, p.m_per_frame);
             const int rem = tile - f * per_frame;
@@ -134,7 +139,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
             const int y_org = ty * TH * STRIDE - 1, x_org = tx * TW * STRIDE - 1;
             const __nv_bfloat16* frame = p.in + static_cast<long long>(f) * p.hi * p.wi * p.in_pitch;
             const uint32_t dst0 = patch_base + slot * PATCH_BYTES;
-            ptx::mbar_wait(&patch_empty[slot], ((it >> 2) & 1) ^ 1);
+            ptx::mbar_wait(&patch_empty[slot], ((it / SLOTS) & 1) ^ 1);
 #pragma unroll 4
             for (int q = ltid; q < ITEMS; q += 128) {
                 const int pix = q / NCH, c = q - pix * NCH;
@@ -145,30 +150,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                 const __nv_bfloat16* src = ok ? frame + (static_cast<long long>(gy) * p.wi + gx) * p.in_pitch + c * 8 : p.in;
                 ptx::cp_async_16(dst0 + c * G::PLANE_BYTES + idx * 16, src, ok ? 16u : 0u);  // 0 bytes: zero fill (padding)
             }
-            ptx::cp_async_commit();
-        };
-        auto publish = [&](int it) {  // the copies of tile `it` have landed: make them visible to the tensor core, hand over
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) ptx::mbar_arrive(&patch_full[it & 3]);
-        };
-        // this team's tiles in order: it = 2*team, 2*team+1, 2*team+4, 2*team+5, ...
-        int prev = -1;
-        for (int base = 2 * team; base < my_tiles; base += 4) {
-            for (int k = 0; k < 2; ++k) {
-                const int it = base + k;
-                if (it >= my_tiles) break;
-                issue(it);
-                if (prev >= 0) {
-                    ptx::cp_async_wait<1>();  // everything but the group just committed
-                    publish(prev);
-                }
-                prev = it;
-            }
-        }
-        if (prev >= 0) {
-            ptx::cp_async_wait<0>();
-            publish(prev);
+            ptx::cp_async_arrive_noinc(&patch_full[slot]);
         }
     } else if (warp == MMA_WARP) {
         // ---------------------------------------------------------------- MMA issuer (all operands warp-uniform)
@@ -182,12 +164,13 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
         const uint32_t b_step = static_cast<uint32_t>(cout) * 2;  // two K chunks per MMA, in 16-byte units: 2 * cout * 16 / 16
         const bool issuer = ptx::elect_one();
         for (int it = 0; it < my_tiles; ++it) {
-            const uint32_t slot = it & 3, phase = (it >> 2) & 1;
-            ptx::mbar_wait_addr(bar0 + 8u * (3 * SLOTS + slot), phase ^ 1);  // acc_empty
-            ptx::mbar_wait_addr(bar0 + 8u * slot, phase);                    // patch_full
+            const uint32_t slot = it % SLOTS, phase = (it / SLOTS) & 1, as = it & 3, aphase = (it >> 2) & 1;
+            ptx::mbar_wait_addr(bar0 + 8u * (2 * SLOTS + ACCS + as), aphase ^ 1);  // acc_empty
+            ptx::mbar_wait_addr(bar0 + 8u * slot, phase);                          // patch_full
+            ptx::fence_proxy_async();  // the builders' cp.async writes (generic proxy), acquired through the barrier -> tensor core
             ptx::tc_fence_after();
             const uint64_t ad = a0 + slot * (PATCH_BYTES / 16);
-            const uint32_t d = tmem_u + slot * acc_cols;
+            const uint32_t d = tmem_u + as * acc_cols;
             if (issuer) {
 #pragma unroll
                 for (int t = 0; t < 9; ++t) {
@@ -199,8 +182,8 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                         ptx::umma_bf16(d, ad + start + j * (2 * G::PLANE_BYTES / 16), b0 + (t * KSTEPS + j) * b_step, idesc,
                                        (t | j) ? 1u : 0u);
                 }
-                ptx::umma_commit_addr(bar0 + 8u * (SLOTS + slot));      // patch_empty
-                ptx::umma_commit_addr(bar0 + 8u * (2 * SLOTS + slot));  // acc_full
+                ptx::umma_commit_addr(bar0 + 8u * (SLOTS + slot));    // patch_empty
+                ptx::umma_commit_addr(bar0 + 8u * (2 * SLOTS + as));  // acc_full
             }
             __syncwarp();
         }
@@ -297,7 +280,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
 template <int CIN, int STRIDE>
 size_t smem_bytes(int cout) {
     return 1024 + 1024 + EPI_WARPS * 4096 + ((9 * (CIN / 8) * cout * 16 + 1023) & ~1023) +
-           static_cast<size_t>(SLOTS) * (CIN / 8) * Geo<STRIDE>::PLANE_BYTES;
+           static_cast<size_t>(Geo<STRIDE>::SLOTS) * (CIN / 8) * Geo<STRIDE>::PLANE_BYTES;
 }
 
 }  // namespace
