@@ -168,6 +168,30 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
             for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
         }
         lap(2);
+        if (mode == 0 && HALF_N >= 64 && p.store64) {
+            // two chunks share one staging tile of 32 rows x 128 B (128-byte swizzle: 16-byte chunk k of row r at slot
+            // k ^ (r & 7)) and leave through ONE TMA store: half the store requests (the TMA engine moves about one
+            // row per 3 cycles whatever its width) and half the proxy fences of the 64-byte form
+            const bool second = ((c0 - c_begin) & 32) != 0;
+            if (!second) {
+                if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous pair's store has finished reading the tile
+                __syncwarp();
+            }
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(stage + lane * 128 + (((c + (second ? 4 : 0)) ^ (lane & 7)) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            if (second) {
+                ptx::fence_proxy_async();  // generic-proxy writes -> visible to the TMA engine
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_2d(tm_out, stage, n0 + c0 - 32, static_cast<int>(m_base));  // rows >= M are clipped by the map
+                    ptx::tma_store_commit();
+                }
+            }
+            lap(3);
+            return;
+        }
         // stage the bf16 row (64 B = 4 x 16 B) with the 64-byte swizzle (chunk c of row r at slot c ^ ((r >> 1) & 3)):
         // conflict-free for these stores, and the layout a SWIZZLE_64B tensor map reads back
         uint8_t* buf = stage + (sbuf & 1) * 2048;
@@ -846,11 +870,13 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     if (p.epi_mode == 0 && !swap) {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.cout), static_cast<cuuint64_t>(M)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_pitch) * 2};
-        cuuint32_t box[2] = {32, 32};
+        static const bool no64 = getenv("FASTDET_NO_STORE64") != nullptr;
+        p.store64 = (bn >= 128 && !no64) ? 1 : 0;  // 128-byte store rows (two 32-column chunks per TMA store)
+        cuuint32_t box[2] = {p.store64 ? 64u : 32u, 32};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, dims, strides, box, estr,
-                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
-                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, p.store64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map OUT encode failed (CUresult %lld)", r); return -1; }
     } else {
         L->tmOut = L->tmB;  // unused by these modes; any valid map

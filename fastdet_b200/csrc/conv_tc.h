@@ -56,6 +56,7 @@ struct ConvParams {
     int n_store_limit;
     long long* prof;  // developer: per-CTA cycle counters [grid][16] (null in production)
     int debug;  // developer switches (0 in production): 1 skip epilogue stores, 2 skip A loads, 4 skip MMA issue
+    int store64;   // 1: the output map's box is 64 channels x 32 rows (SWIZZLE_128B), two chunks per TMA store
     int res_v8;    // 1: residual rows are 32-byte aligned -> 256-bit loads
     int epi_mode;  // 0 bf16 slice through a TMA store (+ residual), 1 fp32 head rows, 2 bf16 with x2 upsampling
     // the layer's bias, read by the epilogue from the constant bank with a warp-uniform index (shared-memory and
