@@ -8,6 +8,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <map>
 #include <memory>
 #include <string>
@@ -51,6 +52,8 @@ struct Exec {  // everything that depends on the batch size
     std::vector<ConvLaunch> conv;  // indexed by layer
     std::vector<HaloLaunch> halo;  // indexed by layer; used where use_halo[layer]
     std::vector<char> use_halo;
+    float* splitk_ws = nullptr;     // shared by the split-K launches of this batch size (they run one after another)
+    int* splitk_counters = nullptr;
     uint8_t* frames = nullptr;     // [n, net_h, net_w, 3]
     uint8_t* src = nullptr;        // staging for frames that need the letterbox
     size_t src_cap = 0;
@@ -105,6 +108,7 @@ size_t buf_bytes(const BufferPlan& b, int n) { return size_t(n) * b.h * b.w * b.
 
 void free_exec(Exec* e) {
     for (void* p : e->bufs) cudaFree(p);
+    cudaFree(e->splitk_ws); cudaFree(e->splitk_counters);
     cudaFree(e->frames); cudaFree(e->src); cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->scores);
     cudaFree(e->dets); cudaFree(e->det_count); cudaFree(e->scratch);
     if (e->h_dets) cudaFreeHost(e->h_dets);
@@ -166,8 +170,20 @@ int get_exec(fd_model* m, int n, Exec** out) {
         d.w = m->d_w + L.w_off; d.bias = m->d_bias + L.b_off; d.bias_host = P.bias_f32.data() + L.b_off; d.act = L.act; d.alpha = L.alpha;
         if (L.res.buf >= 0) { d.residual = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.res, false)); d.res_pitch = L.res.pitch; }
         d.out = loc_ptr(*e, L.out, L.out_fp32 != 0); d.out_pitch = L.out.pitch; d.out_fp32 = L.out_fp32; d.upsample2x = L.upsample2x;
+        d.allow_split_k = 1;
         char err[256] = "";
         if (conv_tc_prepare(d, m->num_sms, 0, &e->conv[i], err, sizeof(err))) { free_exec(e.get()); return fail(FD_ERR_CUDA, "layer %zu (%s): %s", i, L.name.c_str(), err); }
+    }
+    size_t ws_bytes = 0, counter_ints = 0;
+    for (const ConvLaunch& c : e->conv) { ws_bytes = std::max(ws_bytes, c.ws_bytes); counter_ints = std::max(counter_ints, c.counter_ints); }
+    if (ws_bytes) {
+        if (cudaMalloc(&e->splitk_ws, ws_bytes) != cudaSuccess || cudaMalloc(&e->splitk_counters, counter_ints * sizeof(int)) != cudaSuccess ||
+            cudaMemset(e->splitk_counters, 0, counter_ints * sizeof(int)) != cudaSuccess) {
+            free_exec(e.get());
+            return fail(FD_ERR_CUDA, "cudaMalloc(split-K workspace, batch %d) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
+        }
+        for (ConvLaunch& c : e->conv)
+            if (c.ws_bytes) conv_tc_bind_workspace(&c, e->splitk_ws, e->splitk_counters);
     }
     *out = e.get();
     m->execs[n] = std::move(e);

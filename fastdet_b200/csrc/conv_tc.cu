@@ -88,7 +88,8 @@ __device__ __forceinline__ float2 bias_act2(uint32_t a0, uint32_t a1, float b0, 
 template <int BLOCK_N>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtensorMap* tm_out, uint32_t taddr0,
                                               uint8_t* stage, int& sbuf, long long m_base, int n0, int lane, int half,
-                                              uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc) {
+                                              uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc,
+                                              int tile = 0, int part = 0, int region = 0) {
     // the two warps that share a TMEM lane quarter split the tile's columns: all 8 epilogue warps work on the same
     // tile, which halves the time the last tile of a launch (nothing left to overlap with) spends here
     constexpr int HALF_N = BLOCK_N >= 64 ? BLOCK_N / 2 : BLOCK_N;
@@ -248,6 +249,64 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
     };
 
     uint32_t acc_a[32], acc_b[32];
+    if (p.split_k > 1) {
+        // ---- split-K: this launch computed only part `part` of the tile's K range
+        const int S = p.split_k;
+        // partial regions: [tile][part][region = CTA rank * 4 + lane quarter][column / 4][32 lanes][4] fp32: a warp's
+        // 16-byte accesses are 512 contiguous bytes (row-major rows made every access 32 separate lines: 20x slower)
+        const size_t region_elems = static_cast<size_t>(32) * BLOCK_N;
+        float* mine = p.ws + ((static_cast<size_t>(tile) * S + part) * 8 + region) * region_elems + lane * 4;
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            ptx::tmem_ld_32x32(taddr0 + c0, acc_a);
+            ptx::tmem_ld_wait();
+            if (c0 + 32 >= c_end) release_tmem();
+#pragma unroll
+            for (int g = 0; g < 8; ++g)
+                *reinterpret_cast<uint4*>(mine + (c0 / 4 + g) * 128) = make_uint4(acc_a[4 * g], acc_a[4 * g + 1], acc_a[4 * g + 2], acc_a[4 * g + 3]);
+        }
+        __threadfence();
+        __syncwarp();
+        int* counter = p.counters + (tile * 8 + region) * 2 + half;
+        int old = 0;
+        if (lane == 0) old = atomicAdd(counter, 1);
+        old = __shfl_sync(0xffffffffu, old, 0);
+        if (old != S - 1) return;  // another part's warp will find the counter full and finish this region
+        __threadfence();
+        fetch_res(c_begin);
+        for (int c0 = c_begin; c0 < c_end; c0 += 32) {
+            float sum[32];
+#pragma unroll
+            for (int e = 0; e < 32; ++e) sum[e] = 0.f;
+            // parts are added in part order (the result does not depend on which part arrived last); the loads of up to
+            // four parts x 16 columns are issued together so that their latencies overlap
+            for (int sp0 = 0; sp0 < S; sp0 += 4) {
+#pragma unroll
+                for (int hcol = 0; hcol < 2; ++hcol) {
+                    float4 v[4][4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const float* src = p.ws + ((static_cast<size_t>(tile) * S + sp0 + k) * 8 + region) * region_elems + lane * 4 + (c0 / 4 + 4 * hcol) * 128;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) v[k][g] = (sp0 + k < S) ? ptx::ld_cg_f4(src + g * 128) : make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        if (sp0 + k >= S) break;
+#pragma unroll
+                        for (int g = 0; g < 4; ++g) {
+                            float* d4 = sum + 16 * hcol + 4 * g;
+                            d4[0] += v[k][g].x; d4[1] += v[k][g].y; d4[2] += v[k][g].z; d4[3] += v[k][g].w;
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 32; ++e) acc_a[e] = __float_as_uint(sum[e]);
+            chunk(acc_a, c0);
+        }
+        if (lane == 0) *counter = 0;  // ready for the next launch that uses this workspace
+        return;
+    }
     ptx::tmem_ld_32x32(taddr0 + c_begin, acc_a);
 #pragma unroll 1
     for (int c0 = c_begin; c0 < c_end; c0 += 64) {
@@ -421,6 +480,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int num_tiles = (p.debug & 32) ? 0 : p.num_m_tiles * p.num_n_tiles;  // TWO: m tiles are 256 rows
+    // work items: (tile, part) with the tile's K blocks cut into split_k parts (1 = whole tiles); every role walks
+    // items unit, unit + units, ... and derives the same K-block range [kb_lo, kb_hi) for each
+    const int split_k = p.split_k;
+    const int num_items = num_tiles * split_k;
     const uint32_t cta_rank = TWO ? ptx::cluster_ctarank() : 0u;
     const int unit = TWO ? (blockIdx.x >> 1) : blockIdx.x;          // tile-stream index of this CTA (pair)
     const int units = TWO ? (gridDim.x >> 1) : gridDim.x;
@@ -480,7 +543,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int stage = 0;
         uint32_t phase = 0;
         long long t_wait = 0;
-        if (b_res && issuer && unit < num_tiles) {
+        if (b_res && issuer && unit < num_items) {
             const uint32_t bar = ptx::smem_u32(bres_bar);
             ptx::mbar_arrive_expect_tx_addr(bar, b_bytes * nkb);
             for (int kb = 0; kb < nkb; ++kb)
@@ -488,7 +551,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ptx::grid_dep_wait();  // weights above are constants; everything below reads the previous layer's output
         const long long t_start = clock64();
-        for (int tile = unit; tile < num_tiles && !(p.debug & 8); tile += units) {
+        for (int item = unit; item < num_items && !(p.debug & 8); item += units) {
+            const int tile = item / split_k, part = item - tile * split_k;
+            const int kb_lo = (part * nkb) / split_k, kb_hi = ((part + 1) * nkb) / split_k;
             const int m_tile = tile / n_tiles_n;
             // normal: m0 = first output pixel (M side), n0 = first output channel (N side)
             // swapped: m0 = first output pixel (N side, 256 per tile), n0 = first output channel (M side, 128 per tile)
@@ -503,9 +568,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 base_w = (rem - oy * wo) * cstride - pad;
                 base_h = oy * cstride - pad;
             }
-            int cb = 0, tap_s = 0, tap_r = 0, kcoord = 0;
-            for (int kb = 0; kb < nkb; kb += kps) {
-                const int nsub = (nkb - kb < kps) ? nkb - kb : kps;
+            const int tap0 = kb_lo / cin_blocks;
+            int cb = kb_lo - tap0 * cin_blocks, tap_r = tap0 / ksize, tap_s = tap0 - (tap0 / ksize) * ksize, kcoord = kb_lo * block_k;
+            for (int kb = kb_lo; kb < kb_hi; kb += kps) {
+                const int nsub = (kb_hi - kb < kps) ? kb_hi - kb : kps;
                 const uint32_t full_addr = bar_base + 8u * stage;
                 const uint32_t lead_bar = TWO ? (full_addr & ptx::kPeerBitMask) : full_addr;
                 const long long tw0 = prof ? clock64() : 0;
@@ -566,7 +632,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool issuer = ptx::elect_one();
         const uint64_t bres_desc0 = ptx::make_kmajor_desc(__shfl_sync(0xffffffffu, ptx::smem_u32(bres), 0), sbo, layout);
         const uint32_t b_units = b_bytes >> 4;
-        if (b_res && unit < num_tiles) {
+        if (b_res && unit < num_items) {
             ptx::mbar_wait(bres_bar, 0);
             ptx::tc_fence_after();
         }
@@ -580,7 +646,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             constexpr int KS = decltype(ks_tag)::value;  // MMAs (16-wide K steps) per K block
             int stage = 0, it = 0;
             uint32_t phase = 0, stage_off = 0;
-            for (int tile = unit; tile < num_tiles; tile += units, ++it) {
+            for (int item = unit; item < num_items; item += units, ++it) {
+                const int part = item % split_k;
+                const int kb_lo = (part * nkb) / split_k, kb_hi = ((part + 1) * nkb) / split_k;
                 const int as = it & 1;
                 const uint32_t aphase = (it >> 1) & 1;
                 const long long tq0 = prof ? clock64() : 0;
@@ -588,9 +656,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (prof) t_tmem += clock64() - tq0;
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BLOCK_N;
-                uint32_t accumulate = 0, bres_off = 0;
-                for (int kb = 0; kb < nkb; kb += kps) {
-                    const int nsub = (nkb - kb < kps) ? nkb - kb : kps;
+                uint32_t accumulate = 0, bres_off = kb_lo * b_units;
+                for (int kb = kb_lo; kb < kb_hi; kb += kps) {
+                    const int nsub = (kb_hi - kb < kps) ? kb_hi - kb : kps;
                     const uint32_t full_addr = bar_base + 8u * stage;
                     const long long tf0 = prof ? clock64() : 0;
                     if (!skip_full_wait) ptx::mbar_wait_addr(full_addr, phase);
@@ -639,7 +707,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int sbuf = 0;
         ptx::grid_dep_wait();  // residual reads / output writes must not overtake the previous layer
         long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_start = clock64();
-        for (int tile = unit; tile < num_tiles; tile += units, ++it) {
+        for (int item = unit; item < num_items; item += units, ++it) {
+            const int tile = item / split_k, part = item - tile * split_k;
             const int as = it & 1;  // accumulator stage
             if (BLOCK_N < 64 && as != half) continue;  // one-chunk tiles: the two warps of a lane quarter alternate tiles
             const uint32_t aphase = (it >> 1) & 1;
@@ -655,7 +724,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
             const long long m_base = static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
             epilogue_tile<BLOCK_N>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
-                                   prof ? t_acc : nullptr);
+                                   prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
         }
         if (lane == 0) ptx::tma_store_wait<0>();  // outstanding TMA stores read this CTA's shared memory
         if (prof && warp == 4 && lane == 0) {
@@ -884,7 +953,25 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     L->block_n = bn;
     L->two_cta = two;
     L->pdl = 1;
-    const long long tiles = m_tiles * p.num_n_tiles;
+    // split-K for launches that cannot fill the GPU with whole tiles (small batches): parts of >= 4 K blocks
+    p.split_k = 1;
+    {
+        static const bool no_split = getenv("FASTDET_NO_SPLITK") != nullptr;
+        const long long whole = m_tiles * p.num_n_tiles;
+        const long long units_max = two ? num_sms / 2 : num_sms;
+        // (a split costs ~8-10 us of fences, counter traffic and partial-sum reads, so it only pays on long K loops)
+        static const int min_kb = getenv("FASTDET_SPLITK_MIN_KB") ? atoi(getenv("FASTDET_SPLITK_MIN_KB")) : 32;
+        static const int max_s = getenv("FASTDET_SPLITK_MAX") ? atoi(getenv("FASTDET_SPLITK_MAX")) : 4;
+        if (d.allow_split_k && !no_split && !swap && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
+            long long sk = units_max / whole;
+            if (sk > max_s) sk = max_s;
+            if (sk > p.num_k_blocks / 4) sk = p.num_k_blocks / 4;
+            if (sk >= 2) p.split_k = static_cast<int>(sk);
+        }
+    }
+    L->ws_bytes = p.split_k > 1 ? static_cast<size_t>(m_tiles * p.num_n_tiles) * p.split_k * 8 * 32 * bn * sizeof(float) : 0;
+    L->counter_ints = p.split_k > 1 ? static_cast<size_t>(m_tiles * p.num_n_tiles) * 16 : 0;
+    const long long tiles = m_tiles * p.num_n_tiles * p.split_k;
     if (two) {
         const long long pairs = num_sms / 2;
         L->grid = 2 * static_cast<int>(tiles < pairs ? tiles : pairs);
@@ -923,7 +1010,13 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     return 0;
 }
 
+void conv_tc_bind_workspace(ConvLaunch* L, float* ws, int* counters) {
+    L->p.ws = ws;
+    L->p.counters = counters;
+}
+
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
+    if (L.p.split_k > 1 && (!L.p.ws || !L.p.counters)) return -1;  // conv_tc_bind_workspace was not called
     static const bool no_pdl = getenv("FASTDET_NO_PDL") != nullptr;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.grid);

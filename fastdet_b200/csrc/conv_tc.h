@@ -34,6 +34,9 @@ struct ConvDesc {
     int out_fp32;
     int upsample2x;  // write every output pixel to its 2x2 nearest-neighbour block of a (2Ho,2Wo) map
     int ho, wo;      // filled by conv_tc_prepare
+    // 1: the layer may be split along K when it has too few tiles to fill the GPU (small batches); the caller then
+    // provides the workspace conv_tc_prepare asks for through conv_tc_bind_workspace before the first launch
+    int allow_split_k;
 };
 
 struct ConvParams {
@@ -56,6 +59,13 @@ struct ConvParams {
     int n_store_limit;
     long long* prof;  // developer: per-CTA cycle counters [grid][16] (null in production)
     int debug;  // developer switches (0 in production): 1 skip epilogue stores, 2 skip A loads, 4 skip MMA issue
+    // split-K (small batches): a tile's K range is cut into split_k parts run by different CTAs; every epilogue warp
+    // writes its fp32 partial region to `ws`, and the warp that arrives last on the region's counter sums the parts in
+    // part order (deterministic) and finishes the tile.  Results do not depend on arrival order, but do depend on
+    // split_k, i.e. on the batch size.
+    int split_k;
+    float* ws;
+    int* counters;
     int store64;   // 1: the output map's box is 64 channels x 32 rows (SWIZZLE_128B), two chunks per TMA store
     int res_v8;    // 1: residual rows are 32-byte aligned -> 256-bit loads
     int epi_mode;  // 0 bf16 slice through a TMA store (+ residual), 1 fp32 head rows, 2 bf16 with x2 upsampling
@@ -72,6 +82,8 @@ struct ConvLaunch {
     int grid;
     int pdl;      // 1: launched with programmatic stream serialisation (overlaps the previous kernel's drain)
     size_t smem_bytes;
+    size_t ws_bytes;      // split-K workspace this launch needs (0: none)
+    size_t counter_ints;  // zero-initialised ints it needs
     double flops;  // algorithmic: 2*M*cout*K
 };
 
@@ -80,6 +92,9 @@ struct ConvLaunch {
 // Returns 0 on success; on failure writes a message to err (if non-null).
 int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* out, char* err, size_t errlen);
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);
+// Split-K launches (L.ws_bytes > 0) need `ws` (>= L.ws_bytes) and `counters` (>= L.counter_ints, zeroed once; the kernel
+// leaves them zero).  Launches of one stream may share both.
+void conv_tc_bind_workspace(ConvLaunch* L, float* ws, int* counters);
 // Tiled bf16 tensor map (rank 2..5) through the driver entry point this library resolves at run time.
 // swizzle: 0 none, 1 32 B, 2 64 B, 3 128 B.  Returns 0 on success.
 int encode_tiled_bf16(CUtensorMap* out, void* base, int rank, const unsigned long long* dims,

@@ -95,9 +95,15 @@ static int run_case(const Case& c, int num_sms) {
         if (conv_halo_launch(H, 0)) { printf("[%s] halo launch failed: %s\n", c.name, cudaGetErrorString(cudaGetLastError())); return 1; }
         L.grid = H.grid;
     } else {
+    d.allow_split_k = 1;
     if (conv_tc_prepare(d, num_sms, c.block_n, &L, err, sizeof(err))) {
         printf("[%s] prepare failed: %s\n", c.name, err);
         return 1;
+    }
+    if (L.ws_bytes) {
+        float* ws; int* cnt;
+        CK(cudaMalloc(&ws, L.ws_bytes)); CK(cudaMalloc(&cnt, L.counter_ints * 4)); CK(cudaMemset(cnt, 0, L.counter_ints * 4));
+        conv_tc_bind_workspace(&L, ws, cnt);
     }
     if (conv_tc_launch(L, 0)) {
         printf("[%s] launch failed: %s\n", c.name, cudaGetErrorString(cudaGetLastError()));
@@ -159,8 +165,15 @@ static int run_case(const Case& c, int num_sms) {
             for (int ch = c.cout; ch < out_pitch; ++ch)
                 if (o[row * out_pitch + ch] != 0xFFFF) ++clobbered;
     }
-    printf("[%-28s] M=%lld N=%d K=%d bn=%d%s%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
-           c.name, M, c.cout, K, L.block_n, L.two_cta ? "x2" : "", L.p.swap ? "swap" : "", L.grid, max_err, max_ref, bad, clobbered,
+    if (L.p.split_k > 1) {  // a second launch on the same workspace: the counters must have been left at zero
+        CK(cudaMemset(dout, 0xFF, out_bytes));
+        if (conv_tc_launch(L, 0) || cudaDeviceSynchronize() != cudaSuccess) { printf("[%s] relaunch failed\n", c.name); return 1; }
+        std::vector<uint8_t> h2(out_bytes);
+        CK(cudaMemcpy(h2.data(), dout, out_bytes, cudaMemcpyDeviceToHost));
+        if (memcmp(h2.data(), hout.data(), out_bytes)) { printf("[%s] split-K relaunch differs\n", c.name); ++bad; }
+    }
+    printf("[%-28s] M=%lld N=%d K=%d bn=%d%s%s%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
+           c.name, M, c.cout, K, L.block_n, L.two_cta ? "x2" : "", L.p.swap ? "swap" : "", L.p.split_k > 1 ? " splitK" : "", L.grid, max_err, max_ref, bad, clobbered,
            (bad == 0 && clobbered == 0) ? "OK" : "FAIL");
     if (bad) printf("    first bad at m=%lld n=%d\n", first_bad_m, first_bad_n);
     cudaFree(dx); cudaFree(dw); cudaFree(dbias); cudaFree(dout);
@@ -192,7 +205,14 @@ static void time_case(const char* name, int n, int h, int cin, int cout, int k, 
     char err[256] = {0};
     __nv_bfloat16* dres = nullptr;
     if (residual) { CK(cudaMalloc(&dres, out_e * 2)); CK(cudaMemset(dres, 0x3C, out_e * 2)); d.residual = dres; d.res_pitch = cout; }
+    d.allow_split_k = getenv("FD_SPLITK") != nullptr;
     if (conv_tc_prepare(d, num_sms, block_n, &L, err, sizeof(err))) { printf("[%s] prepare failed: %s\n", name, err); return; }
+    if (L.ws_bytes) {
+        float* ws; int* cnt;
+        CK(cudaMalloc(&ws, L.ws_bytes)); CK(cudaMalloc(&cnt, L.counter_ints * 4)); CK(cudaMemset(cnt, 0, L.counter_ints * 4));
+        conv_tc_bind_workspace(&L, ws, cnt);
+        printf("    split_k = %d, workspace %.1f MB\n", L.p.split_k, L.ws_bytes / 1e6);
+    }
     L.p.debug = debug;
     if (grid_limit && grid_limit < L.grid) L.grid = grid_limit;
     cudaEvent_t e0, e1;
@@ -331,6 +351,13 @@ int main(int argc, char** argv) {
         for (int g : {148, 74, 37}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, 7, 0, g);
         for (int g : {148, 74, 37}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, 0, 0, g);
         for (int g : {148, 74, 37}) time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0, 0, 0, g);
+    }
+    if (!strcmp(mode, "small")) {
+        time_case("3x3 128->256 @52 bs1", 1, 52, 128, 256, 3, 1, sms, 0);
+        time_case("3x3 256->512 @26 bs1", 1, 26, 256, 512, 3, 1, sms, 0);
+        time_case("3x3 512->1024 @13 bs1", 1, 13, 512, 1024, 3, 1, sms, 0);
+        time_case("1x1 1024->512 @13 bs1", 1, 13, 1024, 512, 1, 1, sms, 0);
+        time_case("3x3 512->1024 @13 bs8", 8, 13, 512, 1024, 3, 1, sms, 0);
     }
     if (!strcmp(mode, "epi")) {
         for (int dbg : {0, 1, 2, 4, 6, 8}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, dbg);

@@ -23,6 +23,12 @@ __device__ __forceinline__ uint4 ld_nc_v4(const uint4* p) {
     return r;
 }
 
+// 16-byte load that bypasses L1 (data written by other CTAs of the same launch: split-K partial sums)
+__device__ __forceinline__ float4 ld_cg_f4(const float* p) {
+    float4 r;
+    asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p) : "memory");
+    return r;
+}
 // 32-byte read-only load (one full L2 sector per lane), no L1 allocation
 struct U32x8 { uint32_t v[8]; };
 __device__ __forceinline__ U32x8 ld_nc_v8(const void* p) {
