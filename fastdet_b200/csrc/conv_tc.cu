@@ -483,10 +483,16 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // work items: (tile, part) with the tile's K blocks cut into split_k parts (1 = whole tiles); every role walks
     // items unit, unit + units, ... and derives the same K-block range [kb_lo, kb_hi) for each
     const int split_k = p.split_k;
-    const int num_items = num_tiles * split_k;
-    const uint32_t cta_rank = TWO ? ptx::cluster_ctarank() : 0u;
-    const int unit = TWO ? (blockIdx.x >> 1) : blockIdx.x;          // tile-stream index of this CTA (pair)
-    const int units = TWO ? (gridDim.x >> 1) : gridDim.x;
+    const bool quad = TWO && p.quad != 0;                             // clusters of two pairs (see ConvParams::quad)
+    const uint32_t cluster_rank = TWO ? ptx::cluster_ctarank() : 0u;
+    const uint32_t cta_rank = cluster_rank & 1u;                     // rank inside the pair
+    const int pair = static_cast<int>(cluster_rank >> 1);             // 0 unless quad
+    const int unit = TWO ? (blockIdx.x >> (quad ? 2 : 1)) : blockIdx.x;  // tile-stream index of this CTA / pair / quad
+    const int units = TWO ? (gridDim.x >> (quad ? 2 : 1)) : gridDim.x;
+    // quad: an item is a "super tile" = M tiles (2i, 2i+1) of one N tile, one per pair (the odd one may lie past the end of
+    // an odd M: its loads are zero-filled and its stores clipped, it only keeps the two pairs' barrier protocol symmetric)
+    const int num_items = quad ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : num_tiles * split_k;
+    auto tile_of = [&](int item) { return quad ? (2 * (item / p.num_n_tiles) + pair) * p.num_n_tiles + item % p.num_n_tiles : item / split_k; };
 
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmA);
@@ -496,7 +502,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], 1);
+            ptx::mbar_init(&empty_bar[i], (TWO && p.quad) ? 2 : 1);  // quad: both pairs' MMAs read what lands in this slot
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
@@ -552,7 +558,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::grid_dep_wait();  // weights above are constants; everything below reads the previous layer's output
         const long long t_start = clock64();
         for (int item = unit; item < num_items && !(p.debug & 8); item += units) {
-            const int tile = item / split_k, part = item - tile * split_k;
+            const int tile = tile_of(item), part = quad ? 0 : item - tile * split_k;
             const int kb_lo = (part * nkb) / split_k, kb_hi = ((part + 1) * nkb) / split_k;
             const int m_tile = tile / n_tiles_n;
             // normal: m0 = first output pixel (M side), n0 = first output channel (N side)
@@ -590,7 +596,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             else
                                 ptx::tma2_load_2d_addr(dst, mapA, lead_bar, cb * block_k, m0);
                         }
-                        ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
+                        if (quad)  // my 64 of the pair-half's 128 filter rows, to me and to my counterpart in the other pair
+                            ptx::tma2_load_2d_mcast_addr(dst + a_bytes + pair * (b_bytes >> 1), mapB, lead_bar, kcoord, n0 + pair * (B_ROWS >> 1),
+                                                         static_cast<uint16_t>(0x5u << cta_rank));
+                        else
+                            ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
                     } else {
                         // pixels go to the slot of the side they occupy in the MMA (slot 0 = M side, slot 1 = N side)
                         const uint32_t dst_x = swap ? dst + a_bytes : dst, dst_w = swap ? dst : dst + a_bytes;
@@ -674,7 +684,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         bres_off += b_units;
                     }
                     if (issuer) {  // smem slot free (in both CTAs) once these MMAs retire
-                        if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
+                        if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, quad ? 0xF : 3);
                         else ptx::umma_commit_addr(full_addr + 8u * MAX_STAGES);
                     }
                     __syncwarp();
@@ -683,7 +693,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 // accumulator complete (each CTA of a pair drains its own 128 rows)
                 if (issuer) {
-                    if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, 3);
+                    if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, static_cast<uint16_t>(3u << (2 * pair)));
                     else ptx::umma_commit_addr(tmem_full_addr + 8u * as);
                 }
                 __syncwarp();
@@ -708,7 +718,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::grid_dep_wait();  // residual reads / output writes must not overtake the previous layer
         long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_start = clock64();
         for (int item = unit; item < num_items; item += units, ++it) {
-            const int tile = item / split_k, part = item - tile * split_k;
+            const int tile = tile_of(item), part = quad ? 0 : item - tile * split_k;
             const int as = it & 1;  // accumulator stage
             if (BLOCK_N < 64 && as != half) continue;  // one-chunk tiles: the two warps of a lane quarter alternate tiles
             const uint32_t aphase = (it >> 1) & 1;
@@ -852,6 +862,8 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     else if (block_n_hint) swap = 0;
     if (swap) block_n_hint = 257;
     int two = -1;  // -1: decide below
+    int force_quad = 0;
+    if (block_n_hint == 768) { two = 1; force_quad = 1; block_n_hint = 256; }  // developer: CTA pairs in clusters of 4
     if (block_n_hint == 512) { two = 1; block_n_hint = 256; }
     if (block_n_hint == 257) { two = 0; block_n_hint = 256; }
     int bn = block_n_hint ? block_n_hint : choose_block_n(d.cout, m_tiles, num_sms);
@@ -860,6 +872,12 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     if (two < 0) two = (bn == 256 && block_k == 64 && m_tiles >= 2 && !getenv("FASTDET_NO_2CTA")) ? 1 : 0;
     if (two && (bn != 256 || block_k != 64)) { set_err(err, errlen, "conv_tc: the CTA-pair kernel needs Cout > 128 and Cin %% 64 == 0"); return -1; }
     if (two) m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+    // clusters of two pairs sharing the filter tile.  OFF by default: measured on B200 the multicast does not raise the
+    // per-CTA operand rate (738 -> 812 cycles per K block; multicast into <= 4 CTAs behaves like unicast) and only 32
+    // clusters of 4 are co-resident (128 of 148 SMs).  FASTDET_QUAD=1 enables it for experiments.
+    static const int quad_env = getenv("FASTDET_QUAD") ? atoi(getenv("FASTDET_QUAD")) : 0;
+    const int quads_max = num_sms / 4;
+    const int quad = (two && (force_quad || (quad_env && ((m_tiles + 1) / 2) * ((d.cout + bn - 1) / bn) >= 2LL * quads_max))) ? 1 : 0;
     if (swap) m_tiles = (M + 255) / 256;
     ConvParams& p = L->p;
     p.M = static_cast<int>(M);
@@ -929,7 +947,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.cout)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(swap ? BLOCK_M : (two ? bn / 2 : bn))};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(swap ? BLOCK_M : (two ? (quad ? bn / 4 : bn / 2) : bn))};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -952,6 +970,8 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     }
     L->block_n = bn;
     L->two_cta = two;
+    L->quad = quad;
+    p.quad = quad;
     L->pdl = 1;
     // split-K for launches that cannot fill the GPU with whole tiles (small batches): parts of >= 4 K blocks
     p.split_k = 1;
@@ -962,7 +982,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
         // (a split costs ~8-10 us of fences, counter traffic and partial-sum reads, so it only pays on long K loops)
         static const int min_kb = getenv("FASTDET_SPLITK_MIN_KB") ? atoi(getenv("FASTDET_SPLITK_MIN_KB")) : 32;
         static const int max_s = getenv("FASTDET_SPLITK_MAX") ? atoi(getenv("FASTDET_SPLITK_MAX")) : 4;
-        if (d.allow_split_k && !no_split && !swap && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
+        if (d.allow_split_k && !no_split && !swap && !quad && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
             long long sk = units_max / whole;
             if (sk > max_s) sk = max_s;
             if (sk > p.num_k_blocks / 4) sk = p.num_k_blocks / 4;
@@ -972,7 +992,10 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     L->ws_bytes = p.split_k > 1 ? static_cast<size_t>(m_tiles * p.num_n_tiles) * p.split_k * 8 * 32 * bn * sizeof(float) : 0;
     L->counter_ints = p.split_k > 1 ? static_cast<size_t>(m_tiles * p.num_n_tiles) * 16 : 0;
     const long long tiles = m_tiles * p.num_n_tiles * p.split_k;
-    if (two) {
+    if (quad) {
+        const long long supers = ((m_tiles + 1) / 2) * p.num_n_tiles;
+        L->grid = 4 * static_cast<int>(supers < quads_max ? supers : quads_max);
+    } else if (two) {
         const long long pairs = num_sms / 2;
         L->grid = 2 * static_cast<int>(tiles < pairs ? tiles : pairs);
     } else {
@@ -1027,7 +1050,7 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
     int na = 0;
     if (L.two_cta) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = 2;
+        attr[na].val.clusterDim.x = L.quad ? 4 : 2;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;

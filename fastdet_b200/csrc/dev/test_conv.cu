@@ -173,7 +173,7 @@ static int run_case(const Case& c, int num_sms) {
         if (memcmp(h2.data(), hout.data(), out_bytes)) { printf("[%s] split-K relaunch differs\n", c.name); ++bad; }
     }
     printf("[%-28s] M=%lld N=%d K=%d bn=%d%s%s%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
-           c.name, M, c.cout, K, L.block_n, L.two_cta ? "x2" : "", L.p.swap ? "swap" : "", L.p.split_k > 1 ? " splitK" : "", L.grid, max_err, max_ref, bad, clobbered,
+           c.name, M, c.cout, K, L.block_n, L.two_cta ? (L.quad ? "x4" : "x2") : "", L.p.swap ? "swap" : "", L.p.split_k > 1 ? " splitK" : "", L.grid, max_err, max_ref, bad, clobbered,
            (bad == 0 && clobbered == 0) ? "OK" : "FAIL");
     if (bad) printf("    first bad at m=%lld n=%d\n", first_bad_m, first_bad_n);
     cudaFree(dx); cudaFree(dw); cudaFree(dbias); cudaFree(dout);
@@ -291,6 +291,11 @@ int main(int argc, char** argv) {
             {"2cta 1x1 256->256 up",    2, 13, 13, 256, 256, 1, 1, 0, 0, 1, 0, 0, 1, 64, 512},
             {"2cta 3x3 128->256 big",   16, 52, 52, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
             {"1cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 257},
+            {"quad 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 768},
+            {"quad 3x3 64->256 odd M",  4, 13, 13, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 768},
+            {"quad 1x1 512->256 many",  8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 1, 0, 0, 0, 768},
+            {"quad 1x1 256->255 fp32",  2, 13, 13, 256, 255, 1, 1, 0, 0, 0, 0, 1, 0, 0, 768},
+            {"quad 3x3 128->256 big",   16, 52, 52, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 768},
             {"3x3 16->32 s1 (bk16)",    2, 20, 20, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
             {"halo 3x3 32->64 s1 res",  2, 72, 76, 32, 64, 3, 1, 1, 1, 1, 1, 0, 0, 0, 2048},
             {"halo 3x3 32->64 s2",      2, 130, 134, 32, 64, 3, 2, 1, 1, 1, 0, 0, 0, 0, 2048},
@@ -351,6 +356,14 @@ int main(int argc, char** argv) {
         for (int g : {148, 74, 37}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, 7, 0, g);
         for (int g : {148, 74, 37}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, 0, 0, g);
         for (int g : {148, 74, 37}) time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0, 0, 0, g);
+    }
+    if (!strcmp(mode, "quad")) {
+        for (int bn : {512, 768}) {
+            time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, bn);
+            time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, bn);
+            time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, bn);
+        }
+        for (int g : {148, 128, 112, 96, 64}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 768, 0, 0, g);
     }
     if (!strcmp(mode, "small")) {
         time_case("3x3 128->256 @52 bs1", 1, 52, 128, 256, 3, 1, sms, 0);

@@ -163,6 +163,15 @@ __device__ __forceinline__ void tma2_load_2d_addr(uint32_t dst, uint64_t map, ui
         "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+// CTA-pair load multicast to the CTAs in `cta_mask` (cluster ranks): the box lands at the same shared-memory offset in
+// every destination CTA and its bytes are counted on the barrier at `bar`'s offset in each destination's pair leader.
+__device__ __forceinline__ void tma2_load_2d_mcast_addr(uint32_t dst, uint64_t map, uint32_t bar, int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
+        " [%0], [%1, {%4, %5}], [%2], %3;" ::"r"(dst),
+        "l"(map), "r"(bar), "h"(cta_mask), "r"(c0), "r"(c1)
+        : "memory");
+}
 __device__ __forceinline__ void tma2_load_im2col_4d_addr(uint32_t dst, uint64_t map, uint32_t bar, int c, int w, int h,
                                                          int n, uint16_t ow, uint16_t oh) {
     asm volatile(
