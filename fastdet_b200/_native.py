@@ -13,7 +13,7 @@ from typing import List, Optional, Sequence, Tuple
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfastdet_b200.so")
+LIB_PATH = os.environ.get("FASTDET_LIB") or os.path.join(_HERE, "libfastdet_b200.so")  # FASTDET_LIB: developer A/B runs
 
 FD_OK, FD_ERR_ARG, FD_ERR_MODEL, FD_ERR_HEADS, FD_ERR_CUDA, FD_ERR_SIZE = 0, -1, -2, -3, -4, -5
 FD_MAX_HEADS = 4
