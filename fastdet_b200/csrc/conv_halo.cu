@@ -215,6 +215,20 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                 }
             };
             fetch_res(0);
+            if (has_res && it + 2 < my_tiles) {
+                // pull the NEXT tile's residual rows (this lane's pixel, all channels) towards L2 now: no registers held,
+                // and the loads above then come from L2 instead of DRAM (they were the epilogue's largest stall)
+                const int tile2 = blockIdx.x + (it + 2) * gridDim.x;
+                const int f2 = div_magic(tile2, p.m_per_frame);
+                const int rem2 = tile2 - f2 * per_frame;
+                const int ty2 = div_magic(rem2, p.m_tiles_x), tx2 = rem2 - ty2 * tiles_x;
+                const int oy2 = ty2 * TH + 4 * quarter + (lane >> 3), ox2 = tx2 * TW + (lane & 7);
+                if (oy2 < p.ho && ox2 < p.wo) {
+                    const __nv_bfloat16* r2 = p.residual + ((static_cast<long long>(f2) * p.ho + oy2) * p.wo + ox2) * p.res_pitch;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(r2));
+                    if (cout > 64) asm volatile("prefetch.global.L2 [%0];" ::"l"(r2 + 64));
+                }
+            }
             ptx::mbar_wait(&acc_full[as], (it >> 2) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem + as * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
