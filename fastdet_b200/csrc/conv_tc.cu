@@ -330,9 +330,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
 // a narrow Cout cannot be N).  Lane = channel: bias is a per-lane scalar; a 32-pixel column chunk is staged to shared
 // memory transposed ([pixel][32 channels] bf16) and re-read so that 4 lanes cover the 64 contiguous bytes this warp
 // owns of one pixel row.
-__device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint32_t taddr0, float* stage_buf, int ch_warp,
-                                                      long long pix0, int lane, int half, uint32_t full_addr, uint32_t aphase,
-                                                      uint32_t empty_addr, long long* t_acc) {
+__device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const CUtensorMap* tm_out, int& sbuf, uint32_t taddr0,
+                                                      float* stage_buf, int ch_warp, long long pix0, int lane, int half,
+                                                      uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc) {
     const int hw = p.ho * p.wo;
     const int sub = lane >> 2, j = lane & 3;
     const bool warp_has_channels = ch_warp < p.cout;
@@ -343,6 +343,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
     const bool generic_act = p.act == 2;
     const float alpha_eff = p.act ? p.alpha : 1.0f;
     const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
+    const bool tma_path = p.epi_mode == 0 && !has_res && p.swap_tma;  // plain bf16 slice: staged rows leave through TMA stores
 
     const long long ta0 = t_acc ? clock64() : 0;
     ptx::mbar_wait_addr(full_addr, aphase);
@@ -364,6 +365,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
         uint4 res[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
+            if (tma_path) { ok[i] = false; orow[i] = 0; res[i] = make_uint4(0u, 0u, 0u, 0u); continue; }
             const long long m = pix0 + c0 + 8 * i + sub;
             ok[i] = warp_has_channels && m < p.M && ch < p.cout;
             orow[i] = m;
@@ -385,6 +387,32 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, uint3
         }
         lap(1);
         if (!warp_has_channels || (p.debug & 1)) continue;
+        if (tma_path) {
+            // lane = channel: element (pixel q, channel lane) goes to row q of a 32-pixel x 64-byte bf16 tile (64-byte
+            // swizzle: 16-byte chunk (lane >> 3) of row q sits at slot (lane >> 3) ^ ((q >> 1) & 3)) that one TMA store
+            // writes out — no shared-memory loads, no per-thread global stores
+            uint8_t* buf = reinterpret_cast<uint8_t*>(stage_buf) + (sbuf & 1) * 2048;
+            if (lane == 0) ptx::tma_store_wait_read<1>();  // the store that last read this buffer (two chunks ago) is done with it
+            __syncwarp();
+            const uint32_t lane_chunk = static_cast<uint32_t>(lane) >> 3, lane_byte = (static_cast<uint32_t>(lane) & 7u) * 2u;
+#pragma unroll
+            for (int q = 0; q < 32; q += 2) {
+                const float2 x = generic_act ? bias_act2<true>(acc[q], acc[q + 1], bias_own, bias_own, alpha2)
+                                             : bias_act2<false>(acc[q], acc[q + 1], bias_own, bias_own, alpha2);
+                const uint32_t slot = (lane_chunk ^ ((static_cast<uint32_t>(q) >> 1) & 3u)) << 4;  // rows q and q+1 share (q >> 1)
+                *reinterpret_cast<__nv_bfloat16*>(buf + q * 64 + slot + lane_byte) = __float2bfloat16(x.x);
+                *reinterpret_cast<__nv_bfloat16*>(buf + (q + 1) * 64 + slot + lane_byte) = __float2bfloat16(x.y);
+            }
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_2d(tm_out, buf, ch_warp, static_cast<int>(pix0 + c0));  // pixels >= M / channels >= Cout are clipped
+                ptx::tma_store_commit();
+            }
+            ++sbuf;
+            lap(3);
+            continue;
+        }
         // channel-major phase: + bias, LeakyReLU; element (pixel q, channel lane) -> stage_buf[q][lane] (fp32: one
         // conflict-free 128-byte row per store instruction)
         if (!generic_act) {
@@ -498,7 +526,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tma_prefetch_desc(&tmA);
         ptx::tma_prefetch_desc(&tmB);
     }
-    if (warp == 4 && lane == 0 && p.epi_mode == 0) ptx::tma_prefetch_desc(&tmOut);
+    if (warp == 4 && lane == 0 && p.epi_mode == 0) ptx::tma_prefetch_desc(&tmOut);  // (a valid map in every mode)
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
@@ -727,8 +755,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_tile = tile / n_tiles_n;
             if (swap) {
                 const int ch_warp = (tile - m_tile * n_tiles_n) * BLOCK_M + quarter * 32;
-                epilogue_tile_swapped(p, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256, lane,
-                                      half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
+                epilogue_tile_swapped(p, &tmOut, sbuf, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256,
+                                      lane, half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
                 continue;
             }
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
@@ -954,11 +982,13 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map B encode failed (CUresult %lld)", r); return -1; }
     }
-    if (p.epi_mode == 0 && !swap) {
+    static const bool no_swap_tma = getenv("FASTDET_NO_SWAP_TMA") != nullptr;
+    p.swap_tma = (swap && !no_swap_tma) ? 1 : 0;
+    if (p.epi_mode == 0 && (!swap || p.swap_tma)) {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.cout), static_cast<cuuint64_t>(M)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_pitch) * 2};
         static const bool no64 = getenv("FASTDET_NO_STORE64") != nullptr;
-        p.store64 = (bn >= 128 && !no64) ? 1 : 0;  // 128-byte store rows (two 32-column chunks per TMA store)
+        p.store64 = (bn >= 128 && !no64 && !swap) ? 1 : 0;  // 128-byte store rows (two 32-column chunks per TMA store)
         cuuint32_t box[2] = {p.store64 ? 64u : 32u, 32};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, dims, strides, box, estr,
