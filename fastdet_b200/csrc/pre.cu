@@ -554,7 +554,8 @@ static constexpr int C0W_PPL = (C0D_PH * C0D_PW + 31) / 32;  // patch pixels per
 __global__ void __launch_bounds__(C0W_THREADS)
 conv0_ws_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wgt, const float* __restrict__ bias,
                 const __grid_constant__ CUtensorMap tm_out, int n, int h, int wd, int cout, int act, float alpha,
-                unsigned long long m_per_frame, unsigned long long m_tiles_x) {
+                unsigned long long m_per_frame, unsigned long long m_tiles_x, __nv_bfloat16* __restrict__ out, int out_pitch,
+                int direct_store) {
     extern __shared__ __align__(1024) uint8_t c0w_dyn[];        // patch ring
     uint8_t (*s_patch)[C0D_PATCH_BYTES] = reinterpret_cast<uint8_t (*)[C0D_PATCH_BYTES]>(c0w_dyn);
     __shared__ __align__(1024) uint8_t s_w[12 * 32 * 16];       // B: [K chunk 0..11][32 filters][16 B]
@@ -755,12 +756,24 @@ conv0_ws_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wg
                 }
                 pk[c] = c0_pack(x.x, x.y);
             }
+            if (direct_store) {
+                // straight from the registers: a lane owns one pixel's cout channels (64 contiguous bytes), 8 lanes an image
+                // row segment of 512 bytes.  Per tile this costs 4 store instructions of 32 sectors each, against the
+                // ~500 cycles a proxy fence + TMA store round costs this small-tile kernel (ncu source page)
+                const int oy = ty * C0D_TH + 4 * quarter + (lane >> 3), ox = tx * C0D_TW + (lane & 7);
+                if (oy < h && ox < wd) {
+                    __nv_bfloat16* op = out + ((static_cast<long long>(f) * h + oy) * wd + ox) * out_pitch;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c)
+                        if (8 * c < cout) *reinterpret_cast<uint4*>(op + 8 * c) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
+                continue;
+            }
             uint8_t* so = s_out[warp];
             if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store (two tiles ago) has finished reading the buffer
             __syncwarp();
             // dense rows [4 image rows][8 pixels][cout]: with pitch == cout the 8 pixels of an image row are one contiguous
-            // 8*cout*2-byte run in global memory, so the TMA store moves 4 wide rows instead of 32 narrow ones (the L2
-            // takes ~1 request per 3 cycles per SM whatever its size; 64-byte rows made this kernel request-bound)
+            // 8*cout*2-byte run in global memory: the TMA store moves 4 wide rows
             if (cout == 32) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c)  // (un-swizzled: 4-way bank conflicts on 4 stores per tile, noise)
@@ -800,6 +813,7 @@ int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __
     const int act_mode = act ? ((alpha >= 0.f && alpha <= 1.f) ? 1 : 2) : 0;
     if (variant == 0 && (cout == 16 || cout == 32) && out_pitch % 8 == 0 && (reinterpret_cast<uintptr_t>(out) & 15) == 0) {
         static const bool lockstep = getenv("FASTDET_C0_LOCKSTEP") != nullptr;
+        static const int c0_direct = getenv("FASTDET_C0_DIRECT") ? atoi(getenv("FASTDET_C0_DIRECT")) : 0;  // measured slower (293 vs 255 us)
         CUtensorMap tm;
         if (lockstep || out_pitch != cout) {
             if (!lockstep) return -1;  // (the planner gives the first layer a dense output)
@@ -825,7 +839,8 @@ int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __
             if (tiles >= (1LL << 24) || per_frame >= 4096 * 16) return -1;  // range of the multiply-shift division
             const unsigned long long one40 = 1ULL << 40;
             conv0_ws_kernel<<<blocks, C0W_THREADS, C0W_PATCHES * C0D_PATCH_BYTES, s>>>(frames, w, bias, tm, n, h, wd, cout, act_mode, alpha,
-                                                          (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx);
+                                                          (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx, out, out_pitch,
+                                                          c0_direct);
         }
         return cudaGetLastError() == cudaSuccess ? 0 : -1;
     }
