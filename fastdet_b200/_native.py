@@ -64,6 +64,7 @@ _PROTOS = {
                             C.c_void_p, C.c_void_p]),
     "fd_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
     "fd_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_pack_wire": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fd_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_set_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_layer_output_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -247,6 +248,20 @@ class Model:
         ms = np.zeros(self.info.n_layers, np.float32)
         _check(lib().fd_time_layers(self._h, n, reps, _ptr(ms)))
         return ms
+
+
+def pack_wire(dets: np.ndarray, reqid: int = 0, msec: int = 0, saturate: bool = False) -> bytes:
+    """The reference server's response payload (server/server.py:234-239) for one frame's detections (a DET_DTYPE array,
+    already cut to its count).  saturate=False raises struct.error where struct.pack would."""
+    import struct
+    dets = np.ascontiguousarray(dets, DET_DTYPE)
+    buf = np.empty(16 + 10 * len(dets), np.uint8)
+    n = C.c_size_t()
+    rc = lib().fd_pack_wire(_ptr(dets), len(dets), reqid & 0xFFFFFFFF, msec & 0xFFFFFFFF, int(saturate), _ptr(buf), buf.size, C.byref(n))
+    if rc == FD_ERR_ARG and not saturate:
+        raise struct.error((lib().fd_last_error() or b"").decode("utf-8", "replace"))
+    _check(rc)
+    return buf[:n.value].tobytes()
 
 
 def device_count() -> int:

@@ -584,6 +584,40 @@ int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* tot
     return FD_OK;
 }
 
+// ------------------------------------------------------------------ wire format (reference server/server.py:234-239)
+int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, int saturate, uint8_t* out, size_t cap, size_t* len) {
+    if ((!dets && count > 0) || !out || !len || count < 0) return fail(FD_ERR_ARG, "fd_pack_wire: bad argument");
+    const size_t need = 16 + 10 * static_cast<size_t>(count);
+    if (cap < need) return fail(FD_ERR_ARG, "fd_pack_wire: buffer of %zu bytes, %zu needed", cap, need);
+    auto be32 = [](uint8_t* p, uint32_t v) { p[0] = v >> 24; p[1] = (v >> 16) & 255; p[2] = (v >> 8) & 255; p[3] = v & 255; };
+    memcpy(out, "YOLO", 4);
+    be32(out + 4, reqid);
+    be32(out + 8, msec);
+    be32(out + 12, static_cast<uint32_t>(10 * count));
+    uint8_t* r = out + 16;
+    for (int i = 0; i < count; ++i, r += 10) {
+        const fd_det& d = dets[i];
+        long long v[6] = {d.klass, static_cast<long long>(d.conf * 255.0), static_cast<long long>(d.x), static_cast<long long>(d.y),
+                          static_cast<long long>(d.w), static_cast<long long>(d.h)};  // (long long)double truncates toward zero like int()
+        for (int k = 0; k < 6; ++k) {
+            const long long lo = k < 2 ? 0 : -32768, hi = k < 2 ? 255 : 32767;
+            if (v[k] < lo || v[k] > hi) {
+                if (!saturate) return fail(FD_ERR_ARG, "fd_pack_wire: detection %d field %d = %lld does not fit the wire format", i, k, v[k]);
+                v[k] = v[k] < lo ? lo : hi;
+            }
+        }
+        r[0] = static_cast<uint8_t>(v[0]);
+        r[1] = static_cast<uint8_t>(v[1]);
+        for (int k = 0; k < 4; ++k) {
+            const uint16_t u = static_cast<uint16_t>(static_cast<int16_t>(v[2 + k]));
+            r[2 + 2 * k] = u >> 8;
+            r[3 + 2 * k] = u & 255;
+        }
+    }
+    *len = need;
+    return FD_OK;
+}
+
 // ------------------------------------------------------------------ parity / profiling hooks
 static int tensor_to_host_nchw(fd_model* m, Exec* e, const TensorLoc& t, bool fp32, float* dst, int n) {
     const size_t elems = size_t(n) * t.c * t.h * t.w;

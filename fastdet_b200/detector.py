@@ -12,6 +12,7 @@ named ``detector`` (:17) and needs nothing else.
 
 Additive extras (not in the reference): ``image_size=`` and ``device=`` keyword arguments,
 ``perform_batch`` / ``perform_frames`` for decoded RGB frames, ``perform_stream`` (pipelined batches),
+``perform_wire`` (results already in the server's wire format),
 ``forward_raw`` for parity tests.
 ``mode`` is accepted and stored like the reference does; every mode runs on the B200 — there is no
 CPU execution provider here and no fallback.
@@ -123,6 +124,25 @@ class ONNXDetector(Detector):
             out.append([(int(k), float(c), float(x), float(y), float(w), float(h))
                         for k, c, x, y, w, h in zip(d['klass'], d['conf'], d['x'], d['y'], d['w'], d['h'])])
         return out
+
+    def perform_wire(self, data, threshold=0.1, reqid=0, saturate=False):
+        """perform() + the reference server's response packing (server/server.py:231-239) in one call: returns the
+        bytes DetectService.send() would be given (16-byte 'YOLO' header + 10 bytes per detection), built by the
+        native library straight from the detection records (no per-detection Python objects)."""
+        super().perform(data)
+        from PIL import Image
+        (width, height) = self.image_size
+        img = Image.open(io.BytesIO(data))
+        if img.size != self.image_size:
+            raise ValueError('invalid image size')
+        frame = np.array(img)
+        if frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError(f'cannot reshape array of size {frame.size} into shape (1,{height},{width},3)')
+        self.ANCHORS[self.model.n_heads]
+        t0 = time.time()
+        dets, counts = self.model.detect(frame.reshape(1, height, width, 3), threshold, max_det=self.max_det)
+        msec = int((time.time() - t0) * 1000)
+        return _native.pack_wire(dets[0, :counts[0]], reqid, msec, saturate)
 
     def perform_stream(self, batches, threshold=0.1, allow_resize=False):
         """Generator over an iterable of [n, h, w, 3] u8 batches: yields one list of per-frame result lists per

@@ -1,0 +1,115 @@
+"""service.py — micro-batching front end behind the reference's ``perform`` signature.
+
+The reference serves every UDP payload with one blocking ``detector.perform(data, threshold)`` call
+(server/server.py:225-241), so all sessions of a model share batch-1 latency.  ``BatchingService`` keeps that call
+signature — ``perform(data, threshold) -> [(klass, conf, x, y, w, h), ...]``, same exceptions — but lets many threads
+(one per session / stream) call it at once: requests that arrive within ``max_delay`` seconds are decoded in their
+caller's thread, stacked, and run as ONE batch through the detector (pipelined ``perform_stream`` when several batches
+are waiting), and every caller gets exactly the list ``detector.perform`` would have returned for its frame.
+"""
+import io
+import threading
+import time
+from collections import deque
+
+import numpy as np
+
+
+class _Request:
+    __slots__ = ("frame", "threshold", "event", "result", "error")
+
+    def __init__(self, frame, threshold):
+        self.frame = frame
+        self.threshold = threshold
+        self.event = threading.Event()
+        self.result = None
+        self.error = None
+
+
+class BatchingService:
+    """detector: an object with ``image_size`` and ``perform_frames(frames_u8[n,h,w,3], threshold) -> [list per frame]``
+    (fastdet_b200.detector.ONNXDetector).  Thread-safe; ``close()`` stops the worker."""
+
+    def __init__(self, detector, max_batch=64, max_delay=0.002):
+        self.detector = detector
+        self.image_size = tuple(detector.image_size)
+        self.max_batch = int(max_batch)
+        self.max_delay = float(max_delay)
+        self.batches_run = 0
+        self.frames_run = 0
+        self._queue = deque()
+        self._cond = threading.Condition()
+        self._closed = False
+        self._worker = threading.Thread(target=self._run, name="fastdet-batcher", daemon=True)
+        self._worker.start()
+
+    # -- the reference entry point (server/detector.py:126-146), callable from many threads
+    def perform(self, data, threshold=0.1):
+        from PIL import Image
+        (width, height) = self.image_size
+        img = Image.open(io.BytesIO(data))  # decode in the caller's thread: it parallelises across sessions
+        if img.size != self.image_size:
+            raise ValueError('invalid image size')
+        frame = np.array(img)
+        if frame.ndim != 3 or frame.shape[2] != 3:
+            raise ValueError(f'cannot reshape array of size {frame.size} into shape (1,{height},{width},3)')
+        return self.perform_frame(frame, threshold)
+
+    def perform_frame(self, frame, threshold=0.1):
+        """One decoded RGB frame [h, w, 3] u8."""
+        req = _Request(np.ascontiguousarray(frame, np.uint8), float(threshold))
+        with self._cond:
+            if self._closed:
+                raise RuntimeError("BatchingService is closed")
+            self._queue.append(req)
+            self._cond.notify()
+        req.event.wait()
+        if req.error is not None:
+            raise req.error
+        return req.result
+
+    def close(self):
+        with self._cond:
+            self._closed = True
+            self._cond.notify()
+        self._worker.join()
+
+    # -- worker: one batch per distinct threshold among the waiting requests
+    def _take(self):
+        with self._cond:
+            while not self._queue and not self._closed:
+                self._cond.wait()
+            if not self._queue:
+                return None
+            deadline = time.monotonic() + self.max_delay
+            while len(self._queue) < self.max_batch and not self._closed:
+                left = deadline - time.monotonic()
+                if left <= 0:
+                    break
+                self._cond.wait(left)
+            first = self._queue[0].threshold
+            batch, rest = [], deque()
+            while self._queue and len(batch) < self.max_batch:
+                r = self._queue.popleft()
+                (batch if r.threshold == first else rest).append(r)
+            rest.extend(self._queue)
+            self._queue = rest
+            return batch
+
+    def _run(self):
+        while True:
+            batch = self._take()
+            if batch is None:
+                return
+            try:
+                frames = np.stack([r.frame for r in batch])
+                results = self.detector.perform_frames(frames, threshold=batch[0].threshold)
+                for r, res in zip(batch, results):
+                    r.result = res
+            except Exception as e:  # every caller of the batch sees the failure, the worker lives on
+                for r in batch:
+                    r.error = e
+            self.batches_run += 1
+            self.frames_run += len(batch)
+            for r in batch:
+                r.event.set()

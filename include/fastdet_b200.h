@@ -113,6 +113,15 @@ int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, in
               int allow_resize, double threshold, int max_det);
 int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* total);
 
+/* Wire-format packer (host only, no device needed): the response payload the reference builds per request in
+ * DetectService.process_data (server/server.py:234-239): a 16-byte big-endian header '>4sLLL' = (b"YOLO", reqid, msec,
+ * payload length) followed by one 10-byte record '>BBhhhh' = (klass, int(conf*255), int(x), int(y), int(w), int(h)) per
+ * detection, int() truncating toward zero.  saturate = 0 mirrors struct.pack: a klass outside 0..255 or a coordinate
+ * outside int16 returns FD_ERR_ARG (the reference raises struct.error and its server loop dies); saturate != 0 clamps
+ * instead.  *len receives the bytes written; cap must be >= 16 + 10 * count. */
+int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, int saturate, uint8_t* out, size_t cap,
+                 size_t* len);
+
 /* ---- parity / profiling hooks (synchronous; host pointers) ---- */
 /* Raw head tensor `head` of the last forward as f32 NCHW [n, C, H, W] — what model.run returns. */
 int fd_heads_fp32(fd_model* m, int head, float* dst_nchw, int n);

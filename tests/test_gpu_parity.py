@@ -437,3 +437,46 @@ def test_pipelined_submit_collect_equals_detect():
     det = fdet.ONNXDetector(data, num_classes=80, max_det=128)
     streamed = list(det.perform_stream(batches, threshold=0.1))
     assert streamed == [det.perform_frames(b, threshold=0.1) for b in batches]
+
+
+def test_wire_format_and_batching_service_on_device():
+    """perform_wire == the reference's struct.pack of perform's tuples; BatchingService.perform under
+    concurrent callers == detector.perform frame by frame."""
+    import threading
+    from PIL import Image
+    from fastdet_b200 import service
+    from oracle import ref_wire
+    data = modelgen.build_onnx("tiny", 80, 416, 1)
+    det = fdet.ONNXDetector(data, num_classes=80, max_det=256)
+    pngs = []
+    for s in range(6):
+        buf = io.BytesIO()
+        Image.fromarray(modelgen.synthetic_frame(500 + s, 416), "RGB").save(buf, format="PNG")
+        pngs.append(buf.getvalue())
+    want = [det.perform(p, threshold=0.1) for p in pngs]
+    assert any(want)
+    for p, w in zip(pngs, want):
+        wire = det.perform_wire(p, threshold=0.1, reqid=42)
+        ref = ref_wire.pack_results(w, 42, 0)
+        assert wire[:8] == ref[:8] and wire[12:] == ref[12:]  # everything but the elapsed-milliseconds field
+    svc = service.BatchingService(det, max_batch=8, max_delay=0.05)
+    got = [None] * len(pngs)
+
+    def call(i):
+        got[i] = svc.perform(pngs[i], threshold=0.1)
+
+    threads = [threading.Thread(target=call, args=(i,)) for i in range(len(pngs))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    svc.close()
+    assert svc.batches_run < len(pngs)
+    # a frame's tuples do not depend on the batch it rode in beyond the split-K reassociation (see DESIGN.md): same
+    # boxes / classes, scores within the spec's 1e-2
+    for g, w in zip(got, want):
+        gs = {(k, round(x), round(y)): c for k, c, x, y, _, _ in g if c >= 0.11}
+        ws = {(k, round(x), round(y)): c for k, c, x, y, _, _ in w if c >= 0.11}
+        common = set(gs) & set(ws)
+        assert len(common) >= max(len(gs), len(ws)) - 2
+        assert all(abs(gs[k] - ws[k]) <= 1e-2 for k in common)

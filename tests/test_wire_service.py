@@ -1,0 +1,97 @@
+"""CPU tests of the two SURVEY §8f "next" rows built so far: the wire-format packer (native, host-only) against the
+reference's struct.pack lines, and the micro-batching service's host logic with a stand-in detector."""
+import io
+import struct
+import threading
+
+import numpy as np
+import pytest
+
+from fastdet_b200 import _native, service
+from oracle import ref_wire
+
+
+def _dets(rows):
+    a = np.zeros(len(rows), _native.DET_DTYPE)
+    for i, (k, c, x, y, w, h) in enumerate(rows):
+        a[i] = (k, i, c, x, y, w, h)
+    return a
+
+
+def test_pack_matches_reference_dummy_detector_answer():
+    # the one fixed answer the reference ships: DummyDetector.perform (server/detector.py:83-92) at 416x416
+    results = [(16, 1.0, 208.0, 208.0, 166.4, 166.4)]
+    want = ref_wire.pack_results(results, reqid=7, msec=12)
+    assert want == struct.pack('>4sLLL', b'YOLO', 7, 12, 10) + struct.pack('>BBhhhh', 16, 255, 208, 208, 166, 166)
+    assert _native.pack_wire(_dets(results), 7, 12) == want
+
+
+def test_pack_random_detections_bit_exact():
+    rng = np.random.default_rng(5)
+    rows = [(int(rng.integers(1, 81)), float(rng.random()), float(rng.uniform(-500, 900)), float(rng.uniform(-500, 900)),
+             float(rng.uniform(0, 3000)), float(rng.uniform(0, 3000))) for _ in range(300)]
+    rows += [(1, 0.999999, -0.99, 0.99, 32767.9, -32768.9), (255, 0.0, -32768.0, 32767.0, 0.0, 0.0)]  # truncation toward zero, extremes
+    assert _native.pack_wire(_dets(rows), 0xFFFFFFFF, 123456) == ref_wire.pack_results(rows, 0xFFFFFFFF, 123456)
+    assert _native.pack_wire(_dets([]), 1, 2) == ref_wire.pack_results([], 1, 2)
+
+
+def test_pack_out_of_range_like_struct_pack_or_saturating():
+    bad = [(3, 0.5, 40000.0, 0.0, 10.0, 10.0)]
+    with pytest.raises(struct.error):
+        ref_wire.pack_results(bad, 0, 0)
+    with pytest.raises(struct.error):
+        _native.pack_wire(_dets(bad), 0, 0)
+    sat = _native.pack_wire(_dets(bad + [(300, 0.5, -40000.0, 1.0, 2.0, 3.0)]), 0, 0, saturate=True)
+    assert sat[16:] == struct.pack('>BBhhhh', 3, 127, 32767, 0, 10, 10) + struct.pack('>BBhhhh', 255, 127, -32768, 1, 2, 3)
+
+
+class _FakeDetector:
+    """perform_frames returns, per frame, a result that identifies the frame and the batch it rode in."""
+    image_size = (8, 8)
+
+    def __init__(self):
+        self.batches = []
+
+    def perform_frames(self, frames, threshold=0.1):
+        self.batches.append((len(frames), threshold))
+        if threshold == 0.99:
+            raise RuntimeError("boom")
+        return [[(1, float(threshold), float(f[0, 0, 0]), 0.0, 1.0, 1.0)] for f in frames]
+
+
+def _png(value):
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(np.full((8, 8, 3), value, np.uint8), "RGB").save(buf, format="PNG")
+    return buf.getvalue()
+
+
+def test_batching_service_groups_concurrent_callers():
+    det = _FakeDetector()
+    svc = service.BatchingService(det, max_batch=16, max_delay=0.2)
+    out = {}
+
+    def call(i):
+        out[i] = svc.perform(_png(i), threshold=0.1 if i % 4 else 0.25)
+
+    threads = [threading.Thread(target=call, args=(i,)) for i in range(12)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    for i in range(12):  # every caller gets its own frame's answer with its own threshold
+        assert out[i] == [(1, 0.1 if i % 4 else 0.25, float(i), 0.0, 1.0, 1.0)]
+    assert svc.frames_run == 12 and svc.batches_run < 12  # requests were grouped
+    assert all(thr in (0.1, 0.25) for _, thr in det.batches)
+    # errors: bad size is raised in the caller like the reference's ValueError; a failing batch reaches its callers
+    from PIL import Image
+    buf = io.BytesIO()
+    Image.fromarray(np.zeros((4, 8, 3), np.uint8), "RGB").save(buf, format="PNG")
+    with pytest.raises(ValueError, match="invalid image size"):
+        svc.perform(buf.getvalue())
+    with pytest.raises(RuntimeError, match="boom"):
+        svc.perform(_png(1), threshold=0.99)
+    assert svc.perform(_png(9), threshold=0.1) == [(1, 0.1, 9.0, 0.0, 1.0, 1.0)]  # the worker survived
+    svc.close()
+    with pytest.raises(RuntimeError):
+        svc.perform(_png(1))
