@@ -1,4 +1,4 @@
-// conv_halo.cu — 3x3 convolution (stride 1 or 2, pad 1) for NARROW inputs (Cin = 32) on large feature maps, with the
+// conv_halo.cu — 3x3 convolution (stride 1 or 2, pad 1) for NARROW inputs (Cin = 16 or 32) on large feature maps, with the
 // im2col done by the tensor core's operand addressing over a halo patch that is loaded ONCE per tile.
 //
 // Why a second conv kernel: conv_tc.cu feeds its A operand with im2col TMA loads, one "row" (pixel) per L2 request.
@@ -302,7 +302,7 @@ size_t smem_bytes(int cout) {
 bool conv_halo_supported(const HaloDesc& d) {
     static const bool off = getenv("FASTDET_NO_HALO") != nullptr;
     if (off) return false;
-    if (d.cin != 32 || d.ksize != 3 || d.pad_lo != 1 || d.pad_hi > 1 || !(d.stride == 1 || d.stride == 2)) return false;
+    if (!(d.cin == 32 || d.cin == 16) || d.ksize != 3 || d.pad_lo != 1 || d.pad_hi > 1 || !(d.stride == 1 || d.stride == 2)) return false;
     if (!(d.cout == 32 || d.cout == 64) || d.out_fp32 || d.upsample2x) return false;
     if (d.in_pitch % 8 || d.out_pitch % 8 || (reinterpret_cast<uintptr_t>(d.in) & 15) || (reinterpret_cast<uintptr_t>(d.out) & 15) ||
         (reinterpret_cast<uintptr_t>(d.w) & 15))
@@ -342,14 +342,18 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
     const unsigned box[4] = {32, TW, 4, 1};
     if (encode_tiled_bf16(&L->tm_out, d.out, 4, dims, strides, box, 2)) { if (err && errlen) snprintf(err, errlen, "conv_halo: output tensor map encode failed"); return -1; }
     L->stride = d.stride;
-    L->smem_bytes = d.stride == 1 ? smem_bytes<32, 1>(d.cout) : smem_bytes<32, 2>(d.cout);
+    L->cin = d.cin;
+    L->smem_bytes = d.cin == 32 ? (d.stride == 1 ? smem_bytes<32, 1>(d.cout) : smem_bytes<32, 2>(d.cout))
+                                : (d.stride == 1 ? smem_bytes<16, 1>(d.cout) : smem_bytes<16, 2>(d.cout));
     if (L->smem_bytes > static_cast<size_t>(SMEM_LIMIT)) { if (err && errlen) snprintf(err, errlen, "conv_halo: %zu bytes of shared memory", L->smem_bytes); return -1; }
     L->grid = p.total < num_sms ? p.total : num_sms;
     L->flops = 2.0 * d.n * p.ho * p.wo * d.cout * 9.0 * d.cin;
     static bool attr_done = false;
     if (!attr_done) {
         if (cudaFuncSetAttribute(conv_halo_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_halo_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
+            cudaFuncSetAttribute(conv_halo_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_halo_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_halo_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
             if (err && errlen) snprintf(err, errlen, "conv_halo: cudaFuncSetAttribute failed");
             return -1;
         }
@@ -370,8 +374,9 @@ int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream) {
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
-    const cudaError_t e = L.stride == 1 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 1>, L.tm_out, L.p)
-                                        : cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 2>, L.tm_out, L.p);
+    cudaError_t e;
+    if (L.cin == 32) e = L.stride == 1 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 1>, L.tm_out, L.p) : cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 2>, L.tm_out, L.p);
+    else e = L.stride == 1 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, 1>, L.tm_out, L.p) : cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, 2>, L.tm_out, L.p);
     return e == cudaSuccess ? 0 : -1;
 }
 

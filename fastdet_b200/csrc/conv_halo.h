@@ -39,7 +39,7 @@ struct HaloParams {
 struct HaloLaunch {
     CUtensorMap tm_out;  // {C, W, H, N} of the output slice, box 32 channels x 8 pixels x 4 rows, SWIZZLE_64B
     HaloParams p;
-    int stride, grid;
+    int stride, cin, grid;
     size_t smem_bytes;
     double flops;
 };
