@@ -1,4 +1,4 @@
-// conv_halo.cu — 3x3 convolution (stride 1 or 2, pad 1) for NARROW inputs (Cin = 16 or 32) on large feature maps, with the
+// conv_halo.cu — 3x3 convolution (stride 1 or 2, pad 1) for NARROW inputs (Cin = 16, 32 or 64) on large feature maps, with the
 // im2col done by the tensor core's operand addressing over a halo patch that is loaded ONCE per tile.
 //
 // Why a second conv kernel: conv_tc.cu feeds its A operand with im2col TMA loads, one "row" (pixel) per L2 request.
@@ -50,10 +50,12 @@ struct Geo {
     static constexpr int PLANE_PIX = (STRIDE == 1 ? 1 : 4) * SPH * SPW;
     static constexpr int PLANE_BYTES = ((PLANE_PIX * 16 + 127) / 128) * 128;
     static constexpr int SBO = SPW * 16;
-    // patch ring depth: the copies of SLOTS tiles are in flight at once (the ~3 us DRAM/L2 round trip of a patch is what
-    // has to be covered); stride-2 patches are 39 KB each, more than 4 do not fit
-    static constexpr int SLOTS = STRIDE == 1 ? 8 : 4;
 };
+// patch ring depth: the copies of SLOTS tiles are in flight at once (the ~3 us DRAM/L2 round trip of a patch is what has
+// to be covered).  Bounded by shared memory: 32-channel stride-2 patches are 39 KB each; with 64 input channels the
+// resident filter bank (up to 147 KB) leaves room for two 23 KB patches.
+template <int CIN, int STRIDE>
+struct Ring { static constexpr int SLOTS = CIN == 64 ? 2 : (STRIDE == 1 ? 8 : 4); };
 
 __device__ __forceinline__ int div_magic(int x, unsigned long long m) {
     return static_cast<int>((static_cast<unsigned long long>(x) * m) >> 40);
@@ -79,7 +81,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
     constexpr int NCH = CIN / 8;                    // 16-byte channel chunks per pixel
     constexpr int PATCH_BYTES = NCH * G::PLANE_BYTES;
     constexpr int KSTEPS = CIN / 16;                // MMAs per filter tap
-    constexpr int SLOTS = G::SLOTS;
+    constexpr int SLOTS = Ring<CIN, STRIDE>::SLOTS;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     // [0, 1024) barriers | staging 8 warps x 4 KB | weights 9*NCH*cout*16 | patch ring SLOTS x PATCH_BYTES
@@ -195,6 +197,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
         const float2 a2 = make_float2(alpha_eff, alpha_eff);
         const bool generic_act = p.act == 2;
         const bool has_res = p.residual != nullptr;
+        int sbuf = 0;
         ptx::grid_dep_wait();
         for (int it = group; it < my_tiles; it += 2) {
             const int as = it & 3;
@@ -232,8 +235,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
             ptx::mbar_wait(&acc_full[as], (it >> 2) & 1);
             ptx::tc_fence_after();
             const uint32_t taddr = tmem + as * acc_cols + (static_cast<uint32_t>(quarter * 32) << 16);
-            if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous stores have finished reading the staging rows
-            __syncwarp();
+            const bool rotate = cout > 64;  // wide outputs: two 2 KB staging buffers used in turn, one store per chunk
+            if (!rotate) {
+                if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous stores have finished reading the staging rows
+                __syncwarp();
+            }
             for (int c0 = 0; c0 < cout; c0 += 32) {
                 uint32_t acc[32];
                 ptx::tmem_ld_32x32(taddr + c0, acc);
@@ -268,17 +274,32 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                     for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
                 }
                 // 32 pixels x 64 B with the 64-byte swizzle (chunk c of row r at slot c ^ ((r >> 1) & 3)): a SWIZZLE_64B box
-                uint8_t* so = stage + (c0 >> 5) * 2048;
+                uint8_t* so = stage + ((rotate ? sbuf : (c0 >> 5)) & 1) * 2048;
+                if (rotate) {
+                    if (lane == 0) ptx::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago is done with it
+                    __syncwarp();
+                }
 #pragma unroll
                 for (int c = 0; c < 4; ++c)
                     *reinterpret_cast<uint4*>(so + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                if (rotate) {
+                    ptx::fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {
+                        ptx::tma_store_4d(&tm_out, so, c0, tx * TW, ty * TH + 4 * quarter, f);
+                        ptx::tma_store_commit();
+                    }
+                    ++sbuf;
+                }
             }
-            ptx::fence_proxy_async();
-            __syncwarp();
-            if (lane == 0) {
-                for (int c0 = 0; c0 < cout; c0 += 32)
-                    ptx::tma_store_4d(&tm_out, stage + (c0 >> 5) * 2048, c0, tx * TW, ty * TH + 4 * quarter, f);  // clipped at the edges
-                ptx::tma_store_commit();
+            if (!rotate) {
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    for (int c0 = 0; c0 < cout; c0 += 32)
+                        ptx::tma_store_4d(&tm_out, stage + (c0 >> 5) * 2048, c0, tx * TW, ty * TH + 4 * quarter, f);  // clipped at the edges
+                    ptx::tma_store_commit();
+                }
             }
         }
         if (lane == 0) ptx::tma_store_wait<0>();
@@ -294,7 +315,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
 template <int CIN, int STRIDE>
 size_t smem_bytes(int cout) {
     return 1024 + 1024 + EPI_WARPS * 4096 + ((9 * (CIN / 8) * cout * 16 + 1023) & ~1023) +
-           static_cast<size_t>(Geo<STRIDE>::SLOTS) * (CIN / 8) * Geo<STRIDE>::PLANE_BYTES;
+           static_cast<size_t>(Ring<CIN, STRIDE>::SLOTS) * (CIN / 8) * Geo<STRIDE>::PLANE_BYTES;
 }
 
 }  // namespace
@@ -302,8 +323,9 @@ size_t smem_bytes(int cout) {
 bool conv_halo_supported(const HaloDesc& d) {
     static const bool off = getenv("FASTDET_NO_HALO") != nullptr;
     if (off) return false;
-    if (!(d.cin == 32 || d.cin == 16) || d.ksize != 3 || d.pad_lo != 1 || d.pad_hi > 1 || !(d.stride == 1 || d.stride == 2)) return false;
-    if (!(d.cout == 32 || d.cout == 64) || d.out_fp32 || d.upsample2x) return false;
+    if (!(d.cin == 64 || d.cin == 32 || d.cin == 16) || d.ksize != 3 || d.pad_lo != 1 || d.pad_hi > 1 || !(d.stride == 1 || d.stride == 2)) return false;
+    if (!(d.cout == 32 || d.cout == 64 || d.cout == 128) || d.out_fp32 || d.upsample2x) return false;
+    if (d.cin == 64 && d.stride != 1) return false;  // the 78 KB stride-2 patch does not fit next to the resident filters
     if (d.in_pitch % 8 || d.out_pitch % 8 || (reinterpret_cast<uintptr_t>(d.in) & 15) || (reinterpret_cast<uintptr_t>(d.out) & 15) ||
         (reinterpret_cast<uintptr_t>(d.w) & 15))
         return false;
@@ -343,8 +365,9 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
     if (encode_tiled_bf16(&L->tm_out, d.out, 4, dims, strides, box, 2)) { if (err && errlen) snprintf(err, errlen, "conv_halo: output tensor map encode failed"); return -1; }
     L->stride = d.stride;
     L->cin = d.cin;
-    L->smem_bytes = d.cin == 32 ? (d.stride == 1 ? smem_bytes<32, 1>(d.cout) : smem_bytes<32, 2>(d.cout))
-                                : (d.stride == 1 ? smem_bytes<16, 1>(d.cout) : smem_bytes<16, 2>(d.cout));
+    L->smem_bytes = d.cin == 64 ? smem_bytes<64, 1>(d.cout)
+                    : d.cin == 32 ? (d.stride == 1 ? smem_bytes<32, 1>(d.cout) : smem_bytes<32, 2>(d.cout))
+                                  : (d.stride == 1 ? smem_bytes<16, 1>(d.cout) : smem_bytes<16, 2>(d.cout));
     if (L->smem_bytes > static_cast<size_t>(SMEM_LIMIT)) { if (err && errlen) snprintf(err, errlen, "conv_halo: %zu bytes of shared memory", L->smem_bytes); return -1; }
     L->grid = p.total < num_sms ? p.total : num_sms;
     L->flops = 2.0 * d.n * p.ho * p.wo * d.cout * 9.0 * d.cin;
@@ -352,6 +375,7 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
     if (!attr_done) {
         if (cudaFuncSetAttribute(conv_halo_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
             cudaFuncSetAttribute(conv_halo_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
+            cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
             cudaFuncSetAttribute(conv_halo_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
             cudaFuncSetAttribute(conv_halo_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
             if (err && errlen) snprintf(err, errlen, "conv_halo: cudaFuncSetAttribute failed");
@@ -375,7 +399,8 @@ int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = no_pdl ? 0 : 1;
     cudaError_t e;
-    if (L.cin == 32) e = L.stride == 1 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 1>, L.tm_out, L.p) : cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 2>, L.tm_out, L.p);
+    if (L.cin == 64) e = cudaLaunchKernelEx(&cfg, conv_halo_kernel<64, 1>, L.tm_out, L.p);
+    else if (L.cin == 32) e = L.stride == 1 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 1>, L.tm_out, L.p) : cudaLaunchKernelEx(&cfg, conv_halo_kernel<32, 2>, L.tm_out, L.p);
     else e = L.stride == 1 ? cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, 1>, L.tm_out, L.p) : cudaLaunchKernelEx(&cfg, conv_halo_kernel<16, 2>, L.tm_out, L.p);
     return e == cudaSuccess ? 0 : -1;
 }

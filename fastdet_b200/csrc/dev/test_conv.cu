@@ -302,6 +302,8 @@ int main(int argc, char** argv) {
             {"halo 3x3 32->32 s1 pitch",1, 64, 64, 32, 32, 3, 1, 1, 1, 0, 0, 0, 0, 32, 2048},
             {"halo 3x3 32->64 s2 (1,0)",1, 128, 128, 32, 64, 3, 2, 1, 0, 1, 0, 0, 0, 0, 2048},
             {"halo 3x3 16->32 s1",      2, 70, 66, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 2048},
+            {"halo 3x3 64->128 s1 res", 2, 72, 68, 64, 128, 3, 1, 1, 1, 1, 1, 0, 0, 0, 2048},
+            {"halo 3x3 64->64 s1",      1, 64, 64, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 64, 2048},
             {"halo 3x3 16->64 s2 res",  1, 130, 128, 16, 64, 3, 2, 1, 1, 1, 1, 0, 0, 16, 2048},
             {"1x1 48->64 (bk16)",       1, 20, 20, 48, 64, 1, 1, 0, 0, 1, 0, 0, 0, 16, 0},
         };
