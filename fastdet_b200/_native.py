@@ -15,7 +15,8 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("FASTDET_LIB") or os.path.join(_HERE, "libfastdet_b200.so")  # FASTDET_LIB: developer A/B runs
 
-FD_OK, FD_ERR_ARG, FD_ERR_MODEL, FD_ERR_HEADS, FD_ERR_CUDA, FD_ERR_SIZE = 0, -1, -2, -3, -4, -5
+FD_OK, FD_ERR_ARG, FD_ERR_MODEL, FD_ERR_HEADS, FD_ERR_CUDA, FD_ERR_SIZE, FD_ERR_JPEG = 0, -1, -2, -3, -4, -5, -6
+FD_JPEG_OK, FD_JPEG_NOT_JPEG, FD_JPEG_CORRUPT, FD_JPEG_UNSUPPORTED, FD_JPEG_SIZE = 0, 1, 2, 3, 4
 FD_MAX_HEADS = 4
 FD_MAX_SLOTS = 2
 
@@ -47,6 +48,13 @@ class FdLayerDesc(C.Structure):
                 ("name", C.c_char * 96), ("out_name", C.c_char * 96)]
 
 
+class FdJpegInfo(C.Structure):
+    _fields_ = [("status", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32),
+                ("h_samp", C.c_int32), ("v_samp", C.c_int32), ("restart_interval", C.c_int32),
+                ("blocks_w", C.c_int32 * 3), ("blocks_h", C.c_int32 * 3), ("coef_count", C.c_int64),
+                ("quant", C.c_uint16 * (3 * 64)), ("reason", C.c_char * 160)]
+
+
 # every symbol include/fastdet_b200.h declares, with its ctypes signature
 _PROTOS = {
     "fd_last_error": (C.c_char_p, []),
@@ -64,6 +72,11 @@ _PROTOS = {
                             C.c_void_p, C.c_void_p]),
     "fd_submit": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int]),
     "fd_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_jpeg_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(FdJpegInfo)]),
+    "fd_jpeg_coefficients": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(FdJpegInfo)]),
+    "fd_decode_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    "fd_detect_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_submit_jpeg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
     "fd_pack_wire": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fd_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_set_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -97,6 +110,15 @@ class NativeError(RuntimeError):
         super().__init__(f"fastdet_b200 native error {code}: {msg}")
         self.code = code
         self.msg = msg
+
+
+class JpegRefused(NativeError):
+    """FD_ERR_JPEG: a frame is not a JPEG the device decoder takes; nothing was launched.  ``status`` holds one
+    FD_JPEG_* per frame.  The caller decodes those bytes the way the reference does (PIL) instead."""
+
+    def __init__(self, msg: str, status):
+        super().__init__(FD_ERR_JPEG, msg)
+        self.status = status
 
 
 def _check(rc: int):
@@ -198,6 +220,46 @@ class Model:
             self._slot_shape = {}
         self._slot_shape[slot] = (n, max_det, frames)
 
+    # -- JPEG in (reference server/detector.py:128-133): Huffman decode on host threads, the rest on the device
+    @staticmethod
+    def _jpeg_args(datas):
+        n = len(datas)
+        keep = [d if isinstance(d, bytes) else bytes(d) for d in datas]
+        ptrs = (C.c_char_p * n)(*keep)
+        lens = (C.c_size_t * n)(*[len(d) for d in keep])
+        return n, keep, ptrs, lens, np.zeros(n, np.int32)
+
+    @staticmethod
+    def _check_jpeg(rc, status):
+        if rc == FD_ERR_JPEG:
+            raise JpegRefused((lib().fd_last_error() or b"").decode("utf-8", "replace"), status)
+        _check(rc)
+
+    def decode_jpeg(self, datas, want_rgb=True):
+        """Decodes a list of JPEG byte strings into the input tensor of batch size len(datas); returns the decoded
+        frames [n, net_h, net_w, 3] u8 if want_rgb (parity hook), and leaves them on the device for forward(n)."""
+        n, keep, ptrs, lens, status = self._jpeg_args(datas)
+        rgb = np.empty((n, self.net_h, self.net_w, 3), np.uint8) if want_rgb else None
+        rc = lib().fd_decode_jpeg(self._h, ptrs, lens, n, _ptr(status), _ptr(rgb) if want_rgb else None)
+        self._check_jpeg(rc, status)
+        return rgb
+
+    def detect_jpeg(self, datas, threshold: float, max_det: int = 2048):
+        n, keep, ptrs, lens, status = self._jpeg_args(datas)
+        dets = np.zeros((n, max_det), DET_DTYPE)
+        counts = np.zeros(n, np.int32)
+        rc = lib().fd_detect_jpeg(self._h, ptrs, lens, n, float(threshold), max_det, _ptr(dets), _ptr(counts), _ptr(status))
+        self._check_jpeg(rc, status)
+        return dets, counts
+
+    def submit_jpeg(self, slot: int, datas, threshold: float, max_det: int = 2048):
+        n, keep, ptrs, lens, status = self._jpeg_args(datas)
+        rc = lib().fd_submit_jpeg(self._h, slot, ptrs, lens, n, float(threshold), max_det, _ptr(status))
+        self._check_jpeg(rc, status)
+        if not hasattr(self, "_slot_shape"):
+            self._slot_shape = {}
+        self._slot_shape[slot] = (n, max_det, None)  # the coefficients are already in the slot's pinned buffer
+
     def collect(self, slot: int):
         n, max_det, _keepalive = self._slot_shape.pop(slot)
         dets = np.zeros((n, max_det), DET_DTYPE)
@@ -262,6 +324,32 @@ def pack_wire(dets: np.ndarray, reqid: int = 0, msec: int = 0, saturate: bool = 
         raise struct.error((lib().fd_last_error() or b"").decode("utf-8", "replace"))
     _check(rc)
     return buf[:n.value].tobytes()
+
+
+def jpeg_probe(data: bytes) -> FdJpegInfo:
+    """Header parse of one JPEG (host only)."""
+    info = FdJpegInfo()
+    _check(lib().fd_jpeg_probe(C.c_char_p(data), len(data), C.byref(info)))
+    return info
+
+
+def jpeg_coefficients(data: bytes):
+    """Entropy-decodes one JPEG on the host: returns (info, [coefficients of component c as int16 [bh, bw, 8, 8]]).
+    Raises JpegRefused for streams the device decoder does not take."""
+    info = jpeg_probe(data)
+    if info.status != FD_JPEG_OK:
+        raise JpegRefused(info.reason.decode("utf-8", "replace"), np.array([info.status], np.int32))
+    coefs = np.empty(info.coef_count, np.int16)
+    rc = lib().fd_jpeg_coefficients(C.c_char_p(data), len(data), _ptr(coefs), coefs.size, C.byref(info))
+    if rc == FD_ERR_JPEG:
+        raise JpegRefused((lib().fd_last_error() or b"").decode("utf-8", "replace"), np.array([info.status], np.int32))
+    _check(rc)
+    planes, o = [], 0
+    for c in range(3):
+        k = info.blocks_w[c] * info.blocks_h[c] * 64
+        planes.append(coefs[o:o + k].reshape(info.blocks_h[c], info.blocks_w[c], 8, 8))
+        o += k
+    return info, planes
 
 
 def device_count() -> int:

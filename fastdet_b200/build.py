@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfastdet_b200.so")
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_halo.cu", "pre.cu", "pool.cu", "post.cu", "plan.cc", "onnx_reader.cc"]
-HEADERS = ["conv_tc.h", "conv_halo.h", "kernels.h", "plan.h", "onnx_reader.h", "ptx.cuh", os.path.join("..", "..", "include", "fastdet_b200.h")]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_halo.cu", "jpeg.cu", "pre.cu", "pool.cu", "post.cu", "plan.cc", "onnx_reader.cc"]
+HEADERS = ["conv_tc.h", "conv_halo.h", "kernels.h", "jpeg.h", "plan.h", "onnx_reader.h", "ptx.cuh", os.path.join("..", "..", "include", "fastdet_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 

@@ -9,6 +9,7 @@
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <map>
 #include <memory>
 #include <string>
@@ -17,6 +18,7 @@
 #include "../../include/fastdet_b200.h"
 #include "conv_halo.h"
 #include "conv_tc.h"
+#include "jpeg.h"
 #include "kernels.h"
 #include "onnx_reader.h"
 #include "plan.h"
@@ -80,6 +82,8 @@ struct Slot {  // one in-flight fd_submit: staged input + pinned results + the e
     size_t h_dets_cap = 0;
     int* h_count = nullptr;       // pinned [2n]
     size_t h_count_cap = 0;
+    char* h_stage = nullptr;      // pinned: JPEG frame descriptors + quantised coefficients of one batch
+    size_t h_stage_cap = 0;
     cudaEvent_t staged = nullptr, stage_free = nullptr, done = nullptr;
     int n = 0, max_det = 0;
     bool busy = false;
@@ -89,7 +93,11 @@ struct fd_model {
     int device = 0;
     int num_sms = 148;
     cudaStream_t copy_stream = nullptr;
-    Slot slots[FD_MAX_SLOTS];
+    Slot slots[FD_MAX_SLOTS + 1];  // the last one serves the synchronous JPEG calls
+    std::unique_ptr<JpegPool> jpeg_pool;
+    std::vector<JpegInfo> jpeg_info;
+    uint8_t* jpeg_planes = nullptr;  // decoded component planes of the batch being converted (compute stream only)
+    size_t jpeg_planes_cap = 0;
     ModelPlan plan;
     __nv_bfloat16* d_w = nullptr;
     float* d_bias = nullptr;
@@ -327,10 +335,12 @@ void fd_model_destroy(fd_model* m) {
     cudaFree(m->d_w); cudaFree(m->d_bias); cudaFree(m->d_conv0);
     for (Slot& S : m->slots) {
         cudaFree(S.stage);
+        if (S.h_stage) cudaFreeHost(S.h_stage);
         if (S.h_dets) cudaFreeHost(S.h_dets);
         if (S.h_count) cudaFreeHost(S.h_count);
         if (S.staged) { cudaEventDestroy(S.staged); cudaEventDestroy(S.stage_free); cudaEventDestroy(S.done); }
     }
+    cudaFree(m->jpeg_planes);
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -493,25 +503,18 @@ int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, i
     return fd_fetch(m, n, out, counts, nullptr, nullptr);
 }
 
-// ------------------------------------------------------------------ pipelined serving: fd_submit / fd_collect
-// Two (FD_MAX_SLOTS) batches can be in flight: the host->device copy of a slot runs on the model's copy stream while
-// the compute stream works on the other slot, so a caller that alternates slots keeps the conv stack busy
-// back to back (the synchronous fd_detect pays the PCIe copy in front of every batch).
-int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
-              double threshold, int max_det) {
-    if (!m || !frames) return fail(FD_ERR_ARG, "fd_submit: null argument");
-    if (slot < 0 || slot >= FD_MAX_SLOTS) return fail(FD_ERR_ARG, "fd_submit: slot %d out of range [0, %d)", slot, FD_MAX_SLOTS);
-    const ModelPlan& P = m->plan;
+namespace {
+
+// common front of fd_submit / fd_submit_jpeg: argument checks, the Exec of this batch size, the slot's events and
+// pinned result buffers
+int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s_out) {
     const fd_info& I = m->info;
-    const bool same = src_w == P.net_w && src_h == P.net_h;
-    if (!same && !allow_resize) return fail(FD_ERR_SIZE, "invalid image size");  // reference detector.py:132
-    if (src_w < 1 || src_h < 1) return fail(FD_ERR_SIZE, "invalid image size");
     if (I.n_heads != 2 && I.n_heads != 3) return fail(FD_ERR_HEADS, "%d", I.n_heads);
     if (max_det < 1) return fail(FD_ERR_ARG, "max_det must be >= 1");
     NEED_DEVICE(m);
     CU(cudaSetDevice(m->device));
     Slot& S = m->slots[slot];
-    if (S.busy) return fail(FD_ERR_ARG, "fd_submit: slot %d still holds uncollected results", slot);
+    if (S.busy) return fail(FD_ERR_ARG, "slot %d still holds uncollected results", slot);
     Exec* e;
     if (int rc = get_exec(m, n, &e)) return rc;
     if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
@@ -519,13 +522,6 @@ int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, in
         CU(cudaEventCreateWithFlags(&S.staged, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&S.stage_free, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
-    }
-    const size_t bytes = size_t(n) * src_w * src_h * 3;
-    if (S.stage_cap < bytes) {
-        CU(cudaDeviceSynchronize());
-        cudaFree(S.stage); S.stage = nullptr; S.stage_cap = 0;
-        CU(cudaMalloc(&S.stage, bytes));
-        S.stage_cap = bytes;
     }
     const size_t det_bytes = sizeof(Detection) * size_t(n) * max_det, cnt_bytes = sizeof(int) * 2 * size_t(n);
     if (S.h_dets_cap < det_bytes) {
@@ -547,6 +543,201 @@ int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, in
         CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
         e->max_det = max_det;
     }
+    *e_out = e;
+    *s_out = &S;
+    return FD_OK;
+}
+
+int slot_stage_reserve(Slot& S, size_t bytes) {
+    if (S.stage_cap >= bytes) return FD_OK;
+    CU(cudaDeviceSynchronize());
+    cudaFree(S.stage); S.stage = nullptr; S.stage_cap = 0;
+    CU(cudaMalloc(&S.stage, bytes));
+    S.stage_cap = bytes;
+    return FD_OK;
+}
+
+// common tail: the conv stack, decode + Soft-NMS, results into the slot's pinned buffers, the `done` event
+int slot_finish(fd_model* m, Exec* e, Slot& S, int n, double threshold, int max_det) {
+    cudaStream_t s = m->stream;
+    if (int rc = fd_forward(m, n, nullptr)) return rc;
+    if (int rc = postprocess_on(m, e, n, threshold, max_det, s, S.h_dets, S.h_count)) return rc;
+    CU(cudaEventRecord(S.done, s));
+    S.n = n; S.max_det = max_det; S.busy = true;
+    return FD_OK;
+}
+
+int slot_collect(fd_model* m, Slot& S, fd_det* out, int32_t* counts, int32_t* total) {
+    CU(cudaSetDevice(m->device));
+    S.busy = false;
+    CU(cudaEventSynchronize(S.done));
+    for (int f = 0; f < S.n; ++f) {
+        counts[f] = S.h_count[f];
+        if (total) total[f] = S.h_count[S.n + f];
+        memcpy(out + size_t(f) * S.max_det, S.h_dets + size_t(f) * S.max_det, sizeof(fd_det) * size_t(S.h_count[f]));
+    }
+    return FD_OK;
+}
+
+// ------------------------------------------------------------------ JPEG front end (jpeg.h)
+// Host half of a JPEG batch: parse + entropy-decode every frame (one frame per pool thread) into the slot's pinned
+// buffer, laid out as [JpegFrameDev x n][coefficients of frame 0][frame 1]...  Fills status[] (FD_JPEG_*).
+int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size_t* lens, int n, int32_t* status,
+                    size_t* bytes_out, int* max_blocks_out) {
+    const ModelPlan& P = m->plan;
+    if (!m->jpeg_pool) {
+        int t = static_cast<int>(std::thread::hardware_concurrency());
+        if (const char* env = getenv("FASTDET_JPEG_THREADS")) t = atoi(env);
+        m->jpeg_pool.reset(new JpegPool(std::max(1, std::min(t, 64))));
+    }
+    const bool prof = getenv("FASTDET_JPEG_PROF") != nullptr;
+    const auto t_start = std::chrono::steady_clock::now();
+    std::vector<JpegInfo>& info = m->jpeg_info;
+    if (info.size() < size_t(n)) info.resize(n);
+    std::vector<int32_t> local(n, 0);
+    int32_t* st = status ? status : local.data();
+    std::vector<std::string> why(n);
+    m->jpeg_pool->run(n, [&](int i) {
+        char buf[160] = "";
+        st[i] = jpeg_parse(data[i], lens[i], &info[i], buf, sizeof(buf));
+        if (st[i] == JPEG_OK && (info[i].width != P.net_w || info[i].height != P.net_h)) {
+            st[i] = FD_JPEG_SIZE;
+            snprintf(buf, sizeof(buf), "%dx%d", info[i].width, info[i].height);
+        }
+        why[i] = buf;
+    });
+    bool only_size = true;
+    int bad = -1;
+    for (int i = n - 1; i >= 0; --i)
+        if (st[i] != JPEG_OK) { bad = i; only_size = only_size && st[i] == FD_JPEG_SIZE; }
+    if (bad >= 0) {
+        if (only_size) return fail(FD_ERR_SIZE, "invalid image size");  // reference detector.py:132
+        return fail(FD_ERR_JPEG, "frame %d: %s (status %d)", bad, why[bad].c_str(), st[bad]);
+    }
+    const size_t head = (sizeof(JpegFrameDev) * size_t(n) + 255) / 256 * 256;
+    std::vector<size_t> off(n + 1);
+    off[0] = head;
+    int max_blocks = 0;
+    for (int i = 0; i < n; ++i) {
+        const size_t count = jpeg_coef_count(info[i]);
+        off[i + 1] = off[i] + count * sizeof(int16_t);
+        max_blocks = std::max(max_blocks, static_cast<int>(count / 64));
+    }
+    if (off[n] > 0xffffffffull * 2) return fail(FD_ERR_ARG, "JPEG batch too large");
+    if (S.h_stage_cap < off[n]) {
+        if (S.h_stage) {
+            CU(cudaStreamSynchronize(m->copy_stream));
+            cudaFreeHost(S.h_stage);
+        }
+        S.h_stage = nullptr; S.h_stage_cap = 0;
+        CU(cudaMallocHost(&S.h_stage, off[n] + off[n] / 4));
+        S.h_stage_cap = off[n] + off[n] / 4;
+    }
+    char* base = S.h_stage;
+    const auto t_parsed = std::chrono::steady_clock::now();
+    m->jpeg_pool->run(n, [&](int i) {
+        char buf[160] = "";
+        st[i] = jpeg_decode_coefficients(data[i], lens[i], info[i], reinterpret_cast<int16_t*>(base + off[i]), buf, sizeof(buf));
+        why[i] = buf;
+    });
+    for (int i = 0; i < n; ++i)
+        if (st[i] != JPEG_OK) return fail(FD_ERR_JPEG, "frame %d: %s (status %d)", i, why[i].c_str(), st[i]);
+    JpegFrameDev* fr = reinterpret_cast<JpegFrameDev*>(base);
+    for (int i = 0; i < n; ++i) {
+        const JpegInfo& J = info[i];
+        JpegFrameDev& F = fr[i];
+        memset(&F, 0, sizeof(F));
+        memcpy(F.q, J.q, sizeof(F.q));
+        size_t co = (off[i] - head) / sizeof(int16_t), po = 0;
+        for (int c = 0; c < 3; ++c) {
+            F.coef_off[c] = static_cast<uint32_t>(co);
+            F.plane_off[c] = static_cast<uint32_t>(po);
+            F.bw[c] = static_cast<uint16_t>(J.bw[c]);
+            F.bh[c] = static_cast<uint16_t>(J.bh[c]);
+            co += size_t(J.bw[c]) * J.bh[c] * 64;
+            po += size_t(J.bw[c]) * J.bh[c] * 64;
+        }
+        F.hs = static_cast<uint16_t>(J.hs);
+        F.vs = static_cast<uint16_t>(J.vs);
+    }
+    *bytes_out = off[n];
+    *max_blocks_out = max_blocks;
+    if (prof) {
+        const auto t_end = std::chrono::steady_clock::now();
+        fprintf(stderr, "[fastdet jpeg] %d frames, %d threads: parse %.3f ms, entropy decode %.3f ms, %.1f MB of coefficients\n", n,
+                m->jpeg_pool->size(), std::chrono::duration<double, std::milli>(t_parsed - t_start).count(),
+                std::chrono::duration<double, std::milli>(t_end - t_parsed).count(), off[n] / 1e6);
+    }
+    return FD_OK;
+}
+
+// Device half: pinned -> device staging on the copy stream, then IDCT and colour conversion on the compute stream,
+// ending with RGB u8 frames in the Exec's input tensor (where fd_preprocess would have put them).
+int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int max_blocks) {
+    const ModelPlan& P = m->plan;
+    if (int rc = slot_stage_reserve(S, bytes)) return rc;
+    const size_t plane_stride = size_t(3) * ((P.net_w + 15) / 16 * 16) * ((P.net_h + 15) / 16 * 16);
+    if (m->jpeg_planes_cap < plane_stride * n) {
+        CU(cudaDeviceSynchronize());
+        cudaFree(m->jpeg_planes); m->jpeg_planes = nullptr; m->jpeg_planes_cap = 0;
+        CU(cudaMalloc(&m->jpeg_planes, plane_stride * n));
+        m->jpeg_planes_cap = plane_stride * n;
+    }
+    cudaStream_t cs = m->copy_stream, s = m->stream;
+    const bool prof = getenv("FASTDET_JPEG_PROF") != nullptr;  // developer switch: serialises and times the three steps
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    if (prof) {
+        CU(cudaDeviceSynchronize());
+        for (cudaEvent_t& e2 : ev) CU(cudaEventCreate(&e2));
+        CU(cudaEventRecord(ev[0], cs));
+    }
+    CU(cudaStreamWaitEvent(cs, S.stage_free, 0));
+    CU(cudaMemcpyAsync(S.stage, S.h_stage, bytes, cudaMemcpyHostToDevice, cs));
+    CU(cudaEventRecord(S.staged, cs));
+    CU(cudaStreamWaitEvent(s, S.staged, 0));
+    if (prof) CU(cudaEventRecord(ev[1], s));
+    const size_t head = (sizeof(JpegFrameDev) * size_t(n) + 255) / 256 * 256;
+    const JpegFrameDev* fr = reinterpret_cast<const JpegFrameDev*>(S.stage);
+    const int16_t* coefs = reinterpret_cast<const int16_t*>(S.stage + head);
+    if (launch_jpeg_idct(coefs, fr, m->jpeg_planes, plane_stride, n, max_blocks, s))
+        return fail(FD_ERR_CUDA, "JPEG kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (prof) CU(cudaEventRecord(ev[2], s));
+    if (launch_jpeg_rgb(m->jpeg_planes, plane_stride, fr, e->frames, n, P.net_h, P.net_w, s))
+        return fail(FD_ERR_CUDA, "JPEG kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (prof) {
+        CU(cudaEventRecord(ev[3], s));
+        CU(cudaDeviceSynchronize());
+        float t01 = 0, t12 = 0, t23 = 0;
+        cudaEventElapsedTime(&t01, ev[0], ev[1]);
+        cudaEventElapsedTime(&t12, ev[1], ev[2]);
+        cudaEventElapsedTime(&t23, ev[2], ev[3]);
+        fprintf(stderr, "[fastdet jpeg] device: H2D %.3f ms (%.1f MB), idct %.3f ms, upsample+colour %.3f ms\n", t01, bytes / 1e6, t12, t23);
+        for (cudaEvent_t e2 : ev) cudaEventDestroy(e2);
+    }
+    CU(cudaEventRecord(S.stage_free, s));
+    return FD_OK;
+}
+
+}  // namespace
+
+// ------------------------------------------------------------------ pipelined serving: fd_submit / fd_collect
+// Two (FD_MAX_SLOTS) batches can be in flight: the host->device copy of a slot runs on the model's copy stream while
+// the compute stream works on the other slot, so a caller that alternates slots keeps the conv stack busy
+// back to back (the synchronous fd_detect pays the PCIe copy in front of every batch).
+int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
+              double threshold, int max_det) {
+    if (!m || !frames) return fail(FD_ERR_ARG, "fd_submit: null argument");
+    if (slot < 0 || slot >= FD_MAX_SLOTS) return fail(FD_ERR_ARG, "fd_submit: slot %d out of range [0, %d)", slot, FD_MAX_SLOTS);
+    const ModelPlan& P = m->plan;
+    const bool same = src_w == P.net_w && src_h == P.net_h;
+    if (!same && !allow_resize) return fail(FD_ERR_SIZE, "invalid image size");  // reference detector.py:132
+    if (src_w < 1 || src_h < 1) return fail(FD_ERR_SIZE, "invalid image size");
+    Exec* e;
+    Slot* sp;
+    if (int rc = slot_begin(m, slot, n, max_det, &e, &sp)) return rc;
+    Slot& S = *sp;
+    const size_t bytes = size_t(n) * src_w * src_h * 3;
+    if (int rc = slot_stage_reserve(S, bytes)) return rc;
     cudaStream_t cs = m->copy_stream, s = m->stream;
     // copy stream: wait until the compute stream has consumed this slot's previous contents, then stage the frames
     CU(cudaStreamWaitEvent(cs, S.stage_free, 0));
@@ -560,11 +751,7 @@ int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, in
         return fail(FD_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     CU(cudaEventRecord(S.stage_free, s));
-    if (int rc = fd_forward(m, n, nullptr)) return rc;
-    if (int rc = postprocess_on(m, e, n, threshold, max_det, s, S.h_dets, S.h_count)) return rc;
-    CU(cudaEventRecord(S.done, s));
-    S.n = n; S.max_det = max_det; S.busy = true;
-    return FD_OK;
+    return slot_finish(m, e, S, n, threshold, max_det);
 }
 
 int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* total) {
@@ -573,15 +760,91 @@ int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* tot
     NEED_DEVICE(m);
     Slot& S = m->slots[slot];
     if (!S.busy) return fail(FD_ERR_ARG, "fd_collect: nothing was submitted to slot %d", slot);
-    CU(cudaSetDevice(m->device));
-    S.busy = false;
-    CU(cudaEventSynchronize(S.done));
-    for (int f = 0; f < S.n; ++f) {
-        counts[f] = S.h_count[f];
-        if (total) total[f] = S.h_count[S.n + f];
-        memcpy(out + size_t(f) * S.max_det, S.h_dets + size_t(f) * S.max_det, sizeof(fd_det) * size_t(S.h_count[f]));
+    return slot_collect(m, S, out, counts, total);
+}
+
+// ------------------------------------------------------------------ JPEG in: reference detector.py:128-133
+int fd_jpeg_probe(const uint8_t* data, size_t len, fd_jpeg_info* out) {
+    if (!data || !out) return fail(FD_ERR_ARG, "fd_jpeg_probe: null argument");
+    std::unique_ptr<JpegInfo> J(new JpegInfo());
+    char why[160] = "";
+    memset(out, 0, sizeof(*out));
+    out->status = jpeg_parse(data, len, J.get(), why, sizeof(why));
+    snprintf(out->reason, sizeof(out->reason), "%s", why);
+    out->width = J->width; out->height = J->height; out->components = J->ncomp;
+    if (out->status != JPEG_OK) return FD_OK;
+    out->h_samp = J->hs; out->v_samp = J->vs; out->restart_interval = J->restart_interval;
+    for (int c = 0; c < 3; ++c) {
+        out->blocks_w[c] = J->bw[c];
+        out->blocks_h[c] = J->bh[c];
+        memcpy(out->quant[c], J->q[c], sizeof(out->quant[c]));
     }
+    out->coef_count = static_cast<int64_t>(jpeg_coef_count(*J));
     return FD_OK;
+}
+
+int fd_jpeg_coefficients(const uint8_t* data, size_t len, int16_t* coefs, size_t cap, fd_jpeg_info* out) {
+    if (!coefs) return fail(FD_ERR_ARG, "fd_jpeg_coefficients: null argument");
+    if (int rc = fd_jpeg_probe(data, len, out)) return rc;
+    if (out->status != JPEG_OK) return fail(FD_ERR_JPEG, "%s (status %d)", out->reason, out->status);
+    if (cap < size_t(out->coef_count)) return fail(FD_ERR_ARG, "fd_jpeg_coefficients: buffer holds %zu coefficients, %lld needed", cap, static_cast<long long>(out->coef_count));
+    std::unique_ptr<JpegInfo> J(new JpegInfo());
+    char why[160] = "";
+    jpeg_parse(data, len, J.get(), why, sizeof(why));
+    out->status = jpeg_decode_coefficients(data, len, *J, coefs, why, sizeof(why));
+    snprintf(out->reason, sizeof(out->reason), "%s", why);
+    if (out->status != JPEG_OK) return fail(FD_ERR_JPEG, "%s (status %d)", why, out->status);
+    return FD_OK;
+}
+
+int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int32_t* status, uint8_t* rgb_out) {
+    if (!m || !data || !lens) return fail(FD_ERR_ARG, "fd_decode_jpeg: null argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Slot& S = m->slots[FD_MAX_SLOTS];
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    if (!S.staged) {
+        CU(cudaEventCreateWithFlags(&S.staged, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&S.stage_free, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    }
+    size_t bytes = 0;
+    int max_blocks = 0;
+    if (int rc = jpeg_host_stage(m, S, data, lens, n, status, &bytes, &max_blocks)) return rc;
+    if (int rc = jpeg_device_stage(m, e, S, n, bytes, max_blocks)) return rc;
+    if (rgb_out) CU(cudaMemcpyAsync(rgb_out, e->frames, size_t(n) * m->plan.net_w * m->plan.net_h * 3, cudaMemcpyDeviceToHost, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    return FD_OK;
+}
+
+int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, double threshold, int max_det,
+                   int32_t* status) {
+    if (!m || !data || !lens) return fail(FD_ERR_ARG, "fd_submit_jpeg: null argument");
+    if (slot < 0 || slot >= FD_MAX_SLOTS) return fail(FD_ERR_ARG, "fd_submit_jpeg: slot %d out of range [0, %d)", slot, FD_MAX_SLOTS);
+    Exec* e;
+    Slot* sp;
+    if (int rc = slot_begin(m, slot, n, max_det, &e, &sp)) return rc;
+    size_t bytes = 0;
+    int max_blocks = 0;
+    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, status, &bytes, &max_blocks)) return rc;
+    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks)) return rc;
+    return slot_finish(m, e, *sp, n, threshold, max_det);
+}
+
+int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, double threshold, int max_det, fd_det* out,
+                   int32_t* counts, int32_t* status) {
+    if (!m || !data || !lens || !out || !counts) return fail(FD_ERR_ARG, "fd_detect_jpeg: null argument");
+    Exec* e;
+    Slot* sp;
+    if (int rc = slot_begin(m, FD_MAX_SLOTS, n, max_det, &e, &sp)) return rc;
+    size_t bytes = 0;
+    int max_blocks = 0;
+    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, status, &bytes, &max_blocks)) return rc;
+    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks)) return rc;
+    if (int rc = slot_finish(m, e, *sp, n, threshold, max_det)) return rc;
+    return slot_collect(m, *sp, out, counts, nullptr);
 }
 
 // ------------------------------------------------------------------ wire format (reference server/server.py:234-239)

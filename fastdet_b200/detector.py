@@ -70,6 +70,8 @@ class ONNXDetector(Detector):
         self.mode = mode
         self.path = path
         self.max_det = max_det
+        self.jpeg_device_frames = 0  # payloads decoded by the library / by PIL (refused by the library)
+        self.jpeg_host_frames = 0
         if isinstance(path, (bytes, bytearray)):
             data = bytes(path)
             self.path = '<bytes>'
@@ -88,6 +90,13 @@ class ONNXDetector(Detector):
     # -- the reference entry point -------------------------------------------------------------
     def perform(self, data, threshold=0.1):
         super().perform(data)
+        results = self.perform_jpegs([data], threshold=threshold)[0]
+        self.logger.info(f'perform: results={results}')
+        return results
+
+    def _decode_host(self, data):
+        """The reference's own decode lines (server/detector.py:128-133), with their exceptions: used for payloads the
+        device JPEG decoder refuses (PNG, progressive or grey JPEG, damaged streams ...)."""
         from PIL import Image
         (width, height) = self.image_size
         img = Image.open(io.BytesIO(data))
@@ -97,9 +106,30 @@ class ONNXDetector(Detector):
         if frame.ndim != 3 or frame.shape[2] != 3:
             # the reference's reshape(1,height,width,3) raises ValueError for non-RGB modes (:133)
             raise ValueError(f'cannot reshape array of size {frame.size} into shape (1,{height},{width},3)')
-        results = self.perform_frames(frame.reshape(1, height, width, 3), threshold=threshold)[0]
-        self.logger.info(f'perform: results={results}')
-        return results
+        return frame
+
+    def jpeg_probe(self, data):
+        """'device' if the library's JPEG path takes this payload, 'size' if it is such a JPEG of the wrong size
+        (the reference raises ValueError('invalid image size')), else 'host' (decode it the reference's way)."""
+        info = _native.jpeg_probe(bytes(data))
+        if info.status != _native.FD_JPEG_OK:
+            return 'host'
+        return 'device' if (info.width, info.height) == tuple(self.image_size) else 'size'
+
+    def perform_jpegs(self, datas, threshold=0.1):
+        """perform() for a batch of encoded payloads: one result list per payload.  Baseline JPEGs are decoded by the
+        library (Huffman on its host thread pool, IDCT / upsampling / colour on the device: fd_detect_jpeg), bit-identical
+        to PIL; if the library refuses any payload of the batch, the batch is decoded the reference's way instead."""
+        self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
+        datas = list(datas)
+        try:
+            dets, counts = self.model.detect_jpeg(datas, threshold, max_det=self.max_det)
+            self.jpeg_device_frames += len(datas)
+            return self._tuples(dets, counts)
+        except _native.JpegRefused:
+            frames = np.stack([self._decode_host(d) for d in datas])
+            self.jpeg_host_frames += len(datas)
+            return self.perform_frames(frames, threshold=threshold)
 
     # -- extras --------------------------------------------------------------------------------
     def perform_frames(self, frames, threshold=0.1, allow_resize=False):
@@ -107,12 +137,7 @@ class ONNXDetector(Detector):
         self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
         dets, counts = self.model.detect(np.asarray(frames), threshold, allow_resize=allow_resize,
                                          max_det=self.max_det)
-        out = []
-        for f in range(dets.shape[0]):
-            d = dets[f, :counts[f]]
-            out.append([(int(k), float(c), float(x), float(y), float(w), float(h))
-                        for k, c, x, y, w, h in zip(d['klass'], d['conf'], d['x'], d['y'], d['w'], d['h'])])
-        return out
+        return self._tuples(dets, counts)
 
     perform_batch = perform_frames
 
@@ -130,33 +155,43 @@ class ONNXDetector(Detector):
         bytes DetectService.send() would be given (16-byte 'YOLO' header + 10 bytes per detection), built by the
         native library straight from the detection records (no per-detection Python objects)."""
         super().perform(data)
-        from PIL import Image
-        (width, height) = self.image_size
-        img = Image.open(io.BytesIO(data))
-        if img.size != self.image_size:
-            raise ValueError('invalid image size')
-        frame = np.array(img)
-        if frame.ndim != 3 or frame.shape[2] != 3:
-            raise ValueError(f'cannot reshape array of size {frame.size} into shape (1,{height},{width},3)')
         self.ANCHORS[self.model.n_heads]
         t0 = time.time()
-        dets, counts = self.model.detect(frame.reshape(1, height, width, 3), threshold, max_det=self.max_det)
+        try:
+            dets, counts = self.model.detect_jpeg([data], threshold, max_det=self.max_det)
+            self.jpeg_device_frames += 1
+        except _native.JpegRefused:
+            frame = self._decode_host(data)
+            self.jpeg_host_frames += 1
+            (width, height) = self.image_size
+            dets, counts = self.model.detect(frame.reshape(1, height, width, 3), threshold, max_det=self.max_det)
         msec = int((time.time() - t0) * 1000)
         return _native.pack_wire(dets[0, :counts[0]], reqid, msec, saturate)
 
     def perform_stream(self, batches, threshold=0.1, allow_resize=False):
-        """Generator over an iterable of [n, h, w, 3] u8 batches: yields one list of per-frame result lists per
+        """Generator over an iterable of batches, each an [n, h, w, 3] u8 array or a list of JPEG payloads: yields one list of per-frame result lists per
         batch, in order, with two batches in flight (fd_submit / fd_collect) so the host->device copy of batch
         i+1 overlaps the compute of batch i.  Same results as perform_frames on each batch."""
         self.ANCHORS[self.model.n_heads]
         pending = []  # slots in submission order
         slot = 0
         for frames in batches:
-            frames = np.ascontiguousarray(frames, np.uint8)
+            encoded = not isinstance(frames, np.ndarray) and len(frames) and isinstance(frames[0], (bytes, bytearray, memoryview))
+            if not encoded:
+                frames = np.ascontiguousarray(frames, np.uint8)
             if len(pending) == _native.FD_MAX_SLOTS:
                 dets, counts, _ = self.model.collect(pending.pop(0))
                 yield self._tuples(dets, counts)
-            self.model.submit(slot, frames, threshold, allow_resize=allow_resize, max_det=self.max_det)
+            if encoded:  # a list of JPEG payloads: entropy decode here (host pool) while the device runs the other slot
+                try:
+                    self.model.submit_jpeg(slot, frames, threshold, max_det=self.max_det)
+                    self.jpeg_device_frames += len(frames)
+                except _native.JpegRefused:
+                    decoded = np.stack([self._decode_host(d) for d in frames])
+                    self.jpeg_host_frames += len(frames)
+                    self.model.submit(slot, decoded, threshold, max_det=self.max_det)
+            else:
+                self.model.submit(slot, frames, threshold, allow_resize=allow_resize, max_det=self.max_det)
             pending.append(slot)
             slot = (slot + 1) % _native.FD_MAX_SLOTS
         for s in pending:

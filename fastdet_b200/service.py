@@ -19,7 +19,7 @@ class _Request:
     __slots__ = ("frame", "threshold", "event", "result", "error")
 
     def __init__(self, frame, threshold):
-        self.frame = frame
+        self.frame = frame  # decoded RGB array, or the JPEG payload itself (bytes) when the library will decode it
         self.threshold = threshold
         self.event = threading.Event()
         self.result = None
@@ -28,7 +28,9 @@ class _Request:
 
 class BatchingService:
     """detector: an object with ``image_size`` and ``perform_frames(frames_u8[n,h,w,3], threshold) -> [list per frame]``
-    (fastdet_b200.detector.ONNXDetector).  Thread-safe; ``close()`` stops the worker."""
+    (fastdet_b200.detector.ONNXDetector).  If it also has ``jpeg_probe(data)`` and ``perform_jpegs(datas, threshold)``,
+    baseline-JPEG payloads are queued as bytes and decoded by the library (fd_detect_jpeg) as part of the batch.
+    Thread-safe; ``close()`` stops the worker."""
 
     def __init__(self, detector, max_batch=64, max_delay=0.002):
         self.detector = detector
@@ -45,6 +47,13 @@ class BatchingService:
 
     # -- the reference entry point (server/detector.py:126-146), callable from many threads
     def perform(self, data, threshold=0.1):
+        probe = getattr(self.detector, 'jpeg_probe', None)
+        if probe is not None:
+            verdict = probe(data)  # header parse only (microseconds), in the caller's thread
+            if verdict == 'size':
+                raise ValueError('invalid image size')
+            if verdict == 'device':  # the batch worker hands the bytes to the library's JPEG path
+                return self._wait(_Request(bytes(data), float(threshold)))
         from PIL import Image
         (width, height) = self.image_size
         img = Image.open(io.BytesIO(data))  # decode in the caller's thread: it parallelises across sessions
@@ -57,7 +66,9 @@ class BatchingService:
 
     def perform_frame(self, frame, threshold=0.1):
         """One decoded RGB frame [h, w, 3] u8."""
-        req = _Request(np.ascontiguousarray(frame, np.uint8), float(threshold))
+        return self._wait(_Request(np.ascontiguousarray(frame, np.uint8), float(threshold)))
+
+    def _wait(self, req):
         with self._cond:
             if self._closed:
                 raise RuntimeError("BatchingService is closed")
@@ -101,14 +112,19 @@ class BatchingService:
             batch = self._take()
             if batch is None:
                 return
-            try:
-                frames = np.stack([r.frame for r in batch])
-                results = self.detector.perform_frames(frames, threshold=batch[0].threshold)
-                for r, res in zip(batch, results):
-                    r.result = res
-            except Exception as e:  # every caller of the batch sees the failure, the worker lives on
-                for r in batch:
-                    r.error = e
+            for part in ([r for r in batch if isinstance(r.frame, bytes)], [r for r in batch if not isinstance(r.frame, bytes)]):
+                if not part:
+                    continue
+                try:
+                    if isinstance(part[0].frame, bytes):
+                        results = self.detector.perform_jpegs([r.frame for r in part], threshold=part[0].threshold)
+                    else:
+                        results = self.detector.perform_frames(np.stack([r.frame for r in part]), threshold=part[0].threshold)
+                    for r, res in zip(part, results):
+                        r.result = res
+                except Exception as e:  # every caller of the part sees the failure, the worker lives on
+                    for r in part:
+                        r.error = e
             self.batches_run += 1
             self.frames_run += len(batch)
             for r in batch:

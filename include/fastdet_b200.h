@@ -32,10 +32,20 @@ extern "C" {
 #define FD_ERR_HEADS (-3)    /* graph has a number of outputs other than 2 or 3 (reference: KeyError at detector.py:136) */
 #define FD_ERR_CUDA (-4)     /* CUDA runtime / driver failure, or no device */
 #define FD_ERR_SIZE (-5)     /* frame size not accepted (reference: ValueError('invalid image size'), detector.py:132) */
+#define FD_ERR_JPEG (-6)     /* a frame is not a JPEG the device decoder takes (status[] / fd_last_error say which and why);
+                                nothing was launched — give those bytes to the reference's own decoder (PIL) instead */
+
+/* per-frame status of the JPEG entry points */
+#define FD_JPEG_OK 0
+#define FD_JPEG_NOT_JPEG 1    /* no SOI marker: some other image format */
+#define FD_JPEG_CORRUPT 2     /* malformed or truncated stream (also everything libjpeg would only warn about) */
+#define FD_JPEG_UNSUPPORTED 3 /* valid JPEG outside the device path: progressive, arithmetic, 12-bit, grey/CMYK/RGB-coded,
+                                 sampling other than 4:4:4 / 4:2:2 / 4:2:0, non-interleaved scans */
+#define FD_JPEG_SIZE 4        /* decodable, but not the network's size (reference: ValueError('invalid image size')) */
 
 #define FD_MAX_HEADS 4
 #define FD_MAX_SLOTS 2 /* batches in flight through fd_submit / fd_collect */
-#define FD_ABI_VERSION 2
+#define FD_ABI_VERSION 3
 
 typedef struct fd_model fd_model;
 
@@ -112,6 +122,38 @@ int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, i
 int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, int src_h, int on_device,
               int allow_resize, double threshold, int max_det);
 int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* total);
+
+/* ---- JPEG in: the first lines of the reference's perform() (server/detector.py:128-133) are
+ * `img = Image.open(io.BytesIO(data))`, the size check and `np.array(img)`, i.e. a libjpeg decode on one host core per
+ * frame.  These entry points take the JPEG bytes themselves: Huffman decode on a pool of host threads, then
+ * de-quantisation, IDCT (libjpeg's ISLOW), fancy chroma upsampling and YCbCr->RGB on the device, bit-identical to
+ * libjpeg(-turbo)'s default output, written straight into the batch's input tensor.  Baseline / extended-sequential
+ * Huffman, 8-bit, 3-component YCbCr, 4:4:4 / 4:2:2 / 4:2:0, restart intervals.  Anything else is refused with
+ * FD_ERR_JPEG before any device work (no approximation, no silent host decode): status[n] (may be NULL) receives one
+ * FD_JPEG_* per frame.  A batch whose only problem is the frame size returns FD_ERR_SIZE like fd_detect. */
+typedef struct fd_jpeg_info {
+    int32_t status; /* FD_JPEG_* (size is not checked here) */
+    int32_t width, height, components;
+    int32_t h_samp, v_samp; /* luma sampling factors */
+    int32_t restart_interval;
+    int32_t blocks_w[3], blocks_h[3]; /* 8x8 blocks per component plane, padded to whole MCUs */
+    int64_t coef_count;               /* int16 coefficients fd_jpeg_coefficients writes */
+    uint16_t quant[3][64];            /* per component, row-major (de-zigzagged) */
+    char reason[160];
+} fd_jpeg_info;
+/* Host only (no device needed): parse the headers / entropy-decode one frame into quantised coefficients
+ * coefs[component][block row][block col][64], row-major inside a block.  Test and tooling hooks. */
+int fd_jpeg_probe(const uint8_t* data, size_t len, fd_jpeg_info* out);
+int fd_jpeg_coefficients(const uint8_t* data, size_t len, int16_t* coefs, size_t cap, fd_jpeg_info* out);
+/* Decode n JPEGs into the model's input tensor for batch size n (where fd_preprocess puts frames), synchronous; follow
+ * with fd_forward(m, n, NULL).  rgb_out (host, may be NULL) receives the decoded frames [n, net_h, net_w, 3]. */
+int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int32_t* status, uint8_t* rgb_out);
+/* fd_detect / fd_submit taking JPEG bytes.  The entropy decode runs inside the call on the host pool (while the device
+ * works on the other slot); collect with fd_collect. */
+int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, double threshold, int max_det,
+                   fd_det* out, int32_t* counts, int32_t* status);
+int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, double threshold,
+                   int max_det, int32_t* status);
 
 /* Wire-format packer (host only, no device needed): the response payload the reference builds per request in
  * DetectService.process_data (server/server.py:234-239): a 16-byte big-endian header '>4sLLL' = (b"YOLO", reqid, msec,

@@ -1,0 +1,47 @@
+"""Generates tests/golden/jpeg.npz: small baseline JPEG streams written by Pillow / libjpeg-turbo in this image and the
+pixels the reference's decode lines (server/detector.py:128-133: Image.open + np.array) return for them.  The fixture
+travels to the GPU box, so the device decoder is pinned to THESE outputs even if the box's Pillow were different.
+
+    python tests/golden/make_golden_jpeg.py
+"""
+import io
+import os
+import sys
+
+import numpy as np
+from PIL import Image
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+from oracle import ref_jpeg  # noqa: E402
+
+
+def picture(h, w, seed):
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    img = np.stack([127 + 100 * np.sin(xx / 7.0 + seed) * np.cos(yy / 11.0), 127 + 120 * np.sin((xx + yy) / 5.0),
+                    (xx * 3 + yy * 5 + seed * 17) % 256], -1).astype(np.float64)
+    img += rng.normal(0, 25, img.shape)
+    img[h // 4:h // 2, w // 4:w // 2] = rng.integers(0, 255, 3)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def main():
+    out = {}
+    cases = [(64, 80, 0, 75, 0), (64, 80, 1, 75, 0), (64, 80, 2, 75, 0), (37, 29, 2, 90, 0), (37, 29, 1, 30, 2),
+             (48, 48, 2, 100, 3), (17, 131, 0, 50, 1), (96, 96, 2, 5, 0)]
+    for i, (h, w, sub, q, rst) in enumerate(cases):
+        buf = io.BytesIO()
+        kw = dict(restart_marker_blocks=rst) if rst else {}
+        Image.fromarray(picture(h, w, i)).save(buf, 'JPEG', quality=q, subsampling=sub, **kw)
+        data = buf.getvalue()
+        out[f'jpeg{i}'] = np.frombuffer(data, np.uint8)
+        out[f'rgb{i}'] = ref_jpeg.decode_reference(data)
+        out[f'meta{i}'] = np.array([h, w, sub, q, rst])
+    out['count'] = np.array(len(cases))
+    np.savez_compressed(os.path.join(HERE, 'jpeg.npz'), **out)
+    print('wrote', os.path.join(HERE, 'jpeg.npz'), sum(v.nbytes for v in out.values()), 'bytes raw')
+
+
+if __name__ == '__main__':
+    main()
