@@ -191,6 +191,52 @@ def run_reference(args):
 
 
 # ---------------------------------------------------------------------------------------------- GPU arm
+def jpeg_arm(model, frames, n, steps):
+    """The same batches entering as JPEG payloads, the way the reference's perform(data) receives them
+    (server/detector.py:128-133): fd_submit_jpeg / fd_collect, Huffman decode on the library's host threads inside the
+    timed region, IDCT + upsampling + colour conversion on the device.  Reported next to the reference's own decode
+    step (PIL, one frame per call, one core)."""
+    import io
+
+    from PIL import Image
+    datas = []
+    for f in frames[:8]:
+        buf = io.BytesIO()
+        Image.fromarray(np.ascontiguousarray(f)).save(buf, "JPEG", quality=75)  # PIL default 4:2:0
+        datas.append(buf.getvalue())
+    batch = [datas[i % len(datas)] for i in range(n)]
+    t0 = time.perf_counter()
+    decoded = [np.array(Image.open(io.BytesIO(d))) for d in batch[:16]]
+    pil_ms = (time.perf_counter() - t0) / 16 * 1e3
+    exact = bool(np.array_equal(model.decode_jpeg(batch[:8]), np.stack(decoded[:8])))
+
+    def run(k):
+        model.submit_jpeg(0, batch, THRESHOLD, max_det=MAX_DET)
+        for i in range(1, k):
+            model.submit_jpeg(i % 2, batch, THRESHOLD, max_det=MAX_DET)
+            model.collect((i - 1) % 2)
+        model.collect((k - 1) % 2)
+
+    run(3)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    run(steps)
+    torch.cuda.synchronize()
+    secs = time.perf_counter() - t0
+    lat = []
+    for i in range(120):
+        t0 = time.perf_counter()
+        model.detect_jpeg(batch[:1], THRESHOLD, max_det=MAX_DET)
+        if i >= 20:
+            lat.append((time.perf_counter() - t0) * 1e3)
+    return {"value": round(n * steps / secs, 1), "unit": "frames/s",
+            "api": "fd_submit_jpeg / fd_collect: JPEG bytes in (quality 75, 4:2:0), Huffman decode on the host pool inside the timed region, "
+                   "IDCT + fancy upsampling + YCbCr->RGB on the device, records out",
+            "jpeg_kb_per_frame": round(sum(len(d) for d in batch) / n / 1024, 1), "host_threads": os.cpu_count(),
+            "pixels_bit_exact_vs_pillow": exact, "reference_decode_ms_per_frame_one_core": round(pil_ms, 3),
+            "bs1_latency_ms_p50": round(float(np.percentile(lat, 50)), 4)}
+
+
 def run_b200(args):
     import torch
     from fastdet_b200 import _native, modelgen
@@ -384,6 +430,7 @@ def run_b200(args):
                 lat.append((time.perf_counter() - t0) * 1e3)
         line["bs1_latency_ms"] = {"p50": round(float(np.percentile(lat, 50)), 4), "p90": round(float(np.percentile(lat, 90)), 4),
                                   "what": "fd_detect, 1 pinned host frame in, records out (H2D + D2H included), 200 calls"}
+        line["e2e"]["from_jpeg"] = jpeg_arm(model, sets[0], n, args.steps)
     if rank == 0:
         print(json.dumps(line))
     if use_dist:
