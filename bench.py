@@ -198,6 +198,7 @@ def jpeg_arm(model, frames, n, steps):
     step (PIL, one frame per call, one core)."""
     import io
 
+    import torch
     from PIL import Image
     datas = []
     for f in frames[:8]:
