@@ -77,6 +77,8 @@ _PROTOS = {
     "fd_decode_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     "fd_detect_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_submit_jpeg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "fd_letterbox_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int32)] * 4),
+    "fd_unmap_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fd_pack_wire": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
     "fd_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_set_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
@@ -324,6 +326,20 @@ def pack_wire(dets: np.ndarray, reqid: int = 0, msec: int = 0, saturate: bool = 
         raise struct.error((lib().fd_last_error() or b"").decode("utf-8", "replace"))
     _check(rc)
     return buf[:n.value].tobytes()
+
+
+def letterbox_geometry(src_wh, net_wh):
+    """(new_w, new_h, off_x, off_y) of the allow_resize letterbox."""
+    v = [C.c_int32() for _ in range(4)]
+    _check(lib().fd_letterbox_geometry(src_wh[0], src_wh[1], net_wh[0], net_wh[1], *[C.byref(x) for x in v]))
+    return tuple(x.value for x in v)
+
+
+def unmap_letterbox(dets: np.ndarray, src_wh, net_wh) -> np.ndarray:
+    """Detections of a letterboxed frame (DET_DTYPE array cut to its count) -> pixels of the source frame."""
+    out = np.ascontiguousarray(dets, DET_DTYPE).copy()
+    _check(lib().fd_unmap_letterbox(_ptr(out), len(out), src_wh[0], src_wh[1], net_wh[0], net_wh[1]))
+    return out
 
 
 def jpeg_probe(data: bytes) -> FdJpegInfo:

@@ -847,6 +847,38 @@ int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, 
     return slot_collect(m, *sp, out, counts, nullptr);
 }
 
+// ------------------------------------------------------------------ letterbox geometry (extension)
+int fd_letterbox_geometry(int src_w, int src_h, int net_w, int net_h, int32_t* new_w, int32_t* new_h, int32_t* off_x, int32_t* off_y) {
+    if (src_w < 1 || src_h < 1 || net_w < 1 || net_h < 1 || !new_w || !new_h || !off_x || !off_y)
+        return fail(FD_ERR_ARG, "fd_letterbox_geometry: bad argument");
+    int nw, nh;  // the same integers launch_letterbox_u8 derives (pre.cu)
+    if (1LL * src_w * net_h >= 1LL * src_h * net_w) {
+        nw = net_w;
+        nh = static_cast<int>((1LL * src_h * net_w + src_w / 2) / src_w);
+        if (nh < 1) nh = 1;
+    } else {
+        nh = net_h;
+        nw = static_cast<int>((1LL * src_w * net_h + src_h / 2) / src_h);
+        if (nw < 1) nw = 1;
+    }
+    *new_w = nw; *new_h = nh; *off_x = (net_w - nw) / 2; *off_y = (net_h - nh) / 2;
+    return FD_OK;
+}
+
+int fd_unmap_letterbox(fd_det* dets, int count, int src_w, int src_h, int net_w, int net_h) {
+    if ((!dets && count > 0) || count < 0) return fail(FD_ERR_ARG, "fd_unmap_letterbox: bad argument");
+    int32_t nw, nh, ox, oy;
+    if (int rc = fd_letterbox_geometry(src_w, src_h, net_w, net_h, &nw, &nh, &ox, &oy)) return rc;
+    const double sx = static_cast<double>(src_w) / nw, sy = static_cast<double>(src_h) / nh;
+    for (int i = 0; i < count; ++i) {
+        dets[i].x = (dets[i].x - ox) * sx;
+        dets[i].y = (dets[i].y - oy) * sy;
+        dets[i].w *= sx;
+        dets[i].h *= sy;
+    }
+    return FD_OK;
+}
+
 // ------------------------------------------------------------------ wire format (reference server/server.py:234-239)
 int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, int saturate, uint8_t* out, size_t cap, size_t* len) {
     if ((!dets && count > 0) || !out || !len || count < 0) return fail(FD_ERR_ARG, "fd_pack_wire: bad argument");

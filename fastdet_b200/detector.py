@@ -132,11 +132,17 @@ class ONNXDetector(Detector):
             return self.perform_frames(frames, threshold=threshold)
 
     # -- extras --------------------------------------------------------------------------------
-    def perform_frames(self, frames, threshold=0.1, allow_resize=False):
-        """frames: [n, h, w, 3] u8 decoded RGB.  Returns one reference-style result list per frame."""
+    def perform_frames(self, frames, threshold=0.1, allow_resize=False, source_coords=False):
+        """frames: [n, h, w, 3] u8 decoded RGB.  Returns one reference-style result list per frame.  allow_resize
+        (extension): frames of another size are letterboxed on the device; boxes then come back in network pixels, or in
+        pixels of the frames that were passed in with source_coords=True."""
         self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
-        dets, counts = self.model.detect(np.asarray(frames), threshold, allow_resize=allow_resize,
-                                         max_det=self.max_det)
+        frames = np.asarray(frames)
+        dets, counts = self.model.detect(frames, threshold, allow_resize=allow_resize, max_det=self.max_det)
+        if source_coords and allow_resize and frames.shape[1:3] != (self.image_size[1], self.image_size[0]):
+            src = (frames.shape[2], frames.shape[1])
+            for f in range(dets.shape[0]):
+                dets[f, :counts[f]] = _native.unmap_letterbox(dets[f, :counts[f]], src, self.image_size)
         return self._tuples(dets, counts)
 
     perform_batch = perform_frames

@@ -155,6 +155,15 @@ int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, 
 int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, double threshold,
                    int max_det, int32_t* status);
 
+/* Letterbox bookkeeping (host only; extension — the reference rejects frames that are not network-sized).  With
+ * allow_resize the frame is scaled to new_w x new_h (aspect kept, the long side filling the network) and centred at
+ * (off_x, off_y) on a grey canvas; detections come back in network pixels.  fd_unmap_letterbox rewrites `count` records
+ * in place to pixels of the src_w x src_h frame the caller sent: x = (x - off_x) * src_w / new_w, w = w * src_w / new_w,
+ * same for y / h (float64). */
+int fd_letterbox_geometry(int src_w, int src_h, int net_w, int net_h, int32_t* new_w, int32_t* new_h, int32_t* off_x,
+                          int32_t* off_y);
+int fd_unmap_letterbox(fd_det* dets, int count, int src_w, int src_h, int net_w, int net_h);
+
 /* Wire-format packer (host only, no device needed): the response payload the reference builds per request in
  * DetectService.process_data (server/server.py:234-239): a 16-byte big-endian header '>4sLLL' = (b"YOLO", reqid, msec,
  * payload length) followed by one 10-byte record '>BBhhhh' = (klass, int(conf*255), int(x), int(y), int(w), int(h)) per

@@ -480,3 +480,24 @@ def test_wire_format_and_batching_service_on_device():
         common = set(gs) & set(ws)
         assert len(common) >= max(len(gs), len(ws)) - 2
         assert all(abs(gs[k] - ws[k]) <= 1e-2 for k in common)
+
+
+def test_letterboxed_frames_report_source_pixels():
+    """allow_resize + source_coords: a pixel-doubled 832x832 frame letterboxes back to the original
+    416x416 pixels exactly (bilinear taps fall between two equal pixels), so the detections are the original's with
+    every coordinate doubled; a 832x416 canvas holding the frame twice maps through the vertical offset."""
+    data, m = get_model("tiny", 80, 416, 1)
+    det = fdet.ONNXDetector(data, num_classes=80, image_size=(416, 416), max_det=256)
+    frame = frames_for(1, 416, 700)[0]
+    want = det.perform_frames(frame[None], threshold=0.05)[0]
+    assert want
+    doubled = np.repeat(np.repeat(frame, 2, axis=0), 2, axis=1)
+    assert np.array_equal(det.model.letterbox(doubled[None])[0], frame)
+    net = det.perform_frames(doubled[None], threshold=0.05, allow_resize=True)[0]
+    assert net == want
+    src = det.perform_frames(doubled[None], threshold=0.05, allow_resize=True, source_coords=True)[0]
+    assert [(k, c) for k, c, *_ in src] == [(k, c) for k, c, *_ in want]
+    for (_, _, x, y, w, h), (_, _, x0, y0, w0, h0) in zip(src, want):
+        assert (x, y, w, h) == (2 * x0, 2 * y0, 2 * w0, 2 * h0)
+    with pytest.raises(ValueError, match='invalid image size'):
+        det.perform_frames(doubled[None], threshold=0.05)
