@@ -149,8 +149,27 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
 #pragma unroll
             for (int g = 0; g < 16; ++g) x[g] = bias_act2<true>(acc[2 * g], acc[2 * g + 1], bias[2 * g], bias[2 * g + 1], alpha2);
         }
+        if (mode == 1 && p.head_tma) {
+            // head tensors: the lane's 32 fp32 columns (128 B) go into a 32-row staging tile (128-byte swizzle) and leave
+            // through a TMA store.  Direct stores made every warp instruction touch 32 half-used sectors: the 52x52 head
+            // spent 4x its MMA time storing.
+            if (lane == 0) ptx::tma_store_wait_read<0>();  // the previous chunk's store has finished reading the tile
+            __syncwarp();
+#pragma unroll
+            for (int c = 0; c < 8; ++c)
+                *reinterpret_cast<float4*>(stage + lane * 128 + ((c ^ (lane & 7)) << 4)) =
+                    make_float4(x[2 * c].x, x[2 * c].y, x[2 * c + 1].x, x[2 * c + 1].y);
+            ptx::fence_proxy_async();
+            __syncwarp();
+            if (lane == 0) {
+                ptx::tma_store_2d(tm_out, stage, n0 + c0, static_cast<int>(m_base));  // rows >= M, columns >= pitch are clipped
+                ptx::tma_store_commit();
+            }
+            lap(3);
+            return;
+        }
         if (mode == 1) {
-            // head tensors (3 small layers): fp32 rows straight from the registers
+            // fallback: fp32 rows straight from the registers
             if (own_ok) {
                 float* op = reinterpret_cast<float*>(p.out) + m_own * p.out_pitch + n0 + c0;
 #pragma unroll
@@ -526,7 +545,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         ptx::tma_prefetch_desc(&tmA);
         ptx::tma_prefetch_desc(&tmB);
     }
-    if (warp == 4 && lane == 0 && p.epi_mode == 0) ptx::tma_prefetch_desc(&tmOut);  // (a valid map in every mode)
+    if (warp == 4 && lane == 0 && (p.epi_mode == 0 || p.head_tma)) ptx::tma_prefetch_desc(&tmOut);  // (a valid map in every mode)
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
@@ -995,6 +1014,17 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
                           CU_TENSOR_MAP_INTERLEAVE_NONE, p.store64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map OUT encode failed (CUresult %lld)", r); return -1; }
+    } else if (p.epi_mode == 1 && !swap && !getenv("FASTDET_NO_HEAD_TMA")) {
+        // fp32 head rows [M][out_pitch]: 32 columns x 32 rows per store (128-byte rows, SWIZZLE_128B)
+        cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.out_pitch), static_cast<cuuint64_t>(M)};
+        cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_pitch) * 4};
+        cuuint32_t box[2] = {32, 32};
+        cuuint32_t estr[2] = {1, 1};
+        r = g_encodeTiled(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, d.out, dims, strides, box, estr,
+                          CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+                          CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: fp32 tensor map OUT encode failed (CUresult %lld)", r); return -1; }
+        p.head_tma = 1;
     } else {
         L->tmOut = L->tmB;  // unused by these modes; any valid map
     }

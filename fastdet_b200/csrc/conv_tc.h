@@ -71,6 +71,7 @@ struct ConvParams {
     float* ws;
     int* counters;
     int swap_tma;  // swapped mode: plain bf16 outputs without residual leave through TMA stores (32 ch x 32 pixels, SWIZZLE_64B)
+    int head_tma;  // fp32 head rows leave through TMA stores (32 columns x 32 rows, SWIZZLE_128B)
     int store64;   // 1: the output map's box is 64 channels x 32 rows (SWIZZLE_128B), two chunks per TMA store
     int res_v8;    // 1: residual rows are 32-byte aligned -> 256-bit loads
     int epi_mode;  // 0 bf16 slice through a TMA store (+ residual), 1 fp32 head rows, 2 bf16 with x2 upsampling
