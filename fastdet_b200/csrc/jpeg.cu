@@ -42,7 +42,9 @@ bool derive(HuffTable& h, bool is_ac) {
     if (total > 256) return false;
     memset(h.lut, 0, sizeof(h.lut));
     unsigned code = 0;
-    int p = 0;
+    int p = 0, longest = 0;
+    for (int l = 1; l <= 16; ++l)
+        if (h.bits[l]) longest = l;
     for (int l = 1; l <= 16; ++l) {
         h.valoffset[l] = p - static_cast<int>(code);
         for (int i = 0; i < h.bits[l]; ++i, ++p, ++code) {
@@ -52,6 +54,9 @@ bool derive(HuffTable& h, bool is_ac) {
                 for (unsigned k = 0; k < count; ++k) h.lut[first + k] = static_cast<uint16_t>((l << 8) | h.vals[p]);
             }
         }
+        // libjpeg (jpeg_make_d_derived_tbl) also rejects a length whose codes use up the whole code space, all-ones
+        // code included: "Bogus Huffman table definition", which PIL reports as a broken data stream
+        if (l <= longest && code >= (1u << l)) return false;
         h.maxcode[l] = h.bits[l] ? static_cast<int>(code) - 1 : -1;
         code <<= 1;
     }
@@ -154,7 +159,10 @@ int jpeg_parse(const uint8_t* d, size_t len, JpegInfo* info, char* why, size_t c
             if (n != 2) return say(JPEG_CORRUPT, why, cap, "DRI length");
             J.restart_interval = be16(s);
         } else if (m == 0xE0) {
-            if (n >= 5 && !memcmp(s, "JFIF\0", 5)) jfif = true;
+            if (n >= 5 && !memcmp(s, "JFIF\0", 5)) {
+                if (n < 14) return say(JPEG_UNSUPPORTED, why, cap, "short JFIF segment");  // PIL reads version, units and density
+                jfif = true;
+            }
         } else if (m == 0xEE) {
             if (n >= 12 && !memcmp(s, "Adobe", 5)) { adobe = true; adobe_transform = s[11]; }
         } else if (m == 0xDA) {  // SOS
@@ -169,6 +177,13 @@ int jpeg_parse(const uint8_t* d, size_t len, JpegInfo* info, char* why, size_t c
                 J.ac_tbl[c] = s[2 + 2 * c] & 15;
                 if (J.dc_tbl[c] > 3 || J.ac_tbl[c] > 3) return say(JPEG_CORRUPT, why, cap, "SOS table id");
                 if (!J.dc[J.dc_tbl[c]].present || !J.ac[J.ac_tbl[c]].present) return say(JPEG_CORRUPT, why, cap, "scan uses an undefined Huffman table");
+                {   // libjpeg validates the DC symbols of the tables a scan uses when the scan starts
+                    const HuffTable& D = J.dc[J.dc_tbl[c]];
+                    int total = 0;
+                    for (int l = 1; l <= 16; ++l) total += D.bits[l];
+                    for (int i = 0; i < total; ++i)
+                        if (D.vals[i] > 15) return say(JPEG_CORRUPT, why, cap, "DC Huffman table holds a category above 15");
+                }
                 if (!have_qt[comp_tq[c]]) return say(JPEG_CORRUPT, why, cap, "component uses an undefined quantisation table");
                 memcpy(J.q[c], qt[comp_tq[c]], sizeof(J.q[c]));
             }
@@ -194,7 +209,10 @@ int jpeg_parse(const uint8_t* d, size_t len, JpegInfo* info, char* why, size_t c
             J.scan_off = pos;
             return JPEG_OK;
         }
-        // every other marker (APPn, COM, ...) is skipped
+        else if (!((m >= 0xE0 && m <= 0xEF) || m == 0xFE)) {
+            // only APPn and COM are skipped: PIL's marker loop and libjpeg both give up on the reserved / extension ones
+            return say(JPEG_UNSUPPORTED, why, cap, "marker 0x%02x", m);
+        }
     }
 }
 
@@ -461,7 +479,13 @@ constexpr int CONST_BITS = 13, PASS1_BITS = 2;
 constexpr int F_0_298 = 2446, F_0_390 = 3196, F_0_541 = 4433, F_0_765 = 6270, F_0_899 = 7373, F_1_175 = 9633,
               F_1_501 = 12299, F_1_847 = 15137, F_1_961 = 16069, F_2_053 = 16819, F_2_562 = 20995, F_3_072 = 25172;
 
-// one 8-point pass of jpeg_idct_islow; the caller applies the pass-specific descale
+// One 8-point pass of jpeg_idct_islow; the caller applies the pass-specific descale.  Inputs are 16-bit values.  For
+// the streams a sane encoder writes this is jidctint.c to the letter; outside that range it follows the SIMD versions
+// libjpeg-turbo actually runs (jidctint-sse2/avx2: 16-bit paddw/psubw for in0 +- in4 and for z3, z4; 32-bit lanes that
+// wrap; saturating packs after each pass), because that is what PIL returns for a damaged-but-decodable stream.
+__device__ __forceinline__ int wrap16(int v) { return static_cast<int>(static_cast<short>(v)); }
+__device__ __forceinline__ int sat16(int v) { return min(max(v, -32768), 32767); }
+
 __device__ __forceinline__ void idct8(const int (&in)[8], int (&out)[8]) {
     int z2 = in[2], z3 = in[6];
     int z1 = (z2 + z3) * F_0_541;
@@ -469,14 +493,14 @@ __device__ __forceinline__ void idct8(const int (&in)[8], int (&out)[8]) {
     const int e3 = z1 + z2 * F_0_765;
     z2 = in[0];
     z3 = in[4];
-    const int e0 = (z2 + z3) << CONST_BITS;
-    const int e1 = (z2 - z3) << CONST_BITS;
+    const int e0 = wrap16(z2 + z3) << CONST_BITS;
+    const int e1 = wrap16(z2 - z3) << CONST_BITS;
     const int t10 = e0 + e3, t13 = e0 - e3, t11 = e1 + e2, t12 = e1 - e2;
     int o0 = in[7], o1 = in[5], o2 = in[3], o3 = in[1];
     z1 = o0 + o3;
     z2 = o1 + o2;
-    z3 = o0 + o2;
-    int z4 = o1 + o3;
+    z3 = wrap16(o0 + o2);
+    int z4 = wrap16(o1 + o3);
     const int z5 = (z3 + z4) * F_1_175;
     o0 *= F_0_298;
     o1 *= F_2_053;
@@ -498,12 +522,9 @@ __device__ __forceinline__ void idct8(const int (&in)[8], int (&out)[8]) {
     out[3] = t13 + o0; out[4] = t13 - o0;
 }
 
-// libjpeg's IDCT range-limit table, indexed with (x & 0x3ff): clamp(x + 128) for every value a valid stream
-// produces, and the same wrap-around as the table for the ones it does not
-__device__ __forceinline__ unsigned range_limit_idct(int x) {
-    const int i = x & 0x3ff;
-    return i < 128 ? i + 128 : i < 512 ? 255 : i < 896 ? 0 : i - 896;
-}
+// final range limit: clamp(x + 128) — the C code's table look-up for every value a valid stream produces, and the
+// saturating packs of the SIMD code (not the table's wrap-around) beyond
+__device__ __forceinline__ unsigned range_limit_idct(int x) { return static_cast<unsigned>(min(max(x, -128), 127) + 128); }
 
 constexpr int IDCT_BLOCKS = 32, WS_PITCH = 72;
 
@@ -519,17 +540,25 @@ jpeg_idct_kernel(const int16_t* __restrict__ coefs, const JpegFrameDev* __restri
     const int c = !live ? 0 : (b >= n0) + (b >= n0 + n1);
     const int bc = !live ? 0 : b - (c > 0 ? n0 : 0) - (c > 1 ? n1 : 0);
     int v[8], o[8];
+    bool row_nonzero = false;
+    const int lane_in_warp = threadIdx.x & 31;
     if (live) {  // row t of the block: 8 coefficients x 8 quantiser steps (DEQUANTIZE in jidctint.c)
         const int4 raw = __ldg(reinterpret_cast<const int4*>(coefs + F.coef_off[c] + size_t(bc) * 64 + t * 8));
+        row_nonzero = (raw.x | raw.y | raw.z | raw.w) != 0;
         const int4 qv = __ldg(reinterpret_cast<const int4*>(F.q[c] + t * 8));
         const int r[4] = {raw.x, raw.y, raw.z, raw.w};
         const int q[4] = {qv.x, qv.y, qv.z, qv.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            ws[lb][t * 8 + 2 * j] = static_cast<int>(static_cast<short>(r[j] & 0xffff)) * (q[j] & 0xffff);
-            ws[lb][t * 8 + 2 * j + 1] = (r[j] >> 16) * static_cast<int>(static_cast<unsigned>(q[j]) >> 16);
+            // (pmullw: the product is kept to 16 bits)
+            ws[lb][t * 8 + 2 * j] = wrap16(static_cast<int>(static_cast<short>(r[j] & 0xffff)) * (q[j] & 0xffff));
+            ws[lb][t * 8 + 2 * j + 1] = wrap16((r[j] >> 16) * static_cast<int>(static_cast<unsigned>(q[j]) >> 16));
         }
     }
+    // the SIMD code's shortcut for a block whose rows 1..7 are all zero: every column is its DC term shifted left in a
+    // 16-bit lane (psllw wraps where the full column pass would saturate)
+    const unsigned ac_rows = __ballot_sync(0xffffffffu, live && t > 0 && row_nonzero);
+    const bool dc_only = ((ac_rows >> (8 * (lane_in_warp >> 3))) & 0xffu) == 0u;
     __syncwarp();
     if (live) {  // pass 1: column t
 #pragma unroll
@@ -539,7 +568,9 @@ jpeg_idct_kernel(const int16_t* __restrict__ coefs, const JpegFrameDev* __restri
     __syncwarp();
     if (live) {
 #pragma unroll
-        for (int r = 0; r < 8; ++r) ws[lb][r * 8 + t] = (o[r] + (1 << (CONST_BITS - PASS1_BITS - 1))) >> (CONST_BITS - PASS1_BITS);
+        for (int r = 0; r < 8; ++r)
+            ws[lb][r * 8 + t] = dc_only ? wrap16(v[0] << PASS1_BITS)
+                                        : sat16((o[r] + (1 << (CONST_BITS - PASS1_BITS - 1))) >> (CONST_BITS - PASS1_BITS));
     }
     __syncwarp();
     if (live) {  // pass 2: row t

@@ -189,19 +189,29 @@ FIX = dict(f0_298=2446, f0_390=3196, f0_541=4433, f0_765=6270, f0_899=7373, f1_1
            f1_961=16069, f2_053=16819, f2_562=20995, f3_072=25172)
 
 
+def _wrap16(v):
+    return ((v + 32768) & 0xFFFF) - 32768
+
+
+def _wrap32(v):
+    return ((v + (1 << 31)) & 0xFFFFFFFF) - (1 << 31)
+
+
 def _idct_1d(x):
-    """One 8-point pass of jpeg_idct_islow (jidctint.c) along the last axis, before the descale."""
+    """One 8-point pass of jpeg_idct_islow (jidctint.c) along the last axis, before the descale.  The _wrap16 calls are
+    no-ops for the streams a sane encoder writes; for damaged ones they reproduce the 16-bit paddw/psubw of the SIMD
+    versions (jidctint-sse2/avx2.asm) that libjpeg-turbo — hence Pillow — actually executes."""
     F = FIX
     z2, z3 = x[..., 2], x[..., 6]
     z1 = (z2 + z3) * F['f0_541']
     tmp2 = z1 + z3 * (-F['f1_847'])
     tmp3 = z1 + z2 * F['f0_765']
     z2, z3 = x[..., 0], x[..., 4]
-    tmp0 = (z2 + z3) << CONST_BITS
-    tmp1 = (z2 - z3) << CONST_BITS
+    tmp0 = _wrap16(z2 + z3) << CONST_BITS
+    tmp1 = _wrap16(z2 - z3) << CONST_BITS
     tmp10, tmp13, tmp11, tmp12 = tmp0 + tmp3, tmp0 - tmp3, tmp1 + tmp2, tmp1 - tmp2
     tmp0, tmp1, tmp2, tmp3 = x[..., 7], x[..., 5], x[..., 3], x[..., 1]
-    z1, z2, z3, z4 = tmp0 + tmp3, tmp1 + tmp2, tmp0 + tmp2, tmp1 + tmp3
+    z1, z2, z3, z4 = tmp0 + tmp3, tmp1 + tmp2, _wrap16(tmp0 + tmp2), _wrap16(tmp1 + tmp3)
     z5 = (z3 + z4) * F['f1_175']
     tmp0, tmp1, tmp2, tmp3 = tmp0 * F['f0_298'], tmp1 * F['f2_053'], tmp2 * F['f3_072'], tmp3 * F['f1_501']
     z1, z2, z3, z4 = z1 * -F['f0_899'], z2 * -F['f2_562'], z3 * -F['f1_961'], z4 * -F['f0_390']
@@ -212,20 +222,24 @@ def _idct_1d(x):
 
 
 def _descale(x, n):
-    return (x + (1 << (n - 1))) >> n
+    return _wrap32(x + (1 << (n - 1))) >> n  # 32-bit lanes
 
 
 def idct_islow(coef, quant):
     """coef int16 [..., 8, 8] (row-major), quant [8, 8] -> samples u8 [..., 8, 8]."""
-    x = coef.astype(np.int64) * quant.astype(np.int64)
-    # pass 1: columns (transform along axis -2)
-    ws = _descale(_idct_1d(np.swapaxes(x, -1, -2)), CONST_BITS - PASS1_BITS)
+    x = _wrap16(coef.astype(np.int64) * quant.astype(np.int64))  # pmullw
+    # pass 1: columns (transform along axis -2); packssdw saturates the workspace to 16 bits
+    ws = np.clip(_descale(_idct_1d(np.swapaxes(x, -1, -2)), CONST_BITS - PASS1_BITS), -32768, 32767)
     ws = np.swapaxes(ws, -1, -2)
-    # pass 2: rows
+    # the SIMD code's shortcut when rows 1..7 of the (quantised) block are all zero: each column is its DC term shifted
+    # left by PASS1_BITS in a 16-bit lane (psllw: wraps where the full pass would have saturated)
+    dc_only = ~np.any(coef[..., 1:, :] != 0, axis=(-1, -2))
+    short = np.broadcast_to(_wrap16(x[..., :1, :] << PASS1_BITS), x.shape)
+    ws = np.where(dc_only[..., None, None], short, ws)
+    # pass 2: rows; range limit = clamp(x + 128): the table of the C code for every value a valid stream produces, the
+    # saturating packs of the SIMD code beyond (the C table would wrap around there)
     out = _descale(_idct_1d(ws), CONST_BITS + PASS1_BITS + 3)
-    idx = out & 0x3FF  # range_limit table (jdmaster.c prepare_range_limit_table), centred on 128
-    res = np.where(idx < 128, idx + 128, np.where(idx < 512, 255, np.where(idx < 896, 0, idx - 896)))
-    return res.astype(np.uint8)
+    return (np.clip(out, -128, 127) + 128).astype(np.uint8)
 
 
 def planes_from_coefficients(hdr, coefs):

@@ -149,6 +149,42 @@ def test_random_damage_never_crashes():
             pass
 
 
+def damaged_streams(seed, trials, mods=4):
+    """Random byte / bit damage on valid streams; yields the ones the library still accepts."""
+    rng = np.random.default_rng(seed)
+    for trial in range(trials):
+        sub, rst = int(rng.integers(0, 3)), int(rng.integers(0, 3))
+        kw = dict(restart_marker_blocks=rst) if rst else {}
+        d = bytearray(encode(picture(40, 56, trial % 7), quality=int(rng.integers(20, 98)), subsampling=sub, **kw))
+        for _ in range(int(rng.integers(1, mods))):
+            pos = int(rng.integers(2, len(d)))
+            if rng.random() < 0.5:
+                d[pos] ^= 1 << int(rng.integers(0, 8))
+            else:
+                d[pos] = int(rng.integers(0, 256))
+        d = bytes(d)
+        try:
+            info, planes = _native.jpeg_coefficients(d)
+        except (_native.JpegRefused, MemoryError):  # (MemoryError: damaged dimensions, the test hook's numpy buffer)
+            continue
+        yield d, planes
+
+
+def test_accepted_damaged_streams_decode_like_pillow():
+    """Whatever the library does not refuse must come out exactly as Pillow decodes it — including the places where
+    libjpeg-turbo's SIMD IDCT overflows differently from the C code (16-bit lanes, saturating packs, the DC-only
+    shortcut) and a DC predictor that has run away.  Before those were restated, 5 % of the accepted streams differed."""
+    import warnings
+    accepted = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for d, planes in damaged_streams(21, 700):
+            accepted += 1
+            want = ref_jpeg.decode_reference(d)  # must not raise: what Pillow cannot open, the library must refuse
+            assert np.array_equal(ref_jpeg.reconstruct(ref_jpeg.parse(d), planes), want)
+    assert accepted > 150
+
+
 class _FakeDetector:
     """perform_jpegs / perform_frames stand-ins that record how each payload arrived."""
     image_size = (64, 64)
@@ -234,6 +270,41 @@ def test_device_decode_bit_exact_against_pillow():
         for sub in (0, 2):
             d = encode(a, quality=90, subsampling=sub)
             assert np.array_equal(m.decode_jpeg([d])[0], ref_jpeg.decode_reference(d))
+
+
+@pytest.mark.gpu
+def test_device_decode_of_damaged_streams_equals_pillow():
+    """The device IDCT / upsampling / colour kernels on out-of-range coefficients (net size 64x64 model would be needed
+    for tiny frames, so the damaged 40x56 streams are checked through full-size ones: damage applied to 416x416 streams)."""
+    import warnings
+    _, m = gpu_model()
+    rng = np.random.default_rng(33)
+    base = [encode(modelgen.synthetic_frame(500 + i, 416), quality=q, subsampling=s_) for i, (q, s_) in enumerate([(60, 2), (85, 0), (40, 1)])]
+    batch, want, checked = [], [], 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for trial in range(400):
+            d = bytearray(base[trial % 3])
+            start = d.index(b'\xff\xda')
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(start + 14, len(d) - 2)) if rng.random() < 0.8 else int(rng.integers(2, start))
+                d[pos] ^= 1 << int(rng.integers(0, 8))
+            d = bytes(d)
+            if _native.jpeg_probe(d).status != _native.FD_JPEG_OK:
+                continue
+            try:
+                _native.jpeg_coefficients(d)
+            except _native.JpegRefused:
+                continue
+            batch.append(d)
+            want.append(ref_jpeg.decode_reference(d))
+            if len(batch) == 16:
+                got = m.decode_jpeg(batch)
+                for i in range(16):
+                    assert np.array_equal(got[i], want[i]), (trial, i)
+                batch, want = [], []
+                checked += 16
+    assert checked >= 128  # single bit flips mostly re-synchronise: about three quarters of the streams stay decodable
 
 
 @pytest.mark.gpu
