@@ -129,8 +129,22 @@ void* loc_ptr(const Exec& e, const TensorLoc& t, bool fp32) {
     return base + size_t(t.ch_off) * (fp32 ? 4 : 2);
 }
 
-int get_exec(fd_model* m, int n, Exec** out) {
-    if (n <= 0) return fail(FD_ERR_ARG, "batch size must be positive (got %d)", n);
+// Execution state is built per batch-size BUCKET, not per batch size: a serving front end submits whatever arrived
+// (17 frames, then 43, ...), and a buffer set + captured graph for every distinct size would cost seconds of set-up
+// and tens of GB.  n <= 64 rounds up to a power of two, larger batches to a multiple of 64; the conv stack runs on the
+// bucket's frame count (frames past n hold stale pixels and are never decoded or copied out), everything else on n.
+int bucket_of(int n) {
+    static const bool exact = getenv("FASTDET_EXACT_BATCH") != nullptr;  // developer switch: one Exec per exact size
+    if (exact) return n;
+    if (n > 64) return (n + 63) / 64 * 64;
+    int b = 1;
+    while (b < n) b *= 2;
+    return b;
+}
+
+int get_exec(fd_model* m, int n_frames, Exec** out) {
+    if (n_frames <= 0) return fail(FD_ERR_ARG, "batch size must be positive (got %d)", n_frames);
+    const int n = bucket_of(n_frames);
     auto it = m->execs.find(n);
     if (it != m->execs.end()) { *out = it->second.get(); return FD_OK; }
     std::unique_ptr<Exec> e(new Exec());
@@ -148,7 +162,8 @@ int get_exec(fd_model* m, int n, Exec** out) {
         cudaMalloc(&e->cand_count, sizeof(int) * n) != cudaSuccess ||
         cudaMalloc(&e->scores, sizeof(double) * size_t(n) * bpf) != cudaSuccess ||
         cudaMalloc(&e->det_count, sizeof(int) * 2 * n) != cudaSuccess ||
-        cudaMallocHost(&e->h_count, sizeof(int) * 2 * n) != cudaSuccess) {
+        cudaMallocHost(&e->h_count, sizeof(int) * 2 * n) != cudaSuccess ||
+        cudaMemset(e->frames, 0, frame_bytes) != cudaSuccess) {
         free_exec(e.get());
         return fail(FD_ERR_CUDA, "cudaMalloc(per-batch state, batch %d) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
     }
@@ -467,8 +482,8 @@ int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stre
         CU(cudaStreamSynchronize(s));
         cudaFree(e->dets); e->dets = nullptr;
         if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
-        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
-        CU(cudaMallocHost(&e->h_dets, sizeof(Detection) * size_t(n) * max_det));
+        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(e->n) * max_det));
+        CU(cudaMallocHost(&e->h_dets, sizeof(Detection) * size_t(e->n) * max_det));
         e->max_det = max_det;
     }
     // results to pinned host memory on the same stream; fd_fetch synchronises
@@ -480,8 +495,9 @@ int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stre
 
 int fd_fetch(fd_model* m, int n, fd_det* out, int32_t* counts, int32_t* total, void* stream) {
     if (!m || !out || !counts) return fail(FD_ERR_ARG, "fd_fetch: null argument");
-    auto it = m->execs.find(n);
-    if (it == m->execs.end() || !it->second->h_dets) return fail(FD_ERR_ARG, "fd_fetch: no postprocess results for batch %d", n);
+    auto it = m->execs.find(bucket_of(n));
+    if (n < 1 || it == m->execs.end() || !it->second->h_dets)
+        return fail(FD_ERR_ARG, "fd_fetch: no postprocess results for batch %d", n);
     Exec* e = it->second.get();
     NEED_DEVICE(m);
     CU(cudaSetDevice(m->device));
@@ -540,7 +556,7 @@ int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s
         CU(cudaStreamSynchronize(m->stream));
         cudaFree(e->dets); e->dets = nullptr;
         if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
-        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(n) * max_det));
+        CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(e->n) * max_det));
         e->max_det = max_det;
     }
     *e_out = e;

@@ -147,14 +147,34 @@ class ONNXDetector(Detector):
 
     perform_batch = perform_frames
 
-    @staticmethod
-    def _tuples(dets, counts):
-        out = []
-        for f in range(dets.shape[0]):
-            d = dets[f, :counts[f]]
-            out.append([(int(k), float(c), float(x), float(y), float(w), float(h))
-                        for k, c, x, y, w, h in zip(d['klass'], d['conf'], d['x'], d['y'], d['w'], d['h'])])
-        return out
+    _RESULT_FIELDS = ['klass', 'conf', 'x', 'y', 'w', 'h']
+
+    @classmethod
+    def _tuples(cls, dets, counts):
+        """fd_det records -> the reference's result lists: [(klass, conf, x, y, w, h), ...] per frame (:142-144)."""
+        return [dets[f, :counts[f]][cls._RESULT_FIELDS].tolist() for f in range(dets.shape[0])]
+
+    # -- two batches in flight (fd_submit / fd_submit_jpeg + fd_collect): what BatchingService drives
+    def submit_jpegs(self, slot, datas, threshold=0.1):
+        """Starts a batch of encoded payloads in ring slot `slot` and returns; collect(slot) yields the result lists.
+        The entropy decode happens in this call (library's host threads) while the device works on the other slot."""
+        self.ANCHORS[self.model.n_heads]
+        datas = list(datas)
+        try:
+            self.model.submit_jpeg(slot, datas, threshold, max_det=self.max_det)
+            self.jpeg_device_frames += len(datas)
+        except _native.JpegRefused:
+            frames = np.stack([self._decode_host(d) for d in datas])
+            self.jpeg_host_frames += len(datas)
+            self.model.submit(slot, frames, threshold, max_det=self.max_det)
+
+    def submit_frames(self, slot, frames, threshold=0.1):
+        self.ANCHORS[self.model.n_heads]
+        self.model.submit(slot, np.ascontiguousarray(frames, np.uint8), threshold, max_det=self.max_det)
+
+    def collect(self, slot):
+        dets, counts, _ = self.model.collect(slot)
+        return self._tuples(dets, counts)
 
     def perform_wire(self, data, threshold=0.1, reqid=0, saturate=False):
         """perform() + the reference server's response packing (server/server.py:231-239) in one call: returns the

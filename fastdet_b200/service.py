@@ -86,8 +86,10 @@ class BatchingService:
         self._worker.join()
 
     # -- worker: one batch per distinct threshold among the waiting requests
-    def _take(self):
+    def _take(self, block=True):
         with self._cond:
+            if not block and not self._queue:
+                return None
             while not self._queue and not self._closed:
                 self._cond.wait()
             if not self._queue:
@@ -107,25 +109,60 @@ class BatchingService:
             self._queue = rest
             return batch
 
+    @staticmethod
+    def _finish(part, results=None, error=None):
+        for i, r in enumerate(part):
+            r.result, r.error = (results[i] if error is None else None), error
+            r.event.set()
+
     def _run(self):
+        pipelined = all(hasattr(self.detector, a) for a in ("submit_jpegs", "submit_frames", "collect"))
+        pending = deque()  # (slot, requests) in submission order; at most two: the library's two ring slots
+        free = [0, 1]
         while True:
-            batch = self._take()
-            if batch is None:
-                return
-            for part in ([r for r in batch if isinstance(r.frame, bytes)], [r for r in batch if not isinstance(r.frame, bytes)]):
-                if not part:
-                    continue
-                try:
-                    if isinstance(part[0].frame, bytes):
-                        results = self.detector.perform_jpegs([r.frame for r in part], threshold=part[0].threshold)
-                    else:
-                        results = self.detector.perform_frames(np.stack([r.frame for r in part]), threshold=part[0].threshold)
-                    for r, res in zip(part, results):
-                        r.result = res
-                except Exception as e:  # every caller of the part sees the failure, the worker lives on
-                    for r in part:
-                        r.error = e
-            self.batches_run += 1
-            self.frames_run += len(batch)
-            for r in batch:
-                r.event.set()
+            # with work in flight do not wait for new requests: whatever has arrived is taken, else the oldest batch is
+            # collected and delivered
+            batch = self._take(block=not pending)
+            if batch is None and not pending:
+                if self._closed:
+                    return
+                continue
+            if batch:
+                self.batches_run += 1
+                self.frames_run += len(batch)
+                for part in ([r for r in batch if isinstance(r.frame, bytes)], [r for r in batch if not isinstance(r.frame, bytes)]):
+                    if not part:
+                        continue
+                    encoded = isinstance(part[0].frame, bytes)
+                    try:
+                        if pipelined:
+                            if not free:
+                                slot, old = pending.popleft()
+                                free.append(slot)
+                                self._deliver(slot, old)
+                            slot = free.pop(0)
+                            try:
+                                if encoded:
+                                    self.detector.submit_jpegs(slot, [r.frame for r in part], part[0].threshold)
+                                else:
+                                    self.detector.submit_frames(slot, np.stack([r.frame for r in part]), part[0].threshold)
+                            except Exception:
+                                free.insert(0, slot)
+                                raise
+                            pending.append((slot, part))
+                        elif encoded:
+                            self._finish(part, self.detector.perform_jpegs([r.frame for r in part], threshold=part[0].threshold))
+                        else:
+                            self._finish(part, self.detector.perform_frames(np.stack([r.frame for r in part]), threshold=part[0].threshold))
+                    except Exception as e:  # every caller of the part sees the failure, the worker lives on
+                        self._finish(part, error=e)
+            else:
+                slot, old = pending.popleft()
+                free.append(slot)
+                self._deliver(slot, old)
+
+    def _deliver(self, slot, part):
+        try:
+            self._finish(part, self.detector.collect(slot))
+        except Exception as e:
+            self._finish(part, error=e)

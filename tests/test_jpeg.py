@@ -207,8 +207,28 @@ class _FakeDetector:
         return [[(2, 0.5, float(f.sum() % 1000), 0.0, 1.0, 1.0)] for f in frames]
 
 
-def test_service_routes_jpeg_bytes_to_the_library_and_other_formats_to_pil():
-    det = _FakeDetector()
+class _FakePipelinedDetector(_FakeDetector):
+    """Adds the two-slot submit / collect surface; checks the service never overruns a slot."""
+
+    def __init__(self):
+        super().__init__()
+        self.slots = {}
+
+    def submit_jpegs(self, slot, datas, threshold=0.1):
+        assert slot in (0, 1) and slot not in self.slots
+        self.slots[slot] = self.perform_jpegs(datas, threshold)
+
+    def submit_frames(self, slot, frames, threshold=0.1):
+        assert slot in (0, 1) and slot not in self.slots
+        self.slots[slot] = self.perform_frames(frames, threshold)
+
+    def collect(self, slot):
+        return self.slots.pop(slot)
+
+
+@pytest.mark.parametrize('fake', ['sync', 'pipelined'])
+def test_service_routes_jpeg_bytes_to_the_library_and_other_formats_to_pil(fake):
+    det = _FakeDetector() if fake == 'sync' else _FakePipelinedDetector()
     svc = BatchingService(det, max_batch=8, max_delay=0.05)
     a = picture(64, 64, 3)
     jpg = encode(a, quality=80)
