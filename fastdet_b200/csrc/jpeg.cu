@@ -451,6 +451,10 @@ void JpegPool::worker() {
 
 void JpegPool::run(int tasks, const std::function<void(int)>& fn) {
     if (tasks <= 0) return;
+    if (tasks == 1 || workers_.empty()) {  // nothing to share: do not wake the pool (batch-1 latency)
+        for (int i = 0; i < tasks; ++i) fn(i);
+        return;
+    }
     std::unique_lock<std::mutex> lk(mu_);
     fn_ = &fn;
     tasks_ = tasks;

@@ -48,12 +48,14 @@ def gather_results(local: Sequence[list], n_frames: int, dst: int = 0, group=Non
 
 
 def detect_sharded(detector, frames, threshold: float = 0.1, dst: int = 0, group=None):
-    """Runs `detector.perform_frames` on this rank's slice of `frames` ([n,h,w,3] u8, identical on every rank)
-    and gathers the per-frame results on `dst`."""
+    """Runs the detector on this rank's slice of `frames` — an [n,h,w,3] u8 array (`perform_frames`) or a list of encoded
+    payloads (`perform_jpegs`), identical on every rank — and gathers the per-frame results on `dst`."""
     import torch.distributed as dist
 
     n = len(frames)
     rank, world = (dist.get_rank(group), dist.get_world_size(group)) if dist.is_initialized() else (0, 1)
     begin, end = shard_range(n, rank, world)
-    local = detector.perform_frames(frames[begin:end], threshold=threshold) if end > begin else []
+    encoded = n > 0 and isinstance(frames[0], (bytes, bytearray, memoryview))
+    run = detector.perform_jpegs if encoded else detector.perform_frames
+    local = run(frames[begin:end], threshold=threshold) if end > begin else []
     return gather_results(local, n, dst=dst, group=group)

@@ -94,7 +94,9 @@ def test_no_cpu_fallback():
     m = _native.Model(data, 3, (64, 64), device=-1)
     frames = np.zeros((1, 64, 64, 3), np.uint8)
     for call in (lambda: m.forward(1), lambda: m.detect(frames, 0.1), lambda: m.normalise(frames),
-                 lambda: m.heads(1), lambda: m.preprocess(frames, 1, (64, 64))):
+                 lambda: m.heads(1), lambda: m.preprocess(frames, 1, (64, 64)), lambda: m.detect_jpeg([b"\xff\xd8"], 0.1),
+                 lambda: m.decode_jpeg([b"\xff\xd8"]), lambda: m.submit_jpeg(0, [b"\xff\xd8"], 0.1),
+                 lambda: m.submit(0, frames, 0.1)):
         with pytest.raises(_native.NativeError) as e:
             call()
         assert e.value.code == _native.FD_ERR_CUDA

@@ -32,17 +32,23 @@ class TagDetector:
         return [[(int(f[0, 0, 0]) + 1, 1.0, float(f[0, 0, 1]), 0.0, 1.0, 1.0)] * (int(f[0, 0, 2]) % 3) for f in frames]
 
 
+    def perform_jpegs(self, datas, threshold=0.1):
+        return [[(len(d), 1.0, float(d[0]), 0.0, 1.0, 1.0)] for d in datas]
+
+
 def _worker(rank, world, port, n_frames, out_path):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
     dist.init_process_group("gloo", rank=rank, world_size=world)
     rng = np.random.default_rng(0)
     frames = rng.integers(0, 200, size=(n_frames, 4, 4, 3), dtype=np.uint8)
     res = shard.detect_sharded(TagDetector(), frames, 0.1)
+    payloads = [bytes([i % 251]) * (i + 1) for i in range(n_frames)]  # encoded payloads shard the same way
+    res2 = shard.detect_sharded(TagDetector(), payloads, 0.1)
     if rank == 0:
         want = TagDetector().perform_frames(frames)
-        torch.save({"ok": res == want, "n": len(res)}, out_path)
+        torch.save({"ok": res == want and res2 == TagDetector().perform_jpegs(payloads), "n": len(res)}, out_path)
     else:
-        assert res is None
+        assert res is None and res2 is None
     dist.barrier()
     dist.destroy_process_group()
 
