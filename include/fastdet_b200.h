@@ -7,6 +7,8 @@
  *   fd_forward           self.model.run(None, {'input': a})             server/detector.py:135
  *   fd_postprocess       process_yolo + soft_nms + pixel scaling        server/detector.py:136-144, 45-59, 148-166
  *   fd_detect            ONNXDetector.perform after image decode        server/detector.py:126-146
+ *   fd_detect_jpeg       the whole of ONNXDetector.perform, JPEG bytes in   server/detector.py:126-146 (decode :128-133)
+ *   fd_pack_wire         DetectService.process_data's response packing   server/server.py:234-239
  *   fd_heads_fp32 ...    parity hooks (the raw tensors model.run returns, the f32 NCHW input tensor)
  *
  * Conventions: plain C types only; every function returns 0 on success or a negative FD_ERR_* code, with a

@@ -38,6 +38,34 @@ def main():
         out[f'jpeg{i}'] = np.frombuffer(data, np.uint8)
         out[f'rgb{i}'] = ref_jpeg.decode_reference(data)
         out[f'meta{i}'] = np.array([h, w, sub, q, rst])
+    # damaged-but-decodable streams whose coefficients leave the range where libjpeg's C text and its SIMD code agree
+    # (16-bit lane wrap, saturating packs, DC-only shortcut): Pillow's answer for them is part of the contract too
+    import warnings
+    from fastdet_b200 import _native
+    rng = np.random.default_rng(2024)
+    kept = 0
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        while kept < 8:
+            buf = io.BytesIO()
+            Image.fromarray(picture(40, 56, kept)).save(buf, 'JPEG', quality=int(rng.integers(30, 95)), subsampling=int(rng.integers(0, 3)))
+            d = bytearray(buf.getvalue())
+            for _ in range(int(rng.integers(1, 4))):
+                pos = int(rng.integers(2, len(d)))
+                d[pos] = int(rng.integers(0, 256))
+            d = bytes(d)
+            try:
+                _native.jpeg_coefficients(d)
+                rgb = ref_jpeg.decode_reference(d)
+            except Exception:
+                continue
+            clean = ref_jpeg.decode_reference(buf.getvalue())
+            if np.abs(rgb.astype(int) - clean.astype(int)).max() < 200:
+                continue  # keep the ones where the damage drives samples into the clamps
+            out[f'damaged_jpeg{kept}'] = np.frombuffer(d, np.uint8)
+            out[f'damaged_rgb{kept}'] = rgb
+            kept += 1
+    out['damaged_count'] = np.array(kept)
     out['count'] = np.array(len(cases))
     np.savez_compressed(os.path.join(HERE, 'jpeg.npz'), **out)
     print('wrote', os.path.join(HERE, 'jpeg.npz'), sum(v.nbytes for v in out.values()), 'bytes raw')

@@ -55,6 +55,17 @@ def test_restatement_matches_pillow_generated(sub):
         assert np.array_equal(ref_jpeg.decode(data), ref_jpeg.decode_reference(data)), (h, w, q, rst)
 
 
+def test_committed_damaged_streams():
+    """Pillow's pixels for damaged streams (fixture): the restatement on the NATIVE coefficients reproduces them, so the
+    overflow behaviour of libjpeg-turbo's SIMD IDCT is pinned independently of the Pillow build on the test machine."""
+    z = np.load(os.path.join(HERE, 'golden', 'jpeg.npz'))
+    assert int(z['damaged_count']) >= 8
+    for i in range(int(z['damaged_count'])):
+        d = z[f'damaged_jpeg{i}'].tobytes()
+        info, planes = _native.jpeg_coefficients(d)
+        assert np.array_equal(ref_jpeg.reconstruct(ref_jpeg.parse(d), planes), z[f'damaged_rgb{i}']), i
+
+
 def test_idct_known_answers():
     # DC only: every sample = clamp(descale(dc * q) + 128); a full-range DC saturates through the range-limit table
     q = np.full((8, 8), 16, np.int64)
