@@ -74,9 +74,9 @@ _PROTOS = {
     "fd_collect": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
     "fd_jpeg_probe": (C.c_int, [C.c_void_p, C.c_size_t, C.POINTER(FdJpegInfo)]),
     "fd_jpeg_coefficients": (C.c_int, [C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(FdJpegInfo)]),
-    "fd_decode_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
-    "fd_detect_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
-    "fd_submit_jpeg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
+    "fd_decode_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]),
+    "fd_detect_jpeg": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "fd_submit_jpeg": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_int, C.c_void_p]),
     "fd_letterbox_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int32)] * 4),
     "fd_unmap_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fd_pack_wire": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -237,26 +237,27 @@ class Model:
             raise JpegRefused((lib().fd_last_error() or b"").decode("utf-8", "replace"), status)
         _check(rc)
 
-    def decode_jpeg(self, datas, want_rgb=True):
+    def decode_jpeg(self, datas, want_rgb=True, allow_resize=False):
         """Decodes a list of JPEG byte strings into the input tensor of batch size len(datas); returns the decoded
         frames [n, net_h, net_w, 3] u8 if want_rgb (parity hook), and leaves them on the device for forward(n)."""
         n, keep, ptrs, lens, status = self._jpeg_args(datas)
         rgb = np.empty((n, self.net_h, self.net_w, 3), np.uint8) if want_rgb else None
-        rc = lib().fd_decode_jpeg(self._h, ptrs, lens, n, _ptr(status), _ptr(rgb) if want_rgb else None)
+        rc = lib().fd_decode_jpeg(self._h, ptrs, lens, n, int(allow_resize), _ptr(status), _ptr(rgb) if want_rgb else None)
         self._check_jpeg(rc, status)
         return rgb
 
-    def detect_jpeg(self, datas, threshold: float, max_det: int = 2048):
+    def detect_jpeg(self, datas, threshold: float, max_det: int = 2048, allow_resize=False):
         n, keep, ptrs, lens, status = self._jpeg_args(datas)
         dets = np.zeros((n, max_det), DET_DTYPE)
         counts = np.zeros(n, np.int32)
-        rc = lib().fd_detect_jpeg(self._h, ptrs, lens, n, float(threshold), max_det, _ptr(dets), _ptr(counts), _ptr(status))
+        rc = lib().fd_detect_jpeg(self._h, ptrs, lens, n, int(allow_resize), float(threshold), max_det, _ptr(dets), _ptr(counts),
+                                  _ptr(status))
         self._check_jpeg(rc, status)
         return dets, counts
 
-    def submit_jpeg(self, slot: int, datas, threshold: float, max_det: int = 2048):
+    def submit_jpeg(self, slot: int, datas, threshold: float, max_det: int = 2048, allow_resize=False):
         n, keep, ptrs, lens, status = self._jpeg_args(datas)
-        rc = lib().fd_submit_jpeg(self._h, slot, ptrs, lens, n, float(threshold), max_det, _ptr(status))
+        rc = lib().fd_submit_jpeg(self._h, slot, ptrs, lens, n, int(allow_resize), float(threshold), max_det, _ptr(status))
         self._check_jpeg(rc, status)
         if not hasattr(self, "_slot_shape"):
             self._slot_shape = {}

@@ -598,8 +598,8 @@ int slot_collect(fd_model* m, Slot& S, fd_det* out, int32_t* counts, int32_t* to
 // ------------------------------------------------------------------ JPEG front end (jpeg.h)
 // Host half of a JPEG batch: parse + entropy-decode every frame (one frame per pool thread) into the slot's pinned
 // buffer, laid out as [JpegFrameDev x n][coefficients of frame 0][frame 1]...  Fills status[] (FD_JPEG_*).
-int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size_t* lens, int n, int32_t* status,
-                    size_t* bytes_out, int* max_blocks_out) {
+int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, int32_t* status,
+                    size_t* bytes_out, int* max_blocks_out, int* src_w, int* src_h) {
     const ModelPlan& P = m->plan;
     if (!m->jpeg_pool) {
         int t = static_cast<int>(std::thread::hardware_concurrency());
@@ -616,12 +616,23 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
     m->jpeg_pool->run(n, [&](int i) {
         char buf[160] = "";
         st[i] = jpeg_parse(data[i], lens[i], &info[i], buf, sizeof(buf));
-        if (st[i] == JPEG_OK && (info[i].width != P.net_w || info[i].height != P.net_h)) {
-            st[i] = FD_JPEG_SIZE;
-            snprintf(buf, sizeof(buf), "%dx%d", info[i].width, info[i].height);
-        }
         why[i] = buf;
     });
+    // frame size: the network's (reference detector.py:131-132) or, with allow_resize, any one size for the whole batch
+    int want_w = P.net_w, want_h = P.net_h;
+    if (allow_resize)
+        for (int i = 0; i < n; ++i)
+            if (st[i] == JPEG_OK) { want_w = info[i].width; want_h = info[i].height; break; }
+    if (want_w > 8192 || want_h > 8192) { want_w = P.net_w; want_h = P.net_h; }  // bounds the staging memory
+    for (int i = 0; i < n; ++i)
+        if (st[i] == JPEG_OK && (info[i].width != want_w || info[i].height != want_h)) {
+            st[i] = FD_JPEG_SIZE;
+            char buf[64];
+            snprintf(buf, sizeof(buf), "%dx%d", info[i].width, info[i].height);
+            why[i] = buf;
+        }
+    *src_w = want_w;
+    *src_h = want_h;
     bool only_size = true;
     int bad = -1;
     for (int i = n - 1; i >= 0; --i)
@@ -689,10 +700,22 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
 
 // Device half: pinned -> device staging on the copy stream, then IDCT and colour conversion on the compute stream,
 // ending with RGB u8 frames in the Exec's input tensor (where fd_preprocess would have put them).
-int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int max_blocks) {
+int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int max_blocks, int src_w, int src_h) {
     const ModelPlan& P = m->plan;
     if (int rc = slot_stage_reserve(S, bytes)) return rc;
-    const size_t plane_stride = size_t(3) * ((P.net_w + 15) / 16 * 16) * ((P.net_h + 15) / 16 * 16);
+    const bool same = src_w == P.net_w && src_h == P.net_h;
+    const size_t plane_stride = size_t(3) * ((src_w + 15) / 16 * 16) * ((src_h + 15) / 16 * 16);
+    uint8_t* rgb = e->frames;
+    if (!same) {  // decode at the source size, then the letterbox of fd_preprocess
+        const size_t src_bytes = size_t(n) * src_w * src_h * 3;
+        if (e->src_cap < src_bytes) {
+            CU(cudaDeviceSynchronize());
+            cudaFree(e->src); e->src = nullptr; e->src_cap = 0;
+            CU(cudaMalloc(&e->src, src_bytes));
+            e->src_cap = src_bytes;
+        }
+        rgb = e->src;
+    }
     if (m->jpeg_planes_cap < plane_stride * n) {
         CU(cudaDeviceSynchronize());
         cudaFree(m->jpeg_planes); m->jpeg_planes = nullptr; m->jpeg_planes_cap = 0;
@@ -718,8 +741,10 @@ int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int ma
     if (launch_jpeg_idct(coefs, fr, m->jpeg_planes, plane_stride, n, max_blocks, s))
         return fail(FD_ERR_CUDA, "JPEG kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (prof) CU(cudaEventRecord(ev[2], s));
-    if (launch_jpeg_rgb(m->jpeg_planes, plane_stride, fr, e->frames, n, P.net_h, P.net_w, s))
+    if (launch_jpeg_rgb(m->jpeg_planes, plane_stride, fr, rgb, n, src_h, src_w, s))
         return fail(FD_ERR_CUDA, "JPEG kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (!same && launch_letterbox_u8(rgb, e->frames, n, src_h, src_w, P.net_h, P.net_w, 128, s))
+        return fail(FD_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (prof) {
         CU(cudaEventRecord(ev[3], s));
         CU(cudaDeviceSynchronize());
@@ -813,7 +838,8 @@ int fd_jpeg_coefficients(const uint8_t* data, size_t len, int16_t* coefs, size_t
     return FD_OK;
 }
 
-int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int32_t* status, uint8_t* rgb_out) {
+int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, int32_t* status,
+                   uint8_t* rgb_out) {
     if (!m || !data || !lens) return fail(FD_ERR_ARG, "fd_decode_jpeg: null argument");
     NEED_DEVICE(m);
     CU(cudaSetDevice(m->device));
@@ -827,38 +853,38 @@ int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, 
         CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
     }
     size_t bytes = 0;
-    int max_blocks = 0;
-    if (int rc = jpeg_host_stage(m, S, data, lens, n, status, &bytes, &max_blocks)) return rc;
-    if (int rc = jpeg_device_stage(m, e, S, n, bytes, max_blocks)) return rc;
+    int max_blocks = 0, sw = 0, sh = 0;
+    if (int rc = jpeg_host_stage(m, S, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;
+    if (int rc = jpeg_device_stage(m, e, S, n, bytes, max_blocks, sw, sh)) return rc;
     if (rgb_out) CU(cudaMemcpyAsync(rgb_out, e->frames, size_t(n) * m->plan.net_w * m->plan.net_h * 3, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
     return FD_OK;
 }
 
-int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, double threshold, int max_det,
-                   int32_t* status) {
+int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, double threshold,
+                   int max_det, int32_t* status) {
     if (!m || !data || !lens) return fail(FD_ERR_ARG, "fd_submit_jpeg: null argument");
     if (slot < 0 || slot >= FD_MAX_SLOTS) return fail(FD_ERR_ARG, "fd_submit_jpeg: slot %d out of range [0, %d)", slot, FD_MAX_SLOTS);
     Exec* e;
     Slot* sp;
     if (int rc = slot_begin(m, slot, n, max_det, &e, &sp)) return rc;
     size_t bytes = 0;
-    int max_blocks = 0;
-    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, status, &bytes, &max_blocks)) return rc;
-    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks)) return rc;
+    int max_blocks = 0, sw = 0, sh = 0;
+    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;
+    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks, sw, sh)) return rc;
     return slot_finish(m, e, *sp, n, threshold, max_det);
 }
 
-int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, double threshold, int max_det, fd_det* out,
-                   int32_t* counts, int32_t* status) {
+int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, double threshold, int max_det,
+                   fd_det* out, int32_t* counts, int32_t* status) {
     if (!m || !data || !lens || !out || !counts) return fail(FD_ERR_ARG, "fd_detect_jpeg: null argument");
     Exec* e;
     Slot* sp;
     if (int rc = slot_begin(m, FD_MAX_SLOTS, n, max_det, &e, &sp)) return rc;
     size_t bytes = 0;
-    int max_blocks = 0;
-    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, status, &bytes, &max_blocks)) return rc;
-    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks)) return rc;
+    int max_blocks = 0, sw = 0, sh = 0;
+    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;
+    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks, sw, sh)) return rc;
     if (int rc = slot_finish(m, e, *sp, n, threshold, max_det)) return rc;
     return slot_collect(m, *sp, out, counts, nullptr);
 }

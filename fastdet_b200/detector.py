@@ -94,14 +94,14 @@ class ONNXDetector(Detector):
         self.logger.info(f'perform: results={results}')
         return results
 
-    def _decode_host(self, data):
+    def _decode_host(self, data, check_size=True):
         """The reference's own decode lines (server/detector.py:128-133), with their exceptions: used for payloads the
         device JPEG decoder refuses (PNG, progressive or grey JPEG, damaged streams ...)."""
         from PIL import Image
-        (width, height) = self.image_size
         img = Image.open(io.BytesIO(data))
-        if img.size != self.image_size:
+        if check_size and img.size != self.image_size:
             raise ValueError('invalid image size')
+        (width, height) = img.size
         frame = np.array(img)
         if frame.ndim != 3 or frame.shape[2] != 3:
             # the reference's reshape(1,height,width,3) raises ValueError for non-RGB modes (:133)
@@ -116,20 +116,27 @@ class ONNXDetector(Detector):
             return 'host'
         return 'device' if (info.width, info.height) == tuple(self.image_size) else 'size'
 
-    def perform_jpegs(self, datas, threshold=0.1):
+    def perform_jpegs(self, datas, threshold=0.1, allow_resize=False, source_coords=False):
         """perform() for a batch of encoded payloads: one result list per payload.  Baseline JPEGs are decoded by the
         library (Huffman on its host thread pool, IDCT / upsampling / colour on the device: fd_detect_jpeg), bit-identical
-        to PIL; if the library refuses any payload of the batch, the batch is decoded the reference's way instead."""
+        to PIL; if the library refuses any payload of the batch, the batch is decoded the reference's way instead.
+        allow_resize / source_coords (extension): as in perform_frames, for payloads of one common size other than the
+        network's."""
         self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
         datas = list(datas)
         try:
-            dets, counts = self.model.detect_jpeg(datas, threshold, max_det=self.max_det)
+            dets, counts = self.model.detect_jpeg(datas, threshold, max_det=self.max_det, allow_resize=allow_resize)
             self.jpeg_device_frames += len(datas)
+            if allow_resize and source_coords and datas:
+                info = _native.jpeg_probe(bytes(datas[0]))
+                if (info.width, info.height) != tuple(self.image_size):
+                    for f in range(dets.shape[0]):
+                        dets[f, :counts[f]] = _native.unmap_letterbox(dets[f, :counts[f]], (info.width, info.height), self.image_size)
             return self._tuples(dets, counts)
         except _native.JpegRefused:
-            frames = np.stack([self._decode_host(d) for d in datas])
+            frames = np.stack([self._decode_host(d, check_size=not allow_resize) for d in datas])
             self.jpeg_host_frames += len(datas)
-            return self.perform_frames(frames, threshold=threshold)
+            return self.perform_frames(frames, threshold=threshold, allow_resize=allow_resize, source_coords=source_coords)
 
     # -- extras --------------------------------------------------------------------------------
     def perform_frames(self, frames, threshold=0.1, allow_resize=False, source_coords=False):

@@ -132,7 +132,9 @@ int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* tot
  * libjpeg(-turbo)'s default output, written straight into the batch's input tensor.  Baseline / extended-sequential
  * Huffman, 8-bit, 3-component YCbCr, 4:4:4 / 4:2:2 / 4:2:0, restart intervals.  Anything else is refused with
  * FD_ERR_JPEG before any device work (no approximation, no silent host decode): status[n] (may be NULL) receives one
- * FD_JPEG_* per frame.  A batch whose only problem is the frame size returns FD_ERR_SIZE like fd_detect. */
+ * FD_JPEG_* per frame.  A batch whose only problem is the frame size returns FD_ERR_SIZE like fd_detect.
+ * allow_resize != 0 (extension, as in fd_preprocess): the frames may have any ONE size (that of the first decodable
+ * frame, at most 8192 x 8192); they are decoded at that size and letterboxed to the network's on the device. */
 typedef struct fd_jpeg_info {
     int32_t status; /* FD_JPEG_* (size is not checked here) */
     int32_t width, height, components;
@@ -149,13 +151,14 @@ int fd_jpeg_probe(const uint8_t* data, size_t len, fd_jpeg_info* out);
 int fd_jpeg_coefficients(const uint8_t* data, size_t len, int16_t* coefs, size_t cap, fd_jpeg_info* out);
 /* Decode n JPEGs into the model's input tensor for batch size n (where fd_preprocess puts frames), synchronous; follow
  * with fd_forward(m, n, NULL).  rgb_out (host, may be NULL) receives the decoded frames [n, net_h, net_w, 3]. */
-int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int32_t* status, uint8_t* rgb_out);
+int fd_decode_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, int32_t* status,
+                   uint8_t* rgb_out);
 /* fd_detect / fd_submit taking JPEG bytes.  The entropy decode runs inside the call on the host pool (while the device
  * works on the other slot); collect with fd_collect. */
-int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, double threshold, int max_det,
-                   fd_det* out, int32_t* counts, int32_t* status);
-int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, double threshold,
-                   int max_det, int32_t* status);
+int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, double threshold,
+                   int max_det, fd_det* out, int32_t* counts, int32_t* status);
+int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size_t* lens, int n, int allow_resize,
+                   double threshold, int max_det, int32_t* status);
 
 /* Letterbox bookkeeping (host only; extension — the reference rejects frames that are not network-sized).  With
  * allow_resize the frame is scaled to new_w x new_h (aspect kept, the long side filling the network) and centred at

@@ -339,6 +339,36 @@ def test_device_decode_of_damaged_streams_equals_pillow():
 
 
 @pytest.mark.gpu
+def test_jpeg_of_another_size_is_letterboxed_like_decoded_frames():
+    """allow_resize for encoded payloads: decode at the source size on the device, then the same letterbox as
+    fd_preprocess — pixels and detections equal the Pillow-decode + letterbox route bit for bit."""
+    from fastdet_b200 import detector as fdet
+    onnx, m = gpu_model()
+    rng = np.random.default_rng(9)
+    for (h, w, sub) in [(480, 640, 2), (360, 202, 1), (833, 417, 0)]:
+        frames = [np.clip(np.kron(rng.integers(0, 255, (h // 8 + 1, w // 8 + 1, 3)), np.ones((8, 8, 1)))[:h, :w] +
+                          rng.normal(0, 6, (h, w, 3)), 0, 255).astype(np.uint8) for _ in range(3)]
+        datas = [encode(f, quality=85, subsampling=sub) for f in frames]
+        decoded = np.stack([ref_jpeg.decode_reference(d) for d in datas])
+        want = m.letterbox(decoded)
+        got = m.decode_jpeg(datas, allow_resize=True)
+        assert np.array_equal(got, want), (h, w)
+        d0, c0 = m.detect(decoded, 0.05, allow_resize=True, max_det=256)
+        d1, c1 = m.detect_jpeg(datas, 0.05, max_det=256, allow_resize=True)
+        assert np.array_equal(c0, c1)
+        for f in range(3):
+            assert d0[f, :c0[f]].tobytes() == d1[f, :c1[f]].tobytes()
+    with pytest.raises(ValueError, match='invalid image size'):
+        m.detect_jpeg(datas, 0.05)  # without allow_resize the reference's size check stands
+    with pytest.raises(ValueError, match='invalid image size'):  # one size per batch
+        m.detect_jpeg([datas[0], encode(modelgen.synthetic_frame(1, 416), quality=80)], 0.05, allow_resize=True)
+    det = fdet.ONNXDetector(onnx, num_classes=80, image_size=(416, 416), max_det=256)
+    a = det.perform_jpegs(datas, threshold=0.05, allow_resize=True, source_coords=True)
+    b = det.perform_frames(decoded, threshold=0.05, allow_resize=True, source_coords=True)
+    assert a == b and det.jpeg_device_frames == 3
+
+
+@pytest.mark.gpu
 def test_detect_jpeg_equals_detect_on_pillow_frames():
     _, m = gpu_model()
     datas = [encode(modelgen.synthetic_frame(300 + i, 416), quality=80, subsampling=2 if i % 2 else 0) for i in range(5)]
