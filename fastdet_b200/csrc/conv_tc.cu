@@ -100,8 +100,14 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
     const bool generic_act = p.act == 2;
     const float alpha_eff = p.act ? p.alpha : 1.0f;
     const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
-    const long long m_own = m_base + lane;  // the pixel row this lane holds
-    const bool own_ok = m_own < p.M;
+    long long m_own = m_base + lane;  // the pixel row this lane holds
+    bool own_ok = m_own < p.M;
+    if (p.strip) {  // m_base counts zero-padded flat positions: back to the pixel row, pad positions hold nothing
+        const int q = static_cast<int>(m_own), plane = p.strip_wp * p.strip_hp;
+        const int img = q / plane, rem = q - img * plane, yp = rem / p.strip_wp, xp = rem - yp * p.strip_wp;
+        own_ok = q < p.strip_total_q && yp >= 1 && yp <= p.ho && xp >= 1 && xp <= p.wo;
+        m_own = own_ok ? (static_cast<long long>(img) * p.ho + (yp - 1)) * p.wo + (xp - 1) : 0;
+    }
     const bool has_res = mode == 0 && p.residual != nullptr;
     const __nv_bfloat16* res_row = p.residual + m_own * p.res_pitch + n0;
     ptx::U32x8 rnext[2];
@@ -188,6 +194,50 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
             for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
         }
         lap(2);
+        if (p.strip && !has_res) {
+            // The lane's rows are scattered over the image (pad positions in between), so no TMA box fits them: 64 bytes
+            // per lane straight from the registers (measured faster than the staged form below when nothing else loads)
+            if (own_ok) {
+                __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + m_own * p.out_pitch + n0 + c0;
+#pragma unroll
+                for (int c = 0; c < 4; ++c)
+                    if (n0 + c0 + 8 * c < p.cout)
+                        *reinterpret_cast<uint4*>(op + 8 * c) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            }
+            lap(3);
+            return;
+        }
+        if (p.strip) {
+            // With a residual the row-per-lane loads and stores (32 LSU wavefronts per instruction each) get in each
+            // other's way: two chunks are staged as 32 rows x 128 B (128-byte swizzle), read back with 8 lanes per row, and
+            // stored with every instruction covering 4 whole 128-byte lines.
+            const bool second = ((c0 - c_begin) & 32) != 0;
+#pragma unroll
+            for (int c = 0; c < 4; ++c)
+                *reinterpret_cast<uint4*>(stage + lane * 128 + (((c + (second ? 4 : 0)) ^ (lane & 7)) << 4)) =
+                    make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+            if (second) {
+                __syncwarp();
+                const int sub = lane >> 3, ch = lane & 7;
+                const int row32 = own_ok ? static_cast<int>(m_own) : -1;
+                uint4 v[8];
+                int mrow[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int r = 4 * i + sub;
+                    v[i] = *reinterpret_cast<const uint4*>(stage + r * 128 + ((ch ^ (r & 7)) << 4));
+                    mrow[i] = __shfl_sync(0xffffffffu, row32, r);
+                }
+                const int col = n0 + c0 - 32 + 8 * ch;
+#pragma unroll
+                for (int i = 0; i < 8; ++i)
+                    if (mrow[i] >= 0 && col < p.cout)
+                        *reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + static_cast<long long>(mrow[i]) * p.out_pitch + col) = v[i];
+                __syncwarp();  // the staging tile is rewritten by the next pair of chunks
+            }
+            lap(3);
+            return;
+        }
         if (mode == 0 && HALF_N >= 64 && p.store64) {
             // two chunks share one staging tile of 32 rows x 128 B (128-byte swizzle: 16-byte chunk k of row r at slot
             // k ^ (r & 7)) and leave through ONE TMA store: half the store requests (the TMA engine moves about one
@@ -516,7 +566,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool b_res = !TWO && p.b_resident != 0;
     // swapped mode: slot 0 (the MMA's M side, 128 rows) holds filter rows, slot 1 (N side, 256 rows) holds pixels
     constexpr bool swap = SWAP;
-    const uint32_t a_bytes = BLOCK_M * p.block_k * 2;
+    const bool strip = TWO && p.strip != 0;  // A comes from per-channel-block strips (see ConvParams::strip), the ring carries B only
+    uint64_t* strip_full_bar = reinterpret_cast<uint64_t*>(smem + 640);
+    uint64_t* strip_empty_bar = strip_full_bar + 2;
+    const uint32_t a_bytes = strip ? 0u : BLOCK_M * p.block_k * 2;
     const uint32_t b_bytes = B_ROWS * p.block_k * 2;
     uint8_t* bres = smem + SMEM_RING_OFF;
     uint8_t* ring = bres + (b_res ? b_bytes * p.num_k_blocks : 0u);
@@ -556,6 +609,10 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_init(&tmem_empty_bar[i], TWO ? 16 : (BLOCK_N < 64 ? 4 : 8));  // one arrive per epilogue warp (of both CTAs) draining the stage
         }
         ptx::mbar_init(bres_bar, 1);
+        for (int i = 0; i < 2; ++i) {
+            ptx::mbar_init(&strip_full_bar[i], 1);
+            ptx::mbar_init(&strip_empty_bar[i], 1);
+        }
         ptx::fence_barrier_init();
     }
     if (warp == 2) {
@@ -581,6 +638,9 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int n_tiles_n = p.num_n_tiles;
     const bool prof = p.prof != nullptr;
     constexpr int TILE_M = TWO ? 2 * BLOCK_M : BLOCK_M;
+    const uint32_t strip_stride = (static_cast<uint32_t>(p.strip_rows) * 128u + 1023u) & ~1023u;
+    const uint32_t strips_base_v = ring_base_v + static_cast<uint32_t>(STAGES) * stage_bytes;  // two strip buffers behind the ring
+    const uint32_t strip_bar_v = ptx::smem_u32(strip_full_bar);  // full[i] at +8i, empty[i] at +16+8i
 
     if (warp == 0) {
         // ------------------------------------------------------------------ TMA producer (both CTAs of a pair)
@@ -604,10 +664,37 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         ptx::grid_dep_wait();  // weights above are constants; everything below reads the previous layer's output
         const long long t_start = clock64();
+        int sidx = 0;  // strips loaded so far (strip mode)
+        const uint32_t strips_base = __shfl_sync(0xffffffffu, strips_base_v, 0), strip_bar = __shfl_sync(0xffffffffu, strip_bar_v, 0);
         for (int item = unit; item < num_items && !(p.debug & 8); item += units) {
             const int tile = tile_of(item), part = quad ? 0 : item - tile * split_k;
             const int kb_lo = (part * nkb) / split_k, kb_hi = ((part + 1) * nkb) / split_k;
             const int m_tile = tile / n_tiles_n;
+            if (strip) {
+                const int n0s = (tile - m_tile * n_tiles_n) * BLOCK_N + static_cast<int>(cta_rank) * B_ROWS;
+                const int wp = p.strip_wp, plane = p.strip_wp * p.strip_hp;
+                const int qs = p.strip_qfirst + m_tile * TILE_M + static_cast<int>(cta_rank) * BLOCK_M - wp - 1;  // first strip position
+                const int simg = qs / plane, srem = qs - simg * plane, syp = srem / wp, sxp = srem - syp * wp;
+                for (int cbi = 0; cbi < cin_blocks; ++cbi, ++sidx) {
+                    const int sb = sidx & 1;
+                    const uint32_t sfull = strip_bar + 8u * sb;
+                    ptx::mbar_wait_addr(sfull + 16u, ((sidx >> 1) & 1) ^ 1);  // the MMAs of two strips ago have retired
+                    if (issuer && cta_rank == 0) ptx::mbar_arrive_expect_tx_addr(sfull, static_cast<uint32_t>(p.strip_rows) * 128u * 2u);
+                    if (issuer)
+                        ptx::tma2_load_im2col_4d_addr(strips_base + sb * strip_stride, mapA, sfull & ptx::kPeerBitMask, cbi * block_k, sxp - 1,
+                                                      syp - 1, simg, 0, 0);
+                    for (int tap = 0; tap < 9; ++tap) {
+                        const uint32_t full_addr = bar_base + 8u * stage;
+                        ptx::mbar_wait_addr(full_addr + 8u * MAX_STAGES, phase ^ 1);
+                        if (issuer && cta_rank == 0) ptx::mbar_arrive_expect_tx_addr(full_addr, b_bytes * 2u);
+                        if (issuer)
+                            ptx::tma2_load_2d_addr(ring_base + stage * stage_bytes, mapB, full_addr & ptx::kPeerBitMask,
+                                                   (tap * cin_blocks + cbi) * block_k, n0s);
+                        if (++stage == STAGES) { stage = 0; phase ^= 1; }
+                    }
+                }
+                continue;
+            }
             // normal: m0 = first output pixel (M side), n0 = first output channel (N side)
             // swapped: m0 = first output pixel (N side, 256 per tile), n0 = first output channel (M side, 128 per tile)
             const int n0 = swap ? (tile - m_tile * n_tiles_n) * BLOCK_M
@@ -701,8 +788,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // before, against 48 the tensor core needs at N = 64 — dev/mma_rate.cu).
         auto run = [&](auto ks_tag) {
             constexpr int KS = decltype(ks_tag)::value;  // MMAs (16-wide K steps) per K block
-            int stage = 0, it = 0;
+            int stage = 0, it = 0, sidx = 0;
             uint32_t phase = 0, stage_off = 0;
+            const uint32_t strip_bar = __shfl_sync(0xffffffffu, strip_bar_v, 0);
+            const uint64_t strip_desc0 = ptx::make_kmajor_desc(__shfl_sync(0xffffffffu, strips_base_v, 0), 1024u, 2u);
+            const uint32_t strip_units = strip_stride >> 4, wp_units = static_cast<uint32_t>(p.strip_wp) * 8u;  // 128-byte rows in 16-byte units
             for (int item = unit; item < num_items; item += units, ++it) {
                 const int part = item % split_k;
                 const int kb_lo = (part * nkb) / split_k, kb_hi = ((part + 1) * nkb) / split_k;
@@ -714,6 +804,38 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::tc_fence_after();
                 const uint32_t tmem_d = tmem_base + as * BLOCK_N;
                 uint32_t accumulate = 0, bres_off = kb_lo * b_units;
+                if (strip) {
+                    for (int cbi = 0; cbi < cin_blocks; ++cbi, ++sidx) {
+                        const int sb = sidx & 1;
+                        const long long ts0 = prof ? clock64() : 0;
+                        ptx::mbar_wait_addr(strip_bar + 8u * sb, (sidx >> 1) & 1);
+                        if (prof) t_full += clock64() - ts0;
+                        const uint64_t sdesc = strip_desc0 + sb * strip_units;
+                        uint32_t tap_off = 0;
+                        for (int ky = 0; ky < 3; ++ky, tap_off += wp_units) {
+                            for (int kx = 0; kx < 3; ++kx) {
+                                const uint32_t full_addr = bar_base + 8u * stage;
+                                const long long tf0 = prof ? clock64() : 0;
+                                ptx::mbar_wait_addr(full_addr, phase);
+                                if (prof) t_full += clock64() - tf0;
+                                ptx::tc_fence_after();
+                                if (issuer) {
+                                    issue_mmas<KS, TWO>(tmem_d, sdesc + tap_off + 8u * kx, desc0 + stage_off, idesc, accumulate != 0);
+                                    ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
+                                }
+                                accumulate = 1;
+                                __syncwarp();
+                                stage_off += stage_units;
+                                if (++stage == STAGES) { stage = 0; stage_off = 0; phase ^= 1; }
+                            }
+                        }
+                        if (issuer) ptx::umma2_commit_mcast_addr(strip_bar + 16u + 8u * sb, 3);  // strip buffer free in both CTAs
+                        __syncwarp();
+                    }
+                    if (issuer) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, 3);
+                    __syncwarp();
+                    continue;
+                }
                 for (int kb = kb_lo; kb < kb_hi; kb += kps) {
                     const int nsub = (kb_hi - kb < kps) ? kb_hi - kb : kps;
                     const uint32_t full_addr = bar_base + 8u * stage;
@@ -779,7 +901,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 continue;
             }
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
-            const long long m_base = static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
+            const long long m_base = (strip ? p.strip_qfirst : 0) + static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
             epilogue_tile<BLOCK_N>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
                                    prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
         }
@@ -927,6 +1049,22 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     const int quad = (two && (force_quad || (quad_env && ((m_tiles + 1) / 2) * ((d.cout + bn - 1) / bn) >= 2LL * quads_max))) ? 1 : 0;
     if (swap) m_tiles = (M + 255) / 256;
     ConvParams& p = L->p;
+    // strip mode (see ConvParams::strip): 3x3 / stride 1 / pad 1 layers of the CTA-pair kernel on maps where the pad
+    // positions cost less than the operand bytes saved.  FASTDET_STRIP=0 switches it off, =2 forces it wherever it is legal.
+    {
+        static const int strip_env = getenv("FASTDET_STRIP") ? atoi(getenv("FASTDET_STRIP")) : 1;
+        const int wp = d.wi + 2, hp = d.hi + 2, rows = 128 + 2 * wp + 2;
+        const bool legal = two && !quad && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
+                           !d.upsample2x && rows <= 256 && static_cast<long long>(d.n) * wp * hp < (1LL << 30);
+        const bool pays = d.wi >= 20;  // (W+2)(H+2)/(WH): 1.08 at 52x52, 1.16 at 26x26 (both measured faster), 1.33 at 13x13 (not)
+        if (legal && strip_env && (pays || strip_env == 2)) {
+            p.strip = 1;
+            p.strip_wp = wp; p.strip_hp = hp; p.strip_rows = rows;
+            p.strip_qfirst = wp + 1;
+            p.strip_total_q = static_cast<int>(d.n) * wp * hp;
+            m_tiles = (p.strip_total_q - p.strip_qfirst + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
+        }
+    }
     p.M = static_cast<int>(M);
     p.cout = d.cout;
     p.num_k_blocks = k * k * cin_blocks;
@@ -980,9 +1118,11 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
                                  static_cast<cuuint64_t>(d.in_pitch) * 2 * d.wi * d.hi};
         int lower[2] = {-d.pad_lo, -d.pad_lo};
         int upper[2] = {d.pad_hi - (k - 1), d.pad_hi - (k - 1)};
+        if (p.strip) { lower[0] = lower[1] = -1; upper[0] = upper[1] = 1; }  // traversal = the zero-padded image, W+2 x H+2
         cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
         r = g_encodeIm2col(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), dims,
-                           strides, lower, upper, static_cast<cuuint32_t>(block_k), swap ? 256u : BLOCK_M, estr,
+                           strides, lower, upper, static_cast<cuuint32_t>(block_k),
+                           p.strip ? static_cast<cuuint32_t>(p.strip_rows) : (swap ? 256u : BLOCK_M), estr,
                            CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         // Same driver quirk CUTLASS works around for im2col maps over small tensors (< 128 KiB).
@@ -1042,7 +1182,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
         // (a split costs ~8-10 us of fences, counter traffic and partial-sum reads, so it only pays on long K loops)
         static const int min_kb = getenv("FASTDET_SPLITK_MIN_KB") ? atoi(getenv("FASTDET_SPLITK_MIN_KB")) : 32;
         static const int max_s = getenv("FASTDET_SPLITK_MAX") ? atoi(getenv("FASTDET_SPLITK_MAX")) : 4;
-        if (d.allow_split_k && !no_split && !swap && !quad && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
+        if (d.allow_split_k && !no_split && !swap && !quad && !p.strip && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
             long long sk = units_max / whole;
             if (sk > max_s) sk = max_s;
             if (sk > p.num_k_blocks / 4) sk = p.num_k_blocks / 4;
@@ -1067,7 +1207,8 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     const int b_total = bn * K * 2;  // the whole filter bank of one N tile
     const int b_res = (!two && !swap && p.num_n_tiles == 1 && b_total <= 65536 && !getenv("FASTDET_NO_BRES")) ? 1 : 0;
     p.b_resident = b_res;
-    const int sub_bytes = (BLOCK_M + (b_res ? 0 : (two ? bn / 2 : bn))) * block_k * 2;
+    const int sub_bytes = ((p.strip ? 0 : BLOCK_M) + (b_res ? 0 : (two ? bn / 2 : bn))) * block_k * 2;
+    const int strips_bytes = p.strip ? 2 * ((p.strip_rows * 128 + 1023) / 1024 * 1024) : 0;
     int kps = 1;
     const int ring_avail = SMEM_LIMIT - 1024 - SMEM_RING_OFF - (b_res ? b_total : 0);
     if (swap) {
@@ -1083,12 +1224,12 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     }
     if (getenv("FASTDET_KPS")) kps = atoi(getenv("FASTDET_KPS"));
     const int stage_bytes = sub_bytes * kps;
-    int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF - (b_res ? bn * block_k * 2 * p.num_k_blocks : 0)) / stage_bytes;
+    int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF - strips_bytes - (b_res ? bn * block_k * 2 * p.num_k_blocks : 0)) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
     if (stages < 2) { set_err(err, errlen, "conv_tc: stage does not fit in shared memory"); return -1; }
     p.num_stages = stages;
     p.kb_per_stage = kps;
-    L->smem_bytes = 1024 + SMEM_RING_OFF + (b_res ? bn * block_k * 2 * p.num_k_blocks : 0) + static_cast<size_t>(stages) * stage_bytes;
+    L->smem_bytes = 1024 + SMEM_RING_OFF + (b_res ? bn * block_k * 2 * p.num_k_blocks : 0) + static_cast<size_t>(stages) * stage_bytes + strips_bytes;
     L->flops = 2.0 * double(M) * d.cout * K;
     return 0;
 }

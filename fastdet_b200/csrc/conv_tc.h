@@ -72,6 +72,12 @@ struct ConvParams {
     int* counters;
     int swap_tma;  // swapped mode: plain bf16 outputs without residual leave through TMA stores (32 ch x 32 pixels, SWIZZLE_64B)
     int head_tma;  // fp32 head rows leave through TMA stores (32 columns x 32 rows, SWIZZLE_128B)
+    // "strip" mode (3x3, stride 1, pad 1 on the CTA-pair kernel): the M side walks the zero-padded, flattened pixel
+    // positions q = (n * (H+2) + y+1) * (W+2) + x+1; ONE im2col load per 64-channel block (bounding box one pixel larger
+    // than the image on every side, out-of-bounds = zeros) brings the strip of strip_rows = 128 + 2(W+2) + 2 positions a
+    // CTA's 128 rows need, and the nine taps are descriptor row offsets ky*(W+2)+kx into it: a third of the operand
+    // bytes of nine separate tap tiles.  Pad positions are computed and never stored.
+    int strip, strip_wp, strip_hp, strip_rows, strip_qfirst, strip_total_q;
     int store64;   // 1: the output map's box is 64 channels x 32 rows (SWIZZLE_128B), two chunks per TMA store
     int res_v8;    // 1: residual rows are 32-byte aligned -> 256-bit loads
     int epi_mode;  // 0 bf16 slice through a TMA store (+ residual), 1 fp32 head rows, 2 bf16 with x2 upsampling

@@ -290,6 +290,11 @@ int main(int argc, char** argv) {
             {"2cta 1x1 512->256 many",  8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 1, 0, 0, 0, 512},
             {"2cta 1x1 256->256 up",    2, 13, 13, 256, 256, 1, 1, 0, 0, 1, 0, 0, 1, 64, 512},
             {"2cta 3x3 128->256 big",   16, 52, 52, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            // strip mode of the pair kernel (W >= 40): odd sizes, residual, two N tiles, the widest legal map (61: 256 strip rows)
+            {"strip 3x3 64->256 odd",   3, 44, 41, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"strip 3x3 128->512 2n",   2, 52, 52, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 64, 512},
+            {"strip 3x3 64->256 w61",   1, 7, 61, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"strip 3x3 64->256 w62",   1, 7, 62, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
             {"1cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 257},
             {"quad 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 768},
             {"quad 3x3 64->256 odd M",  4, 13, 13, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 768},
@@ -351,6 +356,12 @@ int main(int argc, char** argv) {
             time_case("1x1 1024->512 @13 bs64", 64, 13, 1024, 512, 1, 1, sms, bn);
             time_case("3x3 256->512 s2 @52 bs64", 64, 52, 256, 512, 3, 2, sms, bn);
         }
+    }
+    if (!strcmp(mode, "strip")) {  // run with FASTDET_STRIP=0 / 1 / 2 to compare
+        time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 512);
+        time_case("3x3 128->256 @52 bs64 res", 64, 52, 128, 256, 3, 1, sms, 512, 0, 1);
+        time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, 512);
+        time_case("3x3 512->1024 @13 bs64", 64, 13, 512, 1024, 3, 1, sms, 512);
     }
     if (!strcmp(mode, "grid")) {
         for (int g : {148, 111, 74, 37, 16}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 0, 0, 0, g);
