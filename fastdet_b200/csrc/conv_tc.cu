@@ -85,7 +85,10 @@ __device__ __forceinline__ float2 bias_act2(uint32_t a0, uint32_t a1, float b0, 
 // chunk c+1 is in flight while chunk c is processed.
 //   p.epi_mode 0: bf16 NHWC slice via TMA store (+ residual)   1: fp32 head rows, direct stores
 //              2: bf16 with x2 nearest upsampling (2 layers): staged, re-read transposed, 4 coalesced stores per row
-template <int BLOCK_N>
+// STRIP / RES: compile-time copies for the strip-mode kernel (RES = the layer has a residual input); with STRIP = false the
+// residual, the store mode and the activation form are run-time properties of the launch.  The strip kernel's epilogue is
+// its critical path (the strips took the main loop off it), so every flag it does not need is compiled out.
+template <int BLOCK_N, bool STRIP = false, bool RES = false>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtensorMap* tm_out, uint32_t taddr0,
                                               uint8_t* stage, int& sbuf, long long m_base, int n0, int lane, int half,
                                               uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc,
@@ -96,19 +99,19 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
     // (a 32-column tile is one chunk: there the two warps take alternate tiles instead, see the kernel)
     const int c_begin = (BLOCK_N >= 64) ? half * HALF_N : 0;
     const int c_end = c_begin + HALF_N;
-    const int mode = p.epi_mode;
-    const bool generic_act = p.act == 2;
+    const int mode = STRIP ? 0 : p.epi_mode;
+    const bool generic_act = !STRIP && p.act == 2;
     const float alpha_eff = p.act ? p.alpha : 1.0f;
     const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
     long long m_own = m_base + lane;  // the pixel row this lane holds
     bool own_ok = m_own < p.M;
-    if (p.strip) {  // m_base counts zero-padded flat positions: back to the pixel row, pad positions hold nothing
+    if (STRIP) {  // m_base counts zero-padded flat positions: back to the pixel row, pad positions hold nothing
         const int q = static_cast<int>(m_own), plane = p.strip_wp * p.strip_hp;
         const int img = q / plane, rem = q - img * plane, yp = rem / p.strip_wp, xp = rem - yp * p.strip_wp;
         own_ok = q < p.strip_total_q && yp >= 1 && yp <= p.ho && xp >= 1 && xp <= p.wo;
         m_own = own_ok ? (static_cast<long long>(img) * p.ho + (yp - 1)) * p.wo + (xp - 1) : 0;
     }
-    const bool has_res = mode == 0 && p.residual != nullptr;
+    const bool has_res = STRIP ? RES : (mode == 0 && p.residual != nullptr);
     const __nv_bfloat16* res_row = p.residual + m_own * p.res_pitch + n0;
     ptx::U32x8 rnext[2];
     // this lane's 64 bytes of the residual row for chunk c0, as two 32-byte loads: every L2 sector is requested once
@@ -194,7 +197,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
             for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
         }
         lap(2);
-        if (p.strip && !has_res) {
+        if (STRIP && !RES) {
             // The lane's rows are scattered over the image (pad positions in between), so no TMA box fits them: 64 bytes
             // per lane straight from the registers (measured faster than the staged form below when nothing else loads)
             if (own_ok) {
@@ -207,7 +210,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
             lap(3);
             return;
         }
-        if (p.strip) {
+        if (STRIP) {
             // With a residual the row-per-lane loads and stores (32 LSU wavefronts per instruction each) get in each
             // other's way: two chunks are staged as 32 rows x 128 B (128-byte swizzle), read back with 8 lanes per row, and
             // stored with every instruction covering 4 whole 128-byte lines.
@@ -318,7 +321,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
     };
 
     uint32_t acc_a[32], acc_b[32];
-    if (p.split_k > 1) {
+    if (!STRIP && p.split_k > 1) {
         // ---- split-K: this launch computed only part `part` of the tile's K range
         const int S = p.split_k;
         // partial regions: [tile][part][region = CTA rank * 4 + lane quarter][column / 4][32 lanes][4] fp32: a warp's
@@ -543,7 +546,7 @@ __device__ __forceinline__ void issue_mmas(uint32_t tmem_d, uint64_t adesc, uint
 //              [128r, 128r+128) and stages B rows [128r, 128r+128); the leader (rank 0) issues the MMAs, which
 //              read both CTAs' shared memory.  Per SM and K block this needs 16 KB of A + 16 KB of B instead of
 //              16 + 32 KB, which is what the L2->SM fill latency x shared-memory capacity product can sustain.
-template <int BLOCK_N, bool TWO, bool SWAP = false>
+template <int BLOCK_N, bool TWO, bool SWAP = false, bool STRIP = false>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmOut, const __grid_constant__ ConvParams p) {
@@ -566,7 +569,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const bool b_res = !TWO && p.b_resident != 0;
     // swapped mode: slot 0 (the MMA's M side, 128 rows) holds filter rows, slot 1 (N side, 256 rows) holds pixels
     constexpr bool swap = SWAP;
-    const bool strip = TWO && p.strip != 0;  // A comes from per-channel-block strips (see ConvParams::strip), the ring carries B only
+    static_assert(!STRIP || (TWO && BLOCK_N == 256 && !SWAP), "strip mode belongs to the CTA-pair kernel");
+    constexpr bool strip = STRIP;  // A comes from per-channel-block strips (see ConvParams::strip), the ring carries B only
     uint64_t* strip_full_bar = reinterpret_cast<uint64_t*>(smem + 640);
     uint64_t* strip_empty_bar = strip_full_bar + 2;
     const uint32_t a_bytes = strip ? 0u : BLOCK_M * p.block_k * 2;
@@ -902,8 +906,17 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
             const long long m_base = (strip ? p.strip_qfirst : 0) + static_cast<long long>(m_tile) * TILE_M + cta_rank * BLOCK_M + quarter * 32;
-            epilogue_tile<BLOCK_N>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
-                                   prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
+            if constexpr (STRIP) {
+                if (p.residual)
+                    epilogue_tile<BLOCK_N, true, true>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
+                                                       prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
+                else
+                    epilogue_tile<BLOCK_N, true, false>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
+                                                        prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
+            } else {
+                epilogue_tile<BLOCK_N>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
+                                       prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
+            }
         }
         if (lane == 0) ptx::tma_store_wait<0>();  // outstanding TMA stores read this CTA's shared memory
         if (prof && warp == 4 && lane == 0) {
@@ -940,9 +953,9 @@ void set_err(char* err, size_t n, const char* fmt, long long a = 0, long long b 
     if (err && n) snprintf(err, n, fmt, a, b, c);
 }
 
-template <int BN, bool TWO, bool SWAP = false>
+template <int BN, bool TWO, bool SWAP = false, bool STRIP = false>
 int set_smem_attr() {
-    return cudaFuncSetAttribute(conv_tc_kernel<BN, TWO, SWAP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess
+    return cudaFuncSetAttribute(conv_tc_kernel<BN, TWO, SWAP, STRIP>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess
                ? 0
                : -1;
 }
@@ -967,7 +980,8 @@ int conv_tc_init(char* err, size_t errlen) {
         cudaDriverGetVersion(&g_driver_version);
     }
     if (set_smem_attr<32, false>() || set_smem_attr<64, false>() || set_smem_attr<128, false>() ||
-        set_smem_attr<256, false>() || set_smem_attr<256, true>() || set_smem_attr<256, false, true>()) {
+        set_smem_attr<256, false>() || set_smem_attr<256, true>() || set_smem_attr<256, false, true>() ||
+        set_smem_attr<256, true, false, true>()) {
         set_err(err, errlen, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed: %lld",
                 static_cast<long long>(cudaGetLastError()));
         return -1;
@@ -1054,7 +1068,8 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     {
         static const int strip_env = getenv("FASTDET_STRIP") ? atoi(getenv("FASTDET_STRIP")) : 1;
         const int wp = d.wi + 2, hp = d.hi + 2, rows = 128 + 2 * wp + 2;
-        const bool legal = two && !quad && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
+        const bool plain_act = !d.act || (d.alpha >= 0.f && d.alpha <= 1.f);  // the strip kernel compiles the max(x, alpha x) form only
+        const bool legal = two && !quad && plain_act && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
                            !d.upsample2x && rows <= 256 && static_cast<long long>(d.n) * wp * hp < (1LL << 30);
         const bool pays = d.wi >= 20;  // (W+2)(H+2)/(WH): 1.08 at 52x52, 1.16 at 26x26 (both measured faster), 1.33 at 13x13 (not)
         if (legal && strip_env && (pays || strip_env == 2)) {
@@ -1265,7 +1280,8 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
     cfg.attrs = attr;
     cfg.numAttrs = na;
     cudaError_t e;
-    if (L.two_cta) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, L.tmA, L.tmB, L.tmOut, L.p);
+    if (L.two_cta && L.p.strip) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true, false, true>, L.tmA, L.tmB, L.tmOut, L.p);
+    else if (L.two_cta) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, true>, L.tmA, L.tmB, L.tmOut, L.p);
     else if (L.p.swap) e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<256, false, true>, L.tmA, L.tmB, L.tmOut, L.p);
     else switch (L.block_n) {
         case 32: e = cudaLaunchKernelEx(&cfg, conv_tc_kernel<32, false>, L.tmA, L.tmB, L.tmOut, L.p); break;
