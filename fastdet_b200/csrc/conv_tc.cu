@@ -88,7 +88,10 @@ __device__ __forceinline__ float2 bias_act2(uint32_t a0, uint32_t a1, float b0, 
 // STRIP / RES: compile-time copies for the strip-mode kernel (RES = the layer has a residual input); with STRIP = false the
 // residual, the store mode and the activation form are run-time properties of the launch.  The strip kernel's epilogue is
 // its critical path (the strips took the main loop off it), so every flag it does not need is compiled out.
-template <int BLOCK_N, bool STRIP = false, bool RES = false>
+// FAST: the common production path of the other kernels — bf16 output through 128-byte TMA stores, max(x, alpha x)
+// activation, whole-K tiles — with the same flags fixed at compile time (1x1 layers have K loops of 4-16 K blocks, shorter
+// than one epilogue: they run at the epilogue's speed, which is its instruction count).
+template <int BLOCK_N, bool STRIP = false, bool RES = false, bool FAST = false>
 __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtensorMap* tm_out, uint32_t taddr0,
                                               uint8_t* stage, int& sbuf, long long m_base, int n0, int lane, int half,
                                               uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc,
@@ -99,8 +102,9 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
     // (a 32-column tile is one chunk: there the two warps take alternate tiles instead, see the kernel)
     const int c_begin = (BLOCK_N >= 64) ? half * HALF_N : 0;
     const int c_end = c_begin + HALF_N;
-    const int mode = STRIP ? 0 : p.epi_mode;
-    const bool generic_act = !STRIP && p.act == 2;
+    constexpr bool FIXED = STRIP || FAST;
+    const int mode = FIXED ? 0 : p.epi_mode;
+    const bool generic_act = !FIXED && p.act == 2;
     const float alpha_eff = p.act ? p.alpha : 1.0f;
     const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
     long long m_own = m_base + lane;  // the pixel row this lane holds
@@ -111,7 +115,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
         own_ok = q < p.strip_total_q && yp >= 1 && yp <= p.ho && xp >= 1 && xp <= p.wo;
         m_own = own_ok ? (static_cast<long long>(img) * p.ho + (yp - 1)) * p.wo + (xp - 1) : 0;
     }
-    const bool has_res = STRIP ? RES : (mode == 0 && p.residual != nullptr);
+    const bool has_res = FIXED ? RES : (mode == 0 && p.residual != nullptr);
     const __nv_bfloat16* res_row = p.residual + m_own * p.res_pitch + n0;
     ptx::U32x8 rnext[2];
     // this lane's 64 bytes of the residual row for chunk c0, as two 32-byte loads: every L2 sector is requested once
@@ -241,7 +245,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
             lap(3);
             return;
         }
-        if (mode == 0 && HALF_N >= 64 && p.store64) {
+        if (mode == 0 && HALF_N >= 64 && (FAST || p.store64)) {
             // two chunks share one staging tile of 32 rows x 128 B (128-byte swizzle: 16-byte chunk k of row r at slot
             // k ^ (r & 7)) and leave through ONE TMA store: half the store requests (the TMA engine moves about one
             // row per 3 cycles whatever its width) and half the proxy fences of the 64-byte form
@@ -321,7 +325,7 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
     };
 
     uint32_t acc_a[32], acc_b[32];
-    if (!STRIP && p.split_k > 1) {
+    if (!FIXED && p.split_k > 1) {
         // ---- split-K: this launch computed only part `part` of the tile's K range
         const int S = p.split_k;
         // partial regions: [tile][part][region = CTA rank * 4 + lane quarter][column / 4][32 lanes][4] fp32: a warp's
@@ -888,6 +892,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t empty_mask = TWO ? ptx::kPeerBitMask : 0xFFFFFFFFu;
         int it = 0;
         int sbuf = 0;
+        // the production configuration takes the copy of the epilogue that has its flags compiled in
+        const bool fast_epi = !STRIP && !swap && p.epi_mode == 0 && p.store64 && p.split_k == 1 && p.act != 2 && !p.debug;
         ptx::grid_dep_wait();  // residual reads / output writes must not overtake the previous layer
         long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_start = clock64();
         for (int item = unit; item < num_items; item += units, ++it) {
@@ -913,6 +919,13 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 else
                     epilogue_tile<BLOCK_N, true, false>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
                                                         prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
+            } else if (BLOCK_N >= 128 && fast_epi) {
+                if (p.residual)
+                    epilogue_tile<BLOCK_N, false, true, true>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
+                                                              prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
+                else
+                    epilogue_tile<BLOCK_N, false, false, true>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
+                                                               prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
             } else {
                 epilogue_tile<BLOCK_N>(p, &tmOut, taddr0, stage, sbuf, m_base, n0, lane, half, full_addr, aphase, empty_addr,
                                        prof ? t_acc : nullptr, tile, part, static_cast<int>(cta_rank) * 4 + quarter);
