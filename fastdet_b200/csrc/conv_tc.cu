@@ -1085,7 +1085,10 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
         const bool legal = two && !quad && plain_act && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
                            !d.upsample2x && rows <= 256 && static_cast<long long>(d.n) * wp * hp < (1LL << 30);
         const bool pays = d.wi >= 20;  // (W+2)(H+2)/(WH): 1.08 at 52x52, 1.16 at 26x26 (both measured faster), 1.33 at 13x13 (not)
-        if (legal && strip_env && (pays || strip_env == 2)) {
+        // small batches keep the im2col form: it can split K over idle CTA pairs, the strip form cannot
+        const long long strip_tiles = (static_cast<long long>(d.n) * wp * hp - (wp + 1) + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * ((d.cout + bn - 1) / bn);
+        const bool fills = strip_tiles >= num_sms / 2;
+        if (legal && strip_env && ((pays && fills) || strip_env == 2)) {
             p.strip = 1;
             p.strip_wp = wp; p.strip_hp = hp; p.strip_rows = rows;
             p.strip_qfirst = wp + 1;
