@@ -1080,11 +1080,14 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     // positions cost less than the operand bytes saved.  FASTDET_STRIP=0 switches it off, =2 forces it wherever it is legal.
     {
         static const int strip_env = getenv("FASTDET_STRIP") ? atoi(getenv("FASTDET_STRIP")) : 1;
-        const int wp = d.wi + 2, hp = d.hi + 2, rows = 128 + 2 * wp + 2;
+        // one shared pad column between consecutive image rows and one shared pad row between consecutive images are
+        // enough (the right neighbour of a row's last pixel IS the next row's left pad): (W+1)(H+1) positions per image
+        const int wp = d.wi + 1, hp = d.hi + 1, rows = 128 + 2 * wp + 2;
         const bool plain_act = !d.act || (d.alpha >= 0.f && d.alpha <= 1.f);  // the strip kernel compiles the max(x, alpha x) form only
         const bool legal = two && !quad && plain_act && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
                            !d.upsample2x && rows <= 256 && static_cast<long long>(d.n) * wp * hp < (1LL << 30);
-        const bool pays = d.wi >= 20;  // (W+2)(H+2)/(WH): 1.08 at 52x52, 1.16 at 26x26 (both measured faster), 1.33 at 13x13 (not)
+        static const int strip_min_w = getenv("FASTDET_STRIP_MIN_W") ? atoi(getenv("FASTDET_STRIP_MIN_W")) : 12;
+        const bool pays = d.wi >= strip_min_w;  // (W+1)(H+1)/(WH) extra rows: 1.04 at 52x52, 1.08 at 26x26, 1.16 at 13x13
         // small batches keep the im2col form: it can split K over idle CTA pairs, the strip form cannot
         const long long strip_tiles = (static_cast<long long>(d.n) * wp * hp - (wp + 1) + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * ((d.cout + bn - 1) / bn);
         const bool fills = strip_tiles >= num_sms / 2;
@@ -1149,7 +1152,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
                                  static_cast<cuuint64_t>(d.in_pitch) * 2 * d.wi * d.hi};
         int lower[2] = {-d.pad_lo, -d.pad_lo};
         int upper[2] = {d.pad_hi - (k - 1), d.pad_hi - (k - 1)};
-        if (p.strip) { lower[0] = lower[1] = -1; upper[0] = upper[1] = 1; }  // traversal = the zero-padded image, W+2 x H+2
+        if (p.strip) { lower[0] = lower[1] = -1; upper[0] = upper[1] = 0; }  // traversal = the image with a pad column / row in front: W+1 x H+1
         cuuint32_t estr[4] = {1, static_cast<cuuint32_t>(d.stride), static_cast<cuuint32_t>(d.stride), 1};
         r = g_encodeIm2col(&L->tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(d.in), dims,
                            strides, lower, upper, static_cast<cuuint32_t>(block_k),

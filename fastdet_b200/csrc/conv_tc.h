@@ -73,10 +73,11 @@ struct ConvParams {
     int swap_tma;  // swapped mode: plain bf16 outputs without residual leave through TMA stores (32 ch x 32 pixels, SWIZZLE_64B)
     int head_tma;  // fp32 head rows leave through TMA stores (32 columns x 32 rows, SWIZZLE_128B)
     // "strip" mode (3x3, stride 1, pad 1 on the CTA-pair kernel): the M side walks the zero-padded, flattened pixel
-    // positions q = (n * (H+2) + y+1) * (W+2) + x+1; ONE im2col load per 64-channel block (bounding box one pixel larger
-    // than the image on every side, out-of-bounds = zeros) brings the strip of strip_rows = 128 + 2(W+2) + 2 positions a
-    // CTA's 128 rows need, and the nine taps are descriptor row offsets ky*(W+2)+kx into it: a third of the operand
-    // bytes of nine separate tap tiles.  Pad positions are computed and never stored.
+    // positions q = (n * (H+1) + y+1) * (W+1) + x+1 (one pad column in front of every image row, one pad row in front of
+    // every image: a row's right neighbour is the next row's pad); ONE im2col load per 64-channel block (bounding box one
+    // pixel larger than the image on its low sides, out-of-bounds = zeros) brings the strip of strip_rows = 128 + 2(W+1) + 2
+    // positions a CTA's 128 rows need, and the nine taps are descriptor row offsets ky*(W+1)+kx into it: a third of the
+    // operand bytes of nine separate tap tiles.  Pad positions are computed and never stored.
     int strip, strip_wp, strip_hp, strip_rows, strip_qfirst, strip_total_q;
     int store64;   // 1: the output map's box is 64 channels x 32 rows (SWIZZLE_128B), two chunks per TMA store
     int res_v8;    // 1: residual rows are 32-byte aligned -> 256-bit loads
