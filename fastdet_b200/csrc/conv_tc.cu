@@ -406,6 +406,8 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
 // a narrow Cout cannot be N).  Lane = channel: bias is a per-lane scalar; a 32-pixel column chunk is staged to shared
 // memory transposed ([pixel][32 channels] bf16) and re-read so that 4 lanes cover the 64 contiguous bytes this warp
 // owns of one pixel row.
+// PLAIN: compile-time copy for the production case (bf16 slice through TMA stores, no residual, max(x, alpha x)).
+template <bool PLAIN = false>
 __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const CUtensorMap* tm_out, int& sbuf, uint32_t taddr0,
                                                       float* stage_buf, int ch_warp, long long pix0, int lane, int half,
                                                       uint32_t full_addr, uint32_t aphase, uint32_t empty_addr, long long* t_acc) {
@@ -415,11 +417,11 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const
     const int ch_own = ch_warp + lane;                      // row-major phase: this lane's channel
     const float bias_own = (ch_own < p.cout) ? __ldg(p.bias + ch_own) : 0.f;
     const int ch = ch_warp + 8 * j;                         // transposed phase: this lane's 8 channels
-    const bool has_res = p.residual != nullptr;
-    const bool generic_act = p.act == 2;
+    const bool has_res = !PLAIN && p.residual != nullptr;
+    const bool generic_act = !PLAIN && p.act == 2;
     const float alpha_eff = p.act ? p.alpha : 1.0f;
     const float2 alpha2 = make_float2(alpha_eff, alpha_eff);
-    const bool tma_path = p.epi_mode == 0 && !has_res && p.swap_tma;  // plain bf16 slice: staged rows leave through TMA stores
+    const bool tma_path = PLAIN || (p.epi_mode == 0 && !has_res && p.swap_tma);  // plain bf16 slice: staged rows leave through TMA stores
 
     const long long ta0 = t_acc ? clock64() : 0;
     ptx::mbar_wait_addr(full_addr, aphase);
@@ -441,7 +443,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const
         uint4 res[4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-            if (tma_path) { ok[i] = false; orow[i] = 0; res[i] = make_uint4(0u, 0u, 0u, 0u); continue; }
+            if (PLAIN || tma_path) { ok[i] = false; orow[i] = 0; res[i] = make_uint4(0u, 0u, 0u, 0u); continue; }
             const long long m = pix0 + c0 + 8 * i + sub;
             ok[i] = warp_has_channels && m < p.M && ch < p.cout;
             orow[i] = m;
@@ -489,6 +491,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const
             lap(3);
             continue;
         }
+        if (PLAIN) continue;
         // channel-major phase: + bias, LeakyReLU; element (pixel q, channel lane) -> stage_buf[q][lane] (fp32: one
         // conflict-free 128-byte row per store instruction)
         if (!generic_act) {
@@ -906,8 +909,12 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_tile = tile / n_tiles_n;
             if (swap) {
                 const int ch_warp = (tile - m_tile * n_tiles_n) * BLOCK_M + quarter * 32;
-                epilogue_tile_swapped(p, &tmOut, sbuf, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256,
-                                      lane, half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
+                if (p.epi_mode == 0 && !p.residual && p.swap_tma && p.act != 2 && !p.debug)
+                    epilogue_tile_swapped<true>(p, &tmOut, sbuf, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256,
+                                                lane, half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
+                else
+                    epilogue_tile_swapped<false>(p, &tmOut, sbuf, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256,
+                                                 lane, half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
                 continue;
             }
             const int n0 = (tile - m_tile * n_tiles_n) * BLOCK_N;
