@@ -6,17 +6,20 @@
 // Stands in for the Conv/BatchNormalization/LeakyRelu/Add (and the Resize+Concat that follow a
 // branch conv) nodes ONNX Runtime executes at reference server/detector.py:135.
 //
-// CTA = 12 warps: warp 0 lane 0  TMA producer (A: 2D tiled map for 1x1, im2col map for 3x3; B: 2D tiled)
-//                 warp 1 lane 0  tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction)
-//                 warp 2         TMEM allocator
-//                 warps 4..7     epilogue group 0 (even tiles, TMEM accumulator stage 0)
-//                 warps 8..11    epilogue group 1 (odd tiles,  TMEM accumulator stage 1)   (TMEM lane quarter = warp % 4)
-// Pipelines: smem ring (full/empty mbarriers, num_stages deep) between TMA and MMA; two TMEM accumulator
-// stages (tmem_full/tmem_empty) between MMA and the epilogue groups, so two tiles' epilogues and the next
-// tile's mainloop are in flight at once (the per-tile epilogue latency, not the MMAs, bounds small-K layers).
-// Epilogue: tcgen05.ld -> bias + LeakyReLU in fp32 (lane = pixel row) -> bf16 staging tile in shared memory
-// (XOR-swizzled, conflict-free) -> re-read "transposed" so that 4 lanes cover 64 contiguous bytes of one pixel
-// row: the residual loads and the output stores are coalesced 16-byte-per-lane accesses.
+// CTA = 12 warps: warp 0  TMA producer (A: 2D tiled map for 1x1, im2col map for 3x3; B: 2D tiled)
+//                 warp 1  tcgen05.mma issuer (128 x BLOCK_N x 16 per instruction; 256 x 256 x 16 for a CTA pair)
+//                 warp 2  TMEM allocator
+//                 warps 4..11  epilogue: all eight on the same tile (TMEM lane quarter = warp % 4, the two warps of a
+//                              quarter split the tile's columns)
+// Kernel instantiations: <BLOCK_N, TWO, SWAP, STRIP> — single CTA tiles (32..256 columns), CTA pairs (cta_group::2),
+// the swapped form for 128-channel outputs, and the strip form of the pair kernel for 3x3 / stride 1 / pad 1 layers
+// (ConvParams::strip: one zero-padded flat pixel strip per channel block, the nine taps by descriptor row offsets).
+// Pipelines: smem ring (full/empty mbarriers, num_stages deep) between TMA and MMA; two TMEM accumulator stages
+// (tmem_full/tmem_empty) between MMA and epilogue, so a tile's epilogue overlaps the next tile's main loop.
+// Epilogue: tcgen05.ld (next chunk in flight) -> bias from the constant bank + max(x, alpha x) on packed fp32 pairs ->
+// (+ residual, 256-bit row loads) -> bf16 rows staged with the 128-byte swizzle -> TMA stores; fp32 head rows the same
+// way; strip mode stores rows directly (its rows are scattered over the image).  The production flag combinations have
+// compile-time copies of the epilogue (STRIP / FAST / PLAIN): short-K layers run at the epilogue's instruction count.
 #include "conv_tc.h"
 #include "ptx.cuh"
 
