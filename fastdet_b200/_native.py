@@ -48,6 +48,16 @@ class FdLayerDesc(C.Structure):
                 ("name", C.c_char * 96), ("out_name", C.c_char * 96)]
 
 
+class FdLayerExec(C.Structure):
+    _fields_ = [("kernel", C.c_int32), ("bucket", C.c_int32), ("block_n", C.c_int32), ("split_k", C.c_int32),
+                ("grid", C.c_int32), ("num_stages", C.c_int32), ("kb_per_stage", C.c_int32), ("b_resident", C.c_int32),
+                ("smem_bytes", C.c_int32), ("chunk_frames", C.c_int32), ("launches", C.c_int32), ("reserved", C.c_int32 * 5)]
+
+
+KERNEL_NAMES = {0: "conv0", 1: "tc_single", 2: "tc_pair", 3: "tc_pair_strip", 4: "tc_swapped", 5: "halo", 6: "maxpool",
+                7: "copy", 8: "block"}
+
+
 class FdJpegInfo(C.Structure):
     _fields_ = [("status", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32),
                 ("h_samp", C.c_int32), ("v_samp", C.c_int32), ("restart_interval", C.c_int32),
@@ -64,6 +74,9 @@ _PROTOS = {
     "fd_model_destroy": (None, [C.c_void_p]),
     "fd_model_info": (C.c_int, [C.c_void_p, C.POINTER(FdInfo)]),
     "fd_layer_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FdLayerDesc)]),
+    "fd_layer_exec_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FdLayerExec)]),
+    "fd_set_option": (C.c_int, [C.c_char_p, C.c_int]),
+    "fd_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "fd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fd_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "fd_postprocess": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_void_p]),
@@ -172,6 +185,17 @@ class Model:
             _check(lib().fd_layer_info(self._h, i, C.byref(d)))
             out.append({k: (getattr(d, k).decode() if isinstance(getattr(d, k), bytes) else getattr(d, k))
                         for k, _ in FdLayerDesc._fields_})
+        return out
+
+    def exec_info(self, n: int) -> List[dict]:
+        """Kernel form of every fused layer in the execution state of batch size n (built if needed)."""
+        out = []
+        d = FdLayerExec()
+        for i in range(self.info.n_layers):
+            _check(lib().fd_layer_exec_info(self._h, i, n, C.byref(d)))
+            row = {k: getattr(d, k) for k, _ in FdLayerExec._fields_ if k != "reserved"}
+            row["kernel_name"] = KERNEL_NAMES.get(d.kernel, str(d.kernel))
+            out.append(row)
         return out
 
     # -- staged pipeline (asynchronous on `stream`, a cudaStream_t as int; 0 = the model's own stream)
@@ -367,6 +391,33 @@ def jpeg_coefficients(data: bytes):
         planes.append(coefs[o:o + k].reshape(info.blocks_h[c], info.blocks_w[c], 8, 8))
         o += k
     return info, planes
+
+
+def set_option(name: str, value: int) -> None:
+    """Plan-time option (csrc/options.h); takes effect for execution state built afterwards."""
+    _check(lib().fd_set_option(name.encode(), int(value)))
+
+
+def get_option(name: str) -> int:
+    v = C.c_int()
+    _check(lib().fd_get_option(name.encode(), C.byref(v)))
+    return v.value
+
+
+class option:
+    """with option("strip", 2): ... — sets an option for the block and restores the previous value."""
+
+    def __init__(self, name, value):
+        self.name, self.value = name, value
+
+    def __enter__(self):
+        self.old = get_option(self.name)
+        set_option(self.name, self.value)
+        return self
+
+    def __exit__(self, *exc):
+        set_option(self.name, self.old)
+        return False
 
 
 def device_count() -> int:

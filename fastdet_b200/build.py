@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfastdet_b200.so")
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_halo.cu", "jpeg.cu", "pre.cu", "pool.cu", "post.cu", "plan.cc", "onnx_reader.cc"]
-HEADERS = ["conv_tc.h", "conv_halo.h", "kernels.h", "jpeg.h", "plan.h", "onnx_reader.h", "ptx.cuh", os.path.join("..", "..", "include", "fastdet_b200.h")]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_halo.cu", "jpeg.cu", "pre.cu", "pool.cu", "post.cu", "plan.cc", "onnx_reader.cc", "options.cc"]
+HEADERS = ["conv_tc.h", "conv_halo.h", "kernels.h", "jpeg.h", "plan.h", "onnx_reader.h", "options.h", "ptx.cuh", os.path.join("..", "..", "include", "fastdet_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -70,8 +70,12 @@ def build_dev_harness() -> str:
     """csrc/dev/test_conv: stand-alone conv kernel checker/timer (developer tool)."""
     out = os.path.join(os.path.dirname(HERE), "build", "test_conv")
     os.makedirs(os.path.dirname(out), exist_ok=True)
-    cmd = [nvcc(), "-O3", "-std=c++17", "-lineinfo"] + ARCH + [
-        os.path.join(CSRC, "conv_tc.cu"), os.path.join(CSRC, "conv_halo.cu"), os.path.join(CSRC, "dev", "test_conv.cu"), "-o", out]
+    srcs = [os.path.join(CSRC, "conv_tc.cu"), os.path.join(CSRC, "conv_halo.cu"), os.path.join(CSRC, "options.cc"),
+            os.path.join(CSRC, "dev", "test_conv.cu")]
+    if os.path.exists(out) and not _stale(out, srcs + [os.path.join(CSRC, h) for h in HEADERS]):
+        return out
+    # -DFASTDET_DEV: the harness build is the only one that carries the kernels' cycle counters / skip switches
+    cmd = [nvcc(), "-O3", "-std=c++17", "-lineinfo", "-DFASTDET_DEV"] + ARCH + ["-x", "cu"] + srcs + ["-o", out]
     subprocess.run(cmd, check=True)
     return out
 

@@ -21,6 +21,7 @@
 #include "jpeg.h"
 #include "kernels.h"
 #include "onnx_reader.h"
+#include "options.h"
 #include "plan.h"
 
 using namespace fd;
@@ -134,8 +135,7 @@ void* loc_ptr(const Exec& e, const TensorLoc& t, bool fp32) {
 // and tens of GB.  n <= 64 rounds up to a power of two, larger batches to a multiple of 64; the conv stack runs on the
 // bucket's frame count (frames past n hold stale pixels and are never decoded or copied out), everything else on n.
 int bucket_of(int n) {
-    static const bool exact = getenv("FASTDET_EXACT_BATCH") != nullptr;  // developer switch: one Exec per exact size
-    if (exact) return n;
+    if (options().exact_batch) return n;  // option exact_batch: one Exec per exact size
     if (n > 64) return (n + 63) / 64 * 64;
     int b = 1;
     while (b < n) b *= 2;
@@ -336,7 +336,7 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     CU(cudaMemcpy(m->d_conv0, P.conv0_w.data(), P.conv0_w.size() * 4, cudaMemcpyHostToDevice));
     // host copies are no longer needed
     std::vector<uint16_t>().swap(P.weights_bf16);
-    m->use_graph = getenv("FASTDET_NO_GRAPH") == nullptr;
+    m->use_graph = options().graph != 0;
     *out = m.release();
     return FD_OK;
 }
@@ -381,6 +381,51 @@ int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out) {
     }
     snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
     snprintf(out->out_name, sizeof(out->out_name), "%s", L.out_name.c_str());
+    return FD_OK;
+}
+
+int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
+    if (!m || !out || layer < 0 || layer >= static_cast<int>(m->plan.layers.size())) return fail(FD_ERR_ARG, "fd_layer_exec_info: bad layer %d", layer);
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    Exec* e;
+    if (int rc = get_exec(m, n, &e)) return rc;
+    const LayerPlan& L = m->plan.layers[layer];
+    memset(out, 0, sizeof(*out));
+    out->bucket = e->n;
+    out->chunk_frames = e->n;
+    out->launches = 1;
+    switch (L.kind) {
+        case LAYER_CONV0: out->kernel = FD_KERNEL_CONV0; break;
+        case LAYER_MAXPOOL: out->kernel = FD_KERNEL_MAXPOOL; break;
+        case LAYER_COPY: out->kernel = FD_KERNEL_COPY; break;
+        default:
+            if (e->use_halo[layer]) {
+                out->kernel = FD_KERNEL_HALO;
+                out->grid = e->halo[layer].grid;
+                out->smem_bytes = static_cast<int32_t>(e->halo[layer].smem_bytes);
+            } else {
+                const ConvLaunch& c = e->conv[layer];
+                out->kernel = c.p.strip ? FD_KERNEL_TC_PAIR_STRIP : c.two_cta ? FD_KERNEL_TC_PAIR : c.p.swap ? FD_KERNEL_TC_SWAPPED : FD_KERNEL_TC_SINGLE;
+                out->block_n = c.block_n; out->split_k = c.p.split_k; out->grid = c.grid; out->num_stages = c.p.num_stages;
+                out->kb_per_stage = c.p.kb_per_stage; out->b_resident = c.p.b_resident;
+                out->smem_bytes = static_cast<int32_t>(c.smem_bytes);
+            }
+    }
+    return FD_OK;
+}
+
+int fd_set_option(const char* name, int value) {
+    int* slot = option_slot(name);
+    if (!slot) return fail(FD_ERR_ARG, "fd_set_option: unknown option '%s'", name ? name : "(null)");
+    *slot = value;
+    return FD_OK;
+}
+
+int fd_get_option(const char* name, int* value) {
+    const int* slot = option_slot(name);
+    if (!slot || !value) return fail(FD_ERR_ARG, "fd_get_option: unknown option '%s'", name ? name : "(null)");
+    *value = *slot;
     return FD_OK;
 }
 
@@ -602,12 +647,9 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
                     size_t* bytes_out, int* max_blocks_out, int* src_w, int* src_h) {
     const ModelPlan& P = m->plan;
     if (!m->jpeg_pool) {
-        int t = static_cast<int>(std::thread::hardware_concurrency());
-        if (const char* env = getenv("FASTDET_JPEG_THREADS")) t = atoi(env);
+        int t = options().jpeg_threads > 0 ? options().jpeg_threads : static_cast<int>(std::thread::hardware_concurrency());
         m->jpeg_pool.reset(new JpegPool(std::max(1, std::min(t, 64))));
     }
-    const bool prof = getenv("FASTDET_JPEG_PROF") != nullptr;
-    const auto t_start = std::chrono::steady_clock::now();
     std::vector<JpegInfo>& info = m->jpeg_info;
     if (info.size() < size_t(n)) info.resize(n);
     std::vector<int32_t> local(n, 0);
@@ -661,7 +703,6 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
         S.h_stage_cap = off[n] + off[n] / 4;
     }
     char* base = S.h_stage;
-    const auto t_parsed = std::chrono::steady_clock::now();
     m->jpeg_pool->run(n, [&](int i) {
         char buf[160] = "";
         st[i] = jpeg_decode_coefficients(data[i], lens[i], info[i], reinterpret_cast<int16_t*>(base + off[i]), buf, sizeof(buf));
@@ -689,12 +730,6 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
     }
     *bytes_out = off[n];
     *max_blocks_out = max_blocks;
-    if (prof) {
-        const auto t_end = std::chrono::steady_clock::now();
-        fprintf(stderr, "[fastdet jpeg] %d frames, %d threads: parse %.3f ms, entropy decode %.3f ms, %.1f MB of coefficients\n", n,
-                m->jpeg_pool->size(), std::chrono::duration<double, std::milli>(t_parsed - t_start).count(),
-                std::chrono::duration<double, std::milli>(t_end - t_parsed).count(), off[n] / 1e6);
-    }
     return FD_OK;
 }
 
@@ -723,38 +758,19 @@ int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int ma
         m->jpeg_planes_cap = plane_stride * n;
     }
     cudaStream_t cs = m->copy_stream, s = m->stream;
-    const bool prof = getenv("FASTDET_JPEG_PROF") != nullptr;  // developer switch: serialises and times the three steps
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
-    if (prof) {
-        CU(cudaDeviceSynchronize());
-        for (cudaEvent_t& e2 : ev) CU(cudaEventCreate(&e2));
-        CU(cudaEventRecord(ev[0], cs));
-    }
     CU(cudaStreamWaitEvent(cs, S.stage_free, 0));
     CU(cudaMemcpyAsync(S.stage, S.h_stage, bytes, cudaMemcpyHostToDevice, cs));
     CU(cudaEventRecord(S.staged, cs));
     CU(cudaStreamWaitEvent(s, S.staged, 0));
-    if (prof) CU(cudaEventRecord(ev[1], s));
     const size_t head = (sizeof(JpegFrameDev) * size_t(n) + 255) / 256 * 256;
     const JpegFrameDev* fr = reinterpret_cast<const JpegFrameDev*>(S.stage);
     const int16_t* coefs = reinterpret_cast<const int16_t*>(S.stage + head);
     if (launch_jpeg_idct(coefs, fr, m->jpeg_planes, plane_stride, n, max_blocks, s))
         return fail(FD_ERR_CUDA, "JPEG kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (prof) CU(cudaEventRecord(ev[2], s));
     if (launch_jpeg_rgb(m->jpeg_planes, plane_stride, fr, rgb, n, src_h, src_w, s))
         return fail(FD_ERR_CUDA, "JPEG kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (!same && launch_letterbox_u8(rgb, e->frames, n, src_h, src_w, P.net_h, P.net_w, 128, s))
         return fail(FD_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-    if (prof) {
-        CU(cudaEventRecord(ev[3], s));
-        CU(cudaDeviceSynchronize());
-        float t01 = 0, t12 = 0, t23 = 0;
-        cudaEventElapsedTime(&t01, ev[0], ev[1]);
-        cudaEventElapsedTime(&t12, ev[1], ev[2]);
-        cudaEventElapsedTime(&t23, ev[2], ev[3]);
-        fprintf(stderr, "[fastdet jpeg] device: H2D %.3f ms (%.1f MB), idct %.3f ms, upsample+colour %.3f ms\n", t01, bytes / 1e6, t12, t23);
-        for (cudaEvent_t e2 : ev) cudaEventDestroy(e2);
-    }
     CU(cudaEventRecord(S.stage_free, s));
     return FD_OK;
 }

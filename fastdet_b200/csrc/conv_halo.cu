@@ -27,6 +27,7 @@
 #include <string.h>
 
 #include "conv_tc.h"
+#include "options.h"
 #include "ptx.cuh"
 
 namespace fd {
@@ -321,8 +322,7 @@ size_t smem_bytes(int cout) {
 }  // namespace
 
 bool conv_halo_supported(const HaloDesc& d) {
-    static const bool off = getenv("FASTDET_NO_HALO") != nullptr;
-    if (off) return false;
+    if (!options().halo) return false;
     if (!(d.cin == 64 || d.cin == 32 || d.cin == 16) || d.ksize != 3 || d.pad_lo != 1 || d.pad_hi > 1 || !(d.stride == 1 || d.stride == 2)) return false;
     if (!(d.cout == 32 || d.cout == 64 || d.cout == 128) || d.out_fp32 || d.upsample2x) return false;
     if (d.cin == 64 && d.stride != 1) return false;  // the 78 KB stride-2 patch does not fit next to the resident filters
@@ -387,7 +387,7 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
 }
 
 int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream) {
-    static const bool no_pdl = getenv("FASTDET_NO_PDL") != nullptr;
+    const bool no_pdl = !options().pdl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.grid);
     cfg.blockDim = dim3(THREADS);

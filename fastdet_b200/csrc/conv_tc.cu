@@ -21,6 +21,7 @@
 // way; strip mode stores rows directly (its rows are scattered over the image).  The production flag combinations have
 // compile-time copies of the epilogue (STRIP / FAST / PLAIN): short-K layers run at the epilogue's instruction count.
 #include "conv_tc.h"
+#include "options.h"
 #include "ptx.cuh"
 
 #include <stdio.h>
@@ -30,6 +31,14 @@
 #include <type_traits>
 
 namespace fd {
+
+// Developer instrumentation (per-role cycle counters in ConvParams::prof, the ConvParams::debug switches that skip loads /
+// MMAs / stores) exists only in builds with -DFASTDET_DEV (csrc/dev/test_conv); the library's kernels carry none of it.
+#ifdef FASTDET_DEV
+static constexpr bool kDev = true;
+#else
+static constexpr bool kDev = false;
+#endif
 
 static constexpr int BLOCK_M = 128;
 static constexpr int NUM_THREADS = 384;
@@ -393,13 +402,13 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
         if (HALF_N > 32) ptx::tmem_ld_32x32(taddr0 + c0 + 32, acc_b);  // in flight during chunk c0
         else release_tmem();
         lap(1);
-        if (!(p.debug & 1)) chunk(acc_a, c0);
+        if (!(kDev && (p.debug & 1))) chunk(acc_a, c0);
         if (HALF_N > 32) {
             ptx::tmem_ld_wait();
             if (c0 + 64 < c_end) ptx::tmem_ld_32x32(taddr0 + c0 + 64, acc_a);
             else release_tmem();
             lap(1);
-            if (!(p.debug & 1)) chunk(acc_b, c0 + 32);
+            if (!(kDev && (p.debug & 1))) chunk(acc_b, c0 + 32);
         }
     }
 }
@@ -467,7 +476,7 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const
             if (lane == 0) ptx::mbar_arrive_cluster_addr(empty_addr);
         }
         lap(1);
-        if (!warp_has_channels || (p.debug & 1)) continue;
+        if (!warp_has_channels || (kDev && (p.debug & 1))) continue;
         if (tma_path) {
             // lane = channel: element (pixel q, channel lane) goes to row q of a 32-pixel x 64-byte bf16 tile (64-byte
             // swizzle: 16-byte chunk (lane >> 3) of row q sits at slot (lane >> 3) ^ ((q >> 1) & 3)) that one TMA store
@@ -593,20 +602,15 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int num_tiles = (p.debug & 32) ? 0 : p.num_m_tiles * p.num_n_tiles;  // TWO: m tiles are 256 rows
+    const int num_tiles = (kDev && (p.debug & 32)) ? 0 : p.num_m_tiles * p.num_n_tiles;  // TWO: m tiles are 256 rows
     // work items: (tile, part) with the tile's K blocks cut into split_k parts (1 = whole tiles); every role walks
     // items unit, unit + units, ... and derives the same K-block range [kb_lo, kb_hi) for each
     const int split_k = p.split_k;
-    const bool quad = TWO && p.quad != 0;                             // clusters of two pairs (see ConvParams::quad)
-    const uint32_t cluster_rank = TWO ? ptx::cluster_ctarank() : 0u;
-    const uint32_t cta_rank = cluster_rank & 1u;                     // rank inside the pair
-    const int pair = static_cast<int>(cluster_rank >> 1);             // 0 unless quad
-    const int unit = TWO ? (blockIdx.x >> (quad ? 2 : 1)) : blockIdx.x;  // tile-stream index of this CTA / pair / quad
-    const int units = TWO ? (gridDim.x >> (quad ? 2 : 1)) : gridDim.x;
-    // quad: an item is a "super tile" = M tiles (2i, 2i+1) of one N tile, one per pair (the odd one may lie past the end of
-    // an odd M: its loads are zero-filled and its stores clipped, it only keeps the two pairs' barrier protocol symmetric)
-    const int num_items = quad ? ((p.num_m_tiles + 1) >> 1) * p.num_n_tiles : num_tiles * split_k;
-    auto tile_of = [&](int item) { return quad ? (2 * (item / p.num_n_tiles) + pair) * p.num_n_tiles + item % p.num_n_tiles : item / split_k; };
+    const uint32_t cta_rank = TWO ? ptx::cluster_ctarank() : 0u;    // rank inside the pair
+    const int unit = TWO ? (blockIdx.x >> 1) : blockIdx.x;            // tile-stream index of this CTA / pair
+    const int units = TWO ? (gridDim.x >> 1) : gridDim.x;
+    const int num_items = num_tiles * split_k;
+    auto tile_of = [&](int item) { return item / split_k; };
 
     if (warp == 0 && lane == 0) {
         ptx::tma_prefetch_desc(&tmA);
@@ -616,7 +620,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (warp == 1 && lane == 0) {
         for (int i = 0; i < STAGES; ++i) {
             ptx::mbar_init(&full_bar[i], 1);
-            ptx::mbar_init(&empty_bar[i], (TWO && p.quad) ? 2 : 1);  // quad: both pairs' MMAs read what lands in this slot
+            ptx::mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             ptx::mbar_init(&tmem_full_bar[i], 1);
@@ -650,7 +654,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_full_addr_v = ptx::smem_u32(tmem_full_bar), tmem_empty_addr_v = ptx::smem_u32(tmem_empty_bar);
     const int nkb = p.num_k_blocks, cin_blocks = p.cin_blocks, ksize = p.ksize, block_k = p.block_k;
     const int n_tiles_n = p.num_n_tiles;
-    const bool prof = p.prof != nullptr;
+    const bool prof = kDev && p.prof != nullptr;
     constexpr int TILE_M = TWO ? 2 * BLOCK_M : BLOCK_M;
     const uint32_t strip_stride = (static_cast<uint32_t>(p.strip_rows) * 128u + 1023u) & ~1023u;
     const uint32_t strips_base_v = ring_base_v + static_cast<uint32_t>(STAGES) * stage_bytes;  // two strip buffers behind the ring
@@ -663,7 +667,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const bool issuer = ptx::elect_one();
         const uint32_t ring_base = __shfl_sync(0xffffffffu, ring_base_v, 0);  // warp-uniform for the compiler (see the MMA warp)
         const uint32_t bar_base = __shfl_sync(0xffffffffu, bar_base_v, 0);
-        const bool im2col = p.a_im2col != 0, load_a = !(p.debug & 2);
+        const bool im2col = p.a_im2col != 0, load_a = !(kDev && (p.debug & 2));
         const int ho_wo = p.ho * p.wo, wo = p.wo, cstride = p.stride, pad = p.pad_lo;
         const uint32_t tx_bytes = ((load_a ? a_bytes : 0u) + (b_res ? 0u : b_bytes)) * (TWO ? 2u : 1u);
         const uint64_t mapA = reinterpret_cast<uint64_t>(&tmA), mapB = reinterpret_cast<uint64_t>(&tmB);
@@ -677,11 +681,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 ptx::tma_load_2d_addr(ptx::smem_u32(bres) + kb * b_bytes, mapB, bar, kb * block_k, 0);
         }
         ptx::grid_dep_wait();  // weights above are constants; everything below reads the previous layer's output
-        const long long t_start = clock64();
+        const long long t_start = prof ? clock64() : 0;
         int sidx = 0;  // strips loaded so far (strip mode)
         const uint32_t strips_base = __shfl_sync(0xffffffffu, strips_base_v, 0), strip_bar = __shfl_sync(0xffffffffu, strip_bar_v, 0);
-        for (int item = unit; item < num_items && !(p.debug & 8); item += units) {
-            const int tile = tile_of(item), part = quad ? 0 : item - tile * split_k;
+        for (int item = unit; item < num_items && !(kDev && (p.debug & 8)); item += units) {
+            const int tile = tile_of(item), part = item - tile * split_k;
             const int kb_lo = (part * nkb) / split_k, kb_hi = ((part + 1) * nkb) / split_k;
             const int m_tile = tile / n_tiles_n;
             if (strip) {
@@ -744,11 +748,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             else
                                 ptx::tma2_load_2d_addr(dst, mapA, lead_bar, cb * block_k, m0);
                         }
-                        if (quad)  // my 64 of the pair-half's 128 filter rows, to me and to my counterpart in the other pair
-                            ptx::tma2_load_2d_mcast_addr(dst + a_bytes + pair * (b_bytes >> 1), mapB, lead_bar, kcoord, n0 + pair * (B_ROWS >> 1),
-                                                         static_cast<uint16_t>(0x5u << cta_rank));
-                        else
-                            ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
+                        ptx::tma2_load_2d_addr(dst + a_bytes, mapB, lead_bar, kcoord, n0);
                     } else {
                         // pixels go to the slot of the side they occupy in the MMA (slot 0 = M side, slot 1 = N side)
                         const uint32_t dst_x = swap ? dst + a_bytes : dst, dst_w = swap ? dst : dst + a_bytes;
@@ -777,7 +777,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // swizzle span = one K block: 128 B (block_k 64), 64 B (32) or 32 B (16)
         const uint32_t layout = (block_k == 64) ? 2u : (block_k == 32 ? 4u : 6u);
         const uint32_t sbo = 16u * block_k;  // 8 rows x swizzle span
-        const int k_steps = (p.debug & 4) ? 0 : block_k / 16;
+        const int k_steps = (kDev && (p.debug & 4)) ? 0 : block_k / 16;
         // shared-memory / TMEM base addresses are the same in every lane, but the compiler cannot see that (they come
         // from a cvta and a shared-memory load): a broadcast shuffle marks them warp-uniform
         const uint32_t ring_base = __shfl_sync(0xffffffffu, ring_base_v, 0);
@@ -794,8 +794,8 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             ptx::mbar_wait(bres_bar, 0);
             ptx::tc_fence_after();
         }
-        long long t_full = 0, t_tmem = 0, t_start = clock64();
-        const bool skip_full_wait = (p.debug & 8) != 0;  // developer: MMA-only run (operands = whatever is in smem)
+        long long t_full = 0, t_tmem = 0, t_start = prof ? clock64() : 0;
+        const bool skip_full_wait = kDev && (p.debug & 8) != 0;  // developer: MMA-only run (operands = whatever is in smem)
         // The loop is walked by the whole warp with every address / descriptor a warp-uniform value computed OUTSIDE the
         // elected lane's branch: that keeps them in uniform registers, so a tcgen05.mma costs one UIADD3.64 per operand
         // instead of a chain of R2UR moves (the narrow layers are bound by this warp's issue rate: ~150 cycles per MMA
@@ -867,7 +867,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                         bres_off += b_units;
                     }
                     if (issuer) {  // smem slot free (in both CTAs) once these MMAs retire
-                        if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, quad ? 0xF : 3);
+                        if (TWO) ptx::umma2_commit_mcast_addr(full_addr + 8u * MAX_STAGES, 3);
                         else ptx::umma_commit_addr(full_addr + 8u * MAX_STAGES);
                     }
                     __syncwarp();
@@ -876,7 +876,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
                 // accumulator complete (each CTA of a pair drains its own 128 rows)
                 if (issuer) {
-                    if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, static_cast<uint16_t>(3u << (2 * pair)));
+                    if (TWO) ptx::umma2_commit_mcast_addr(tmem_full_addr + 8u * as, 3);
                     else ptx::umma_commit_addr(tmem_full_addr + 8u * as);
                 }
                 __syncwarp();
@@ -899,11 +899,11 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         int it = 0;
         int sbuf = 0;
         // the production configuration takes the copy of the epilogue that has its flags compiled in
-        const bool fast_epi = !STRIP && !swap && p.epi_mode == 0 && p.store64 && p.split_k == 1 && p.act != 2 && !p.debug;
+        const bool fast_epi = !STRIP && !swap && p.epi_mode == 0 && p.store64 && p.split_k == 1 && p.act != 2 && !(kDev && p.debug);
         ptx::grid_dep_wait();  // residual reads / output writes must not overtake the previous layer
-        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_start = clock64();
+        long long t_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0}, t_start = prof ? clock64() : 0;
         for (int item = unit; item < num_items; item += units, ++it) {
-            const int tile = tile_of(item), part = quad ? 0 : item - tile * split_k;
+            const int tile = tile_of(item), part = item - tile * split_k;
             const int as = it & 1;  // accumulator stage
             if (BLOCK_N < 64 && as != half) continue;  // one-chunk tiles: the two warps of a lane quarter alternate tiles
             const uint32_t aphase = (it >> 1) & 1;
@@ -912,7 +912,7 @@ conv_tc_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const int m_tile = tile / n_tiles_n;
             if (swap) {
                 const int ch_warp = (tile - m_tile * n_tiles_n) * BLOCK_M + quarter * 32;
-                if (p.epi_mode == 0 && !p.residual && p.swap_tma && p.act != 2 && !p.debug)
+                if (p.epi_mode == 0 && !p.residual && p.swap_tma && p.act != 2 && !(kDev && p.debug))
                     epilogue_tile_swapped<true>(p, &tmOut, sbuf, taddr0, reinterpret_cast<float*>(stage), ch_warp, static_cast<long long>(m_tile) * 256,
                                                 lane, half, full_addr, aphase, empty_addr, prof ? t_acc : nullptr);
                 else
@@ -1062,42 +1062,35 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     long long m_tiles = (M + BLOCK_M - 1) / BLOCK_M;
     // swapped mode for narrow layers: channels on the MMA's M side (128-row tiles), 256 pixels on its N side
     // (only where Cout fills the 128 lanes: with fewer channels most epilogue warps idle and the normal mode wins)
-    static const int swap_min = getenv("FASTDET_SWAP_MIN") ? atoi(getenv("FASTDET_SWAP_MIN")) : 64;
-    int swap = (d.cout > swap_min && d.cout <= 128 && !d.out_fp32 && M >= 256 && !getenv("FASTDET_NO_SWAP")) ? 1 : 0;
+    const Options& O = options();
+    int swap = (d.cout > 64 && d.cout <= 128 && !d.out_fp32 && M >= 256 && O.swap) ? 1 : 0;
     if (block_n_hint == 1024) { swap = 1; block_n_hint = 0; }
     else if (block_n_hint) swap = 0;
     if (swap) block_n_hint = 257;
     int two = -1;  // -1: decide below
-    int force_quad = 0;
-    if (block_n_hint == 768) { two = 1; force_quad = 1; block_n_hint = 256; }  // developer: CTA pairs in clusters of 4
     if (block_n_hint == 512) { two = 1; block_n_hint = 256; }
     if (block_n_hint == 257) { two = 0; block_n_hint = 256; }
     int bn = block_n_hint ? block_n_hint : choose_block_n(d.cout, m_tiles, num_sms);
     if (!(bn == 32 || bn == 64 || bn == 128 || bn == 256)) { set_err(err, errlen, "conv_tc: bad block_n %lld", bn); return -1; }
 
-    if (two < 0) two = (bn == 256 && block_k == 64 && m_tiles >= 2 && !getenv("FASTDET_NO_2CTA")) ? 1 : 0;
+    if (two < 0) two = (bn == 256 && block_k == 64 && m_tiles >= 2 && O.two_cta) ? 1 : 0;
     if (two && (bn != 256 || block_k != 64)) { set_err(err, errlen, "conv_tc: the CTA-pair kernel needs Cout > 128 and Cin %% 64 == 0"); return -1; }
     if (two) m_tiles = (M + 2 * BLOCK_M - 1) / (2 * BLOCK_M);
-    // clusters of two pairs sharing the filter tile.  OFF by default: measured on B200 the multicast does not raise the
-    // per-CTA operand rate (738 -> 812 cycles per K block; multicast into <= 4 CTAs behaves like unicast) and only 32
-    // clusters of 4 are co-resident (128 of 148 SMs).  FASTDET_QUAD=1 enables it for experiments.
-    static const int quad_env = getenv("FASTDET_QUAD") ? atoi(getenv("FASTDET_QUAD")) : 0;
-    const int quads_max = num_sms / 4;
-    const int quad = (two && (force_quad || (quad_env && ((m_tiles + 1) / 2) * ((d.cout + bn - 1) / bn) >= 2LL * quads_max))) ? 1 : 0;
+    // (clusters of two pairs sharing the filter tile through TMA multicast were built and measured in round 1: 812 instead
+    // of 738 cycles per K block per CTA and only 32 clusters of 4 co-resident — removed)
     if (swap) m_tiles = (M + 255) / 256;
     ConvParams& p = L->p;
     // strip mode (see ConvParams::strip): 3x3 / stride 1 / pad 1 layers of the CTA-pair kernel on maps where the pad
-    // positions cost less than the operand bytes saved.  FASTDET_STRIP=0 switches it off, =2 forces it wherever it is legal.
+    // positions cost less than the operand bytes saved.  Option strip: 0 switches it off, 2 forces it wherever it is legal.
     {
-        static const int strip_env = getenv("FASTDET_STRIP") ? atoi(getenv("FASTDET_STRIP")) : 1;
+        const int strip_env = O.strip;
         // one shared pad column between consecutive image rows and one shared pad row between consecutive images are
         // enough (the right neighbour of a row's last pixel IS the next row's left pad): (W+1)(H+1) positions per image
         const int wp = d.wi + 1, hp = d.hi + 1, rows = 128 + 2 * wp + 2;
         const bool plain_act = !d.act || (d.alpha >= 0.f && d.alpha <= 1.f);  // the strip kernel compiles the max(x, alpha x) form only
-        const bool legal = two && !quad && plain_act && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
-                           !d.upsample2x && rows <= 256 && static_cast<long long>(d.n) * wp * hp < (1LL << 30);
-        static const int strip_min_w = getenv("FASTDET_STRIP_MIN_W") ? atoi(getenv("FASTDET_STRIP_MIN_W")) : 12;
-        const bool pays = d.wi >= strip_min_w;  // (W+1)(H+1)/(WH) extra rows: 1.04 at 52x52, 1.08 at 26x26, 1.16 at 13x13
+        const bool legal = two && plain_act && k == 3 && d.stride == 1 && d.pad_lo == 1 && d.pad_hi == 1 && block_k == 64 && !d.out_fp32 &&
+                           !d.upsample2x && rows <= 400 && static_cast<long long>(d.n) * wp * hp < (1LL << 30);  // 400 rows: two strip buffers + a 5-stage B ring still fit
+        const bool pays = d.wi >= O.strip_min_w;  // (W+1)(H+1)/(WH) extra rows: 1.04 at 52x52, 1.08 at 26x26, 1.16 at 13x13
         // small batches keep the im2col form: it can split K over idle CTA pairs, the strip form cannot
         const long long strip_tiles = (static_cast<long long>(d.n) * wp * hp - (wp + 1) + 2 * BLOCK_M - 1) / (2 * BLOCK_M) * ((d.cout + bn - 1) / bn);
         const bool fills = strip_tiles >= num_sms / 2;
@@ -1178,27 +1171,25 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(K), static_cast<cuuint64_t>(d.cout)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(K) * 2};
-        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(swap ? BLOCK_M : (two ? (quad ? bn / 4 : bn / 2) : bn))};
+        cuuint32_t box[2] = {static_cast<cuuint32_t>(block_k), static_cast<cuuint32_t>(swap ? BLOCK_M : (two ? bn / 2 : bn))};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(d.w), dims,
                           strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                           CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map B encode failed (CUresult %lld)", r); return -1; }
     }
-    static const bool no_swap_tma = getenv("FASTDET_NO_SWAP_TMA") != nullptr;
-    p.swap_tma = (swap && !no_swap_tma) ? 1 : 0;
+    p.swap_tma = swap ? 1 : 0;
     if (p.epi_mode == 0 && (!swap || p.swap_tma)) {
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.cout), static_cast<cuuint64_t>(M)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_pitch) * 2};
-        static const bool no64 = getenv("FASTDET_NO_STORE64") != nullptr;
-        p.store64 = (bn >= 128 && !no64 && !swap) ? 1 : 0;  // 128-byte store rows (two 32-column chunks per TMA store)
+        p.store64 = (bn >= 128 && !swap) ? 1 : 0;  // 128-byte store rows (two 32-column chunks per TMA store)
         cuuint32_t box[2] = {p.store64 ? 64u : 32u, 32};
         cuuint32_t estr[2] = {1, 1};
         r = g_encodeTiled(&L->tmOut, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, d.out, dims, strides, box, estr,
                           CU_TENSOR_MAP_INTERLEAVE_NONE, p.store64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                           CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) { set_err(err, errlen, "conv_tc: tensor map OUT encode failed (CUresult %lld)", r); return -1; }
-    } else if (p.epi_mode == 1 && !swap && !getenv("FASTDET_NO_HEAD_TMA")) {
+    } else if (p.epi_mode == 1 && !swap) {
         // fp32 head rows [M][out_pitch]: 32 columns x 32 rows per store (128-byte rows, SWIZZLE_128B)
         cuuint64_t dims[2] = {static_cast<cuuint64_t>(d.out_pitch), static_cast<cuuint64_t>(M)};
         cuuint64_t strides[1] = {static_cast<cuuint64_t>(d.out_pitch) * 4};
@@ -1214,19 +1205,15 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     }
     L->block_n = bn;
     L->two_cta = two;
-    L->quad = quad;
-    p.quad = quad;
     L->pdl = 1;
     // split-K for launches that cannot fill the GPU with whole tiles (small batches): parts of >= 4 K blocks
     p.split_k = 1;
     {
-        static const bool no_split = getenv("FASTDET_NO_SPLITK") != nullptr;
         const long long whole = m_tiles * p.num_n_tiles;
         const long long units_max = two ? num_sms / 2 : num_sms;
         // (a split costs ~8-10 us of fences, counter traffic and partial-sum reads, so it only pays on long K loops)
-        static const int min_kb = getenv("FASTDET_SPLITK_MIN_KB") ? atoi(getenv("FASTDET_SPLITK_MIN_KB")) : 32;
-        static const int max_s = getenv("FASTDET_SPLITK_MAX") ? atoi(getenv("FASTDET_SPLITK_MAX")) : 4;
-        if (d.allow_split_k && !no_split && !swap && !quad && !p.strip && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
+        const int min_kb = O.split_k_min_kb, max_s = O.split_k_max;
+        if (d.allow_split_k && O.split_k && !swap && !p.strip && bn >= 64 && whole * 2 <= units_max && p.num_k_blocks >= min_kb) {
             long long sk = units_max / whole;
             if (sk > max_s) sk = max_s;
             if (sk > p.num_k_blocks / 4) sk = p.num_k_blocks / 4;
@@ -1236,10 +1223,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     L->ws_bytes = p.split_k > 1 ? static_cast<size_t>(m_tiles * p.num_n_tiles) * p.split_k * 8 * 32 * bn * sizeof(float) : 0;
     L->counter_ints = p.split_k > 1 ? static_cast<size_t>(m_tiles * p.num_n_tiles) * 16 : 0;
     const long long tiles = m_tiles * p.num_n_tiles * p.split_k;
-    if (quad) {
-        const long long supers = ((m_tiles + 1) / 2) * p.num_n_tiles;
-        L->grid = 4 * static_cast<int>(supers < quads_max ? supers : quads_max);
-    } else if (two) {
+    if (two) {
         const long long pairs = num_sms / 2;
         L->grid = 2 * static_cast<int>(tiles < pairs ? tiles : pairs);
     } else {
@@ -1249,7 +1233,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     // full barrier round trip (~450 cycles of wait/fence/commit in the issuing warp), so narrow layers put several
     // K blocks into one stage; then as many stages as fit (bytes in flight hide the ~1.5 us L2->SM fill latency).
     const int b_total = bn * K * 2;  // the whole filter bank of one N tile
-    const int b_res = (!two && !swap && p.num_n_tiles == 1 && b_total <= 65536 && !getenv("FASTDET_NO_BRES")) ? 1 : 0;
+    const int b_res = (!two && !swap && p.num_n_tiles == 1 && b_total <= 65536 && O.b_resident) ? 1 : 0;
     p.b_resident = b_res;
     const int sub_bytes = ((p.strip ? 0 : BLOCK_M) + (b_res ? 0 : (two ? bn / 2 : bn))) * block_k * 2;
     const int strips_bytes = p.strip ? 2 * ((p.strip_rows * 128 + 1023) / 1024 * 1024) : 0;
@@ -1266,7 +1250,6 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
         if (kps > p.num_k_blocks) kps = p.num_k_blocks;
         if (k == 3 && p.num_k_blocks % 3 == 0 && kps == 4) kps = 3;  // keep whole filter rows together
     }
-    if (getenv("FASTDET_KPS")) kps = atoi(getenv("FASTDET_KPS"));
     const int stage_bytes = sub_bytes * kps;
     int stages = (SMEM_LIMIT - 1024 - SMEM_RING_OFF - strips_bytes - (b_res ? bn * block_k * 2 * p.num_k_blocks : 0)) / stage_bytes;
     if (stages > MAX_STAGES) stages = MAX_STAGES;
@@ -1285,7 +1268,7 @@ void conv_tc_bind_workspace(ConvLaunch* L, float* ws, int* counters) {
 
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
     if (L.p.split_k > 1 && (!L.p.ws || !L.p.counters)) return -1;  // conv_tc_bind_workspace was not called
-    static const bool no_pdl = getenv("FASTDET_NO_PDL") != nullptr;
+    const bool no_pdl = !options().pdl;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(L.grid);
     cfg.blockDim = dim3(NUM_THREADS);
@@ -1295,7 +1278,7 @@ int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream) {
     int na = 0;
     if (L.two_cta) {
         attr[na].id = cudaLaunchAttributeClusterDimension;
-        attr[na].val.clusterDim.x = L.quad ? 4 : 2;
+        attr[na].val.clusterDim.x = 2;
         attr[na].val.clusterDim.y = 1;
         attr[na].val.clusterDim.z = 1;
         ++na;

@@ -63,10 +63,6 @@ struct ConvParams {
     // writes its fp32 partial region to `ws`, and the warp that arrives last on the region's counter sums the parts in
     // part order (deterministic) and finishes the tile.  Results do not depend on arrival order, but do depend on
     // split_k, i.e. on the batch size.
-    // "quad": the CTA-pair kernel launched in clusters of 4 = two pairs that work on two M tiles of the same N tile; each
-    // CTA loads only 64 of its pair's 128 filter rows per K block and multicasts them to its counterpart in the other pair
-    // (the TMA engine issues ~1 row per 3 cycles: 192 instead of 256 rows per K block per CTA)
-    int quad;
     int split_k;
     float* ws;
     int* counters;
@@ -92,7 +88,6 @@ struct ConvLaunch {
     ConvParams p;
     int block_n;
     int two_cta;  // 1: CTA-pair kernel (cta_group::2, 256 x 256 tiles)
-    int quad;     // 1: ... in clusters of two pairs sharing the filter tile (multicast)
     int grid;
     int pdl;      // 1: launched with programmatic stream serialisation (overlaps the previous kernel's drain)
     size_t smem_bytes;
@@ -102,8 +97,7 @@ struct ConvLaunch {
 };
 
 // Builds tensor maps + launch geometry.  block_n_hint: 0 = choose, else one of 32/64/128/256;
-// 512 = force the CTA-pair kernel, 768 = the CTA-pair kernel in clusters of 4, 257 = force the single-CTA 256-wide
-// kernel, 1024 = force the swapped mode.
+// 512 = force the CTA-pair kernel, 257 = force the single-CTA 256-wide kernel, 1024 = force the swapped mode.
 // Returns 0 on success; on failure writes a message to err (if non-null).
 int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch* out, char* err, size_t errlen);
 int conv_tc_launch(const ConvLaunch& L, cudaStream_t stream);

@@ -10,6 +10,7 @@
 
 #include "../conv_halo.h"
 #include "../conv_tc.h"
+#include "../options.h"
 
 using namespace fd;
 
@@ -96,10 +97,15 @@ static int run_case(const Case& c, int num_sms) {
         L.grid = H.grid;
     } else {
     d.allow_split_k = 1;
-    if (conv_tc_prepare(d, num_sms, c.block_n, &L, err, sizeof(err))) {
+    const bool want_strip = !strncmp(c.name, "strip", 5);
+    options().strip = want_strip ? 2 : 1;  // "strip ..." cases force the strip form wherever it is legal
+    const int prc = conv_tc_prepare(d, num_sms, c.block_n, &L, err, sizeof(err));
+    options().strip = 1;
+    if (prc) {
         printf("[%s] prepare failed: %s\n", c.name, err);
         return 1;
     }
+    if (want_strip && !L.p.strip) printf("[%s] note: the strip form is not legal for this shape, im2col form checked\n", c.name);
     if (L.ws_bytes) {
         float* ws; int* cnt;
         CK(cudaMalloc(&ws, L.ws_bytes)); CK(cudaMalloc(&cnt, L.counter_ints * 4)); CK(cudaMemset(cnt, 0, L.counter_ints * 4));
@@ -173,7 +179,7 @@ static int run_case(const Case& c, int num_sms) {
         if (memcmp(h2.data(), hout.data(), out_bytes)) { printf("[%s] split-K relaunch differs\n", c.name); ++bad; }
     }
     printf("[%-28s] M=%lld N=%d K=%d bn=%d%s%s%s grid=%d  max_err=%.4g (max|ref|=%.3g) bad=%lld clobbered=%lld %s\n",
-           c.name, M, c.cout, K, L.block_n, L.two_cta ? (L.quad ? "x4" : "x2") : "", L.p.swap ? "swap" : "", L.p.split_k > 1 ? " splitK" : "", L.grid, max_err, max_ref, bad, clobbered,
+           c.name, M, c.cout, K, L.block_n, L.two_cta ? (L.p.strip ? "x2 strip" : "x2") : "", L.p.swap ? "swap" : "", L.p.split_k > 1 ? " splitK" : "", L.grid, max_err, max_ref, bad, clobbered,
            (bad == 0 && clobbered == 0) ? "OK" : "FAIL");
     if (bad) printf("    first bad at m=%lld n=%d\n", first_bad_m, first_bad_n);
     cudaFree(dx); cudaFree(dw); cudaFree(dbias); cudaFree(dout);
@@ -206,6 +212,7 @@ static void time_case(const char* name, int n, int h, int cin, int cout, int k, 
     __nv_bfloat16* dres = nullptr;
     if (residual) { CK(cudaMalloc(&dres, out_e * 2)); CK(cudaMemset(dres, 0x3C, out_e * 2)); d.residual = dres; d.res_pitch = cout; }
     d.allow_split_k = getenv("FD_SPLITK") != nullptr;
+    if (getenv("FD_STRIP")) options().strip = atoi(getenv("FD_STRIP"));  // harness only: 0 / 1 / 2
     if (conv_tc_prepare(d, num_sms, block_n, &L, err, sizeof(err))) { printf("[%s] prepare failed: %s\n", name, err); return; }
     if (L.ws_bytes) {
         float* ws; int* cnt;
@@ -296,11 +303,12 @@ int main(int argc, char** argv) {
             {"strip 3x3 64->256 w61",   1, 7, 61, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
             {"strip 3x3 64->256 w62",   1, 7, 62, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
             {"1cta 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 257},
-            {"quad 3x3 128->512",       2, 13, 13, 128, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 768},
-            {"quad 3x3 64->256 odd M",  4, 13, 13, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 768},
-            {"quad 1x1 512->256 many",  8, 26, 26, 512, 256, 1, 1, 0, 0, 1, 1, 0, 0, 0, 768},
-            {"quad 1x1 256->255 fp32",  2, 13, 13, 256, 255, 1, 1, 0, 0, 0, 0, 1, 0, 0, 768},
-            {"quad 3x3 128->256 big",   16, 52, 52, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 768},
+            // maps wider than 61 need strips of more than 256 positions (YOLOv3-608: 76x76), and the 608 grids 38 / 19
+            {"strip 3x3 64->256 w76",   2, 9, 76, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"strip 3x3 128->256 76sq", 2, 76, 76, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"strip 3x3 64->512 38sq",  3, 38, 38, 64, 512, 3, 1, 1, 1, 1, 0, 0, 0, 0, 512},
+            {"strip 3x3 64->256 19sq",  5, 19, 19, 64, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
+            {"strip 3x3 128->256 13sq", 9, 13, 13, 128, 256, 3, 1, 1, 1, 1, 1, 0, 0, 0, 512},
             {"3x3 16->32 s1 (bk16)",    2, 20, 20, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 0},
             {"halo 3x3 32->64 s1 res",  2, 72, 76, 32, 64, 3, 1, 1, 1, 1, 1, 0, 0, 0, 2048},
             {"halo 3x3 32->64 s2",      2, 130, 134, 32, 64, 3, 2, 1, 1, 1, 0, 0, 0, 0, 2048},
@@ -357,7 +365,7 @@ int main(int argc, char** argv) {
             time_case("3x3 256->512 s2 @52 bs64", 64, 52, 256, 512, 3, 2, sms, bn);
         }
     }
-    if (!strcmp(mode, "strip")) {  // run with FASTDET_STRIP=0 / 1 / 2 to compare
+    if (!strcmp(mode, "strip")) {  // run with FD_STRIP=0 / 1 / 2 to compare
         time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 512);
         time_case("3x3 128->256 @52 bs64 res", 64, 52, 128, 256, 3, 1, sms, 512, 0, 1);
         time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, 512);
@@ -371,14 +379,6 @@ int main(int argc, char** argv) {
         for (int g : {148, 74, 37}) time_case("3x3 32->64 s1 @208 bs64", 64, 208, 32, 64, 3, 1, sms, 0, 7, 0, g);
         for (int g : {148, 74, 37}) time_case("3x3 64->128 @104 bs64", 64, 104, 64, 128, 3, 1, sms, 0, 0, 0, g);
         for (int g : {148, 74, 37}) time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, 0, 0, 0, g);
-    }
-    if (!strcmp(mode, "quad")) {
-        for (int bn : {512, 768}) {
-            time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, bn);
-            time_case("3x3 256->512 @26 bs64", 64, 26, 256, 512, 3, 1, sms, bn);
-            time_case("1x1 512->256 @26 bs64", 64, 26, 512, 256, 1, 1, sms, bn);
-        }
-        for (int g : {148, 128, 112, 96, 64}) time_case("3x3 128->256 @52 bs64", 64, 52, 128, 256, 3, 1, sms, 768, 0, 0, g);
     }
     if (!strcmp(mode, "small")) {
         time_case("3x3 128->256 @52 bs1", 1, 52, 128, 256, 3, 1, sms, 0);

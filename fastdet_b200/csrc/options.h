@@ -1,0 +1,34 @@
+// options.h — plan-time options of the library (process-wide, read when execution state for a batch size is built).
+//
+// They replace the getenv() switches of the first round: a test or tool sets one through the C ABI
+// (fd_set_option / fd_get_option, include/fastdet_b200.h), builds a model, and asserts the kernel form each layer took
+// through fd_layer_exec_info.  The defaults are the production configuration; nothing reads the environment.
+#pragma once
+
+namespace fd {
+
+struct Options {
+    int strip = 1;            // 3x3 s1 p1 layers of the CTA-pair kernel: 0 im2col form only, 1 strips where they pay and fill the GPU, 2 wherever legal
+    int strip_min_w = 12;     // strips only on maps at least this wide (pad positions cost (W+1)(H+1)/(WH))
+    int swap = 1;             // swapped (channels on the MMA's M side) form for 65..128 output channels
+    int two_cta = 1;          // CTA-pair (cta_group::2) kernel for Cout > 128, Cin % 64 == 0
+    int split_k = 1;          // split long K loops when a launch cannot fill the GPU (small batches)
+    int split_k_min_kb = 32;  // ... only with at least this many K blocks
+    int split_k_max = 4;      // ... into at most this many parts
+    int b_resident = 1;       // keep a narrow layer's whole filter bank in shared memory
+    int halo = 1;             // halo-patch kernel for 16/32/64-channel 3x3 layers on large maps
+    int pdl = 1;              // programmatic dependent launch between layers
+    int graph = 1;            // replay the forward pass as a captured CUDA graph
+    int exact_batch = 0;      // one execution state per exact batch size instead of per bucket
+    int nms_general = 0;      // force the general (global-memory) Soft-NMS loop
+    int jpeg_threads = 0;     // host threads of the JPEG entropy decoder; 0 = all hardware threads (max 64)
+    int fuse_block = 1;       // residual blocks on large maps (1x1 C->C/2, 3x3 C/2->C, + input) as one kernel
+    int chunk_frames = 0;     // early layers run in chunks of this many frames so a chunk's activations stay in L2; 0 = auto
+    int detect_overlap = 1;   // synchronous fd_detect copies the frames in two halves so the second overlaps conv0
+};
+
+Options& options();
+// name -> field; returns nullptr for unknown names
+int* option_slot(const char* name);
+
+}  // namespace fd

@@ -17,6 +17,7 @@
 #include <stdlib.h>
 
 #include "kernels.h"
+#include "options.h"
 
 namespace fd {
 
@@ -301,7 +302,7 @@ soft_nms_kernel(const Candidate* __restrict__ cand_all, const int* __restrict__ 
 int launch_soft_nms(Candidate* cand, const int* cand_count, double* score_scratch, int boxes_per_frame, int n,
                     int net_w, int net_h, double threshold, Detection* out, int* out_count, int* total_count,
                     int max_det, cudaStream_t s) {
-    static const int allow_fast = getenv("FASTDET_NMS_GENERAL") == nullptr;  // developer switch: force the general loop
+    const int allow_fast = options().nms_general ? 0 : 1;  // option nms_general: force the general loop (tests run both)
     soft_nms_kernel<<<n, NMS_THREADS, 0, s>>>(cand, cand_count, score_scratch, boxes_per_frame, net_w, net_h, threshold,
                                               out, out_count, total_count, max_det, allow_fast);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;

@@ -497,11 +497,10 @@ int kernels_init() {
 
 int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __nv_bfloat16* out, int n, int h,
                     int wd, int cout, int out_pitch, int act, float alpha, cudaStream_t s) {
-    static const bool cuda_cores = getenv("FASTDET_CONV0_FMA") != nullptr;  // developer: the CUDA-core kernel for every shape
     const int act_mode = act ? ((alpha >= 0.f && alpha <= 1.f) ? 1 : 2) : 0;
     const long long tiles = 1LL * n * ((wd + C0D_TW - 1) / C0D_TW) * ((h + C0D_TH - 1) / C0D_TH);
     const int tx = (wd + C0D_TW - 1) / C0D_TW, per_frame = tx * ((h + C0D_TH - 1) / C0D_TH);
-    if (!cuda_cores && (cout == 16 || cout == 32) && out_pitch == cout && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
+    if ((cout == 16 || cout == 32) && out_pitch == cout && (reinterpret_cast<uintptr_t>(out) & 15) == 0 &&
         tiles < (1LL << 24) && per_frame < 65536) {  // (ranges of the multiply-shift division)
         // dense NHWC output: an image row is one run of W*C elements; TMA store box = 8 pixels x 4 rows
         CUtensorMap tm;
@@ -510,8 +509,7 @@ int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __
         const unsigned long long strides[2] = {2ULL * cout * wd, 2ULL * cout * wd * h};
         const unsigned box[3] = {static_cast<unsigned>(cout) * C0D_TW, 4, 1};
         if (encode_tiled_bf16(&tm, out, 3, dims, strides, box, 0)) return -1;
-        static const int per_sm = getenv("FASTDET_C0_CTAS") ? atoi(getenv("FASTDET_C0_CTAS")) : 1;
-        const int blocks = static_cast<int>(tiles < 148LL * per_sm ? tiles : 148LL * per_sm);
+        const int blocks = static_cast<int>(tiles < 148LL ? tiles : 148LL);
         const unsigned long long one40 = 1ULL << 40;
         conv0_ws_kernel<<<blocks, C0W_THREADS, C0W_PATCHES * C0D_PATCH_BYTES, s>>>(frames, w, bias, tm, n, h, wd, cout, act_mode, alpha,
                                                                                   (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx);

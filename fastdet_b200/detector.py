@@ -116,27 +116,57 @@ class ONNXDetector(Detector):
             return 'host'
         return 'device' if (info.width, info.height) == tuple(self.image_size) else 'size'
 
-    def perform_jpegs(self, datas, threshold=0.1, allow_resize=False, source_coords=False):
+    def perform_jpegs(self, datas, threshold=0.1, allow_resize=False, source_coords=False, return_exceptions=False):
         """perform() for a batch of encoded payloads: one result list per payload.  Baseline JPEGs are decoded by the
         library (Huffman on its host thread pool, IDCT / upsampling / colour on the device: fd_detect_jpeg), bit-identical
-        to PIL; if the library refuses any payload of the batch, the batch is decoded the reference's way instead.
+        to PIL.  Payloads the library refuses (its per-frame status says which) go, one by one, through the reference's own
+        decode lines and raise what the reference raises; the others still run as one batch, so one bad payload neither
+        slows nor fails its neighbours.  An exception is raised for the first failing payload, or — with
+        return_exceptions=True — stands in that payload's place in the returned list.
         allow_resize / source_coords (extension): as in perform_frames, for payloads of one common size other than the
         network's."""
         self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
         datas = list(datas)
-        try:
-            dets, counts = self.model.detect_jpeg(datas, threshold, max_det=self.max_det, allow_resize=allow_resize)
-            self.jpeg_device_frames += len(datas)
-            if allow_resize and source_coords and datas:
-                info = _native.jpeg_probe(bytes(datas[0]))
+        results = [None] * len(datas)
+        todo = list(range(len(datas)))
+        for _ in range(3):  # a refusal names its offenders; parse problems surface before entropy-decode problems
+            if not todo:
+                break
+            batch = [datas[i] for i in todo]
+            try:
+                dets, counts = self.model.detect_jpeg(batch, threshold, max_det=self.max_det, allow_resize=allow_resize)
+            except _native.JpegRefused as e:
+                bad = [i for i, st in zip(todo, e.status) if int(st) != _native.FD_JPEG_OK] or list(todo)
+                for i in bad:
+                    results[i] = self._perform_host_one(datas[i], threshold, allow_resize, source_coords)
+                todo = [i for i in todo if i not in set(bad)]
+                continue
+            self.jpeg_device_frames += len(batch)
+            if allow_resize and source_coords and batch:
+                info = _native.jpeg_probe(bytes(batch[0]))
                 if (info.width, info.height) != tuple(self.image_size):
                     for f in range(dets.shape[0]):
                         dets[f, :counts[f]] = _native.unmap_letterbox(dets[f, :counts[f]], (info.width, info.height), self.image_size)
-            return self._tuples(dets, counts)
-        except _native.JpegRefused:
-            frames = np.stack([self._decode_host(d, check_size=not allow_resize) for d in datas])
-            self.jpeg_host_frames += len(datas)
-            return self.perform_frames(frames, threshold=threshold, allow_resize=allow_resize, source_coords=source_coords)
+            for i, r in zip(todo, self._tuples(dets, counts)):
+                results[i] = r
+            todo = []
+        for i in todo:  # (not reached in practice: three refusals in a row)
+            results[i] = self._perform_host_one(datas[i], threshold, allow_resize, source_coords)
+        if not return_exceptions:
+            for r in results:
+                if isinstance(r, BaseException):
+                    raise r
+        return results
+
+    def _perform_host_one(self, data, threshold, allow_resize=False, source_coords=False):
+        """One payload through the reference's decode lines; returns its result list, or the exception the reference's
+        perform() would have raised for it."""
+        try:
+            frame = self._decode_host(data, check_size=not allow_resize)
+            self.jpeg_host_frames += 1
+            return self.perform_frames(frame[None], threshold=threshold, allow_resize=allow_resize, source_coords=source_coords)[0]
+        except Exception as e:  # noqa: BLE001 — delivered to the owner of this payload only
+            return e
 
     # -- extras --------------------------------------------------------------------------------
     def perform_frames(self, frames, threshold=0.1, allow_resize=False, source_coords=False):
@@ -162,15 +192,19 @@ class ONNXDetector(Detector):
         return [dets[f, :counts[f]][cls._RESULT_FIELDS].tolist() for f in range(dets.shape[0])]
 
     # -- two batches in flight (fd_submit / fd_submit_jpeg + fd_collect): what BatchingService drives
-    def submit_jpegs(self, slot, datas, threshold=0.1):
+    def submit_jpegs(self, slot, datas, threshold=0.1, strict=False):
         """Starts a batch of encoded payloads in ring slot `slot` and returns; collect(slot) yields the result lists.
-        The entropy decode happens in this call (library's host threads) while the device works on the other slot."""
+        The entropy decode happens in this call (library's host threads) while the device works on the other slot.
+        strict=True: a refusal (JpegRefused, with the per-frame status) is raised instead of decoding the whole batch the
+        reference's way — nothing was launched and the slot is free; BatchingService uses it to isolate the offenders."""
         self.ANCHORS[self.model.n_heads]
         datas = list(datas)
         try:
             self.model.submit_jpeg(slot, datas, threshold, max_det=self.max_det)
             self.jpeg_device_frames += len(datas)
         except _native.JpegRefused:
+            if strict:
+                raise
             frames = np.stack([self._decode_host(d) for d in datas])
             self.jpeg_host_frames += len(datas)
             self.model.submit(slot, frames, threshold, max_det=self.max_det)

@@ -5,8 +5,11 @@ The reference serves every UDP payload with one blocking ``detector.perform(data
 signature — ``perform(data, threshold) -> [(klass, conf, x, y, w, h), ...]``, same exceptions — but lets many threads
 (one per session / stream) call it at once: requests that arrive within ``max_delay`` seconds are decoded in their
 caller's thread, stacked, and run as ONE batch through the detector (pipelined ``perform_stream`` when several batches
-are waiting), and every caller gets exactly the list ``detector.perform`` would have returned for its frame.
+are waiting), and every caller gets exactly the list ``detector.perform`` would have returned for its frame — or the
+exception it would have raised: a payload the batch path cannot take (damaged entropy data behind a valid header, say) is
+taken out of its batch, answered on its own, and the rest of the batch runs as a batch.
 """
+import inspect
 import io
 import threading
 import time
@@ -42,6 +45,11 @@ class BatchingService:
         self._queue = deque()
         self._cond = threading.Condition()
         self._closed = False
+        self.isolated = 0  # requests answered on their own after their batch was refused or failed
+        sj = getattr(detector, "submit_jpegs", None)
+        self._strict = sj is not None and "strict" in inspect.signature(sj).parameters
+        pj = getattr(detector, "perform_jpegs", None)
+        self._ret_exc = pj is not None and "return_exceptions" in inspect.signature(pj).parameters
         self._worker = threading.Thread(target=self._run, name="fastdet-batcher", daemon=True)
         self._worker.start()
 
@@ -116,14 +124,14 @@ class BatchingService:
             r.event.set()
 
     def _run(self):
-        pipelined = all(hasattr(self.detector, a) for a in ("submit_jpegs", "submit_frames", "collect"))
-        pending = deque()  # (slot, requests) in submission order; at most two: the library's two ring slots
-        free = [0, 1]
+        self._pipelined = all(hasattr(self.detector, a) for a in ("submit_jpegs", "submit_frames", "collect"))
+        self._pending = deque()  # (slot, requests) in submission order; at most two: the library's two ring slots
+        self._free = [0, 1]
         while True:
             # with work in flight do not wait for new requests: whatever has arrived is taken, else the oldest batch is
             # collected and delivered
-            batch = self._take(block=not pending)
-            if batch is None and not pending:
+            batch = self._take(block=not self._pending)
+            if batch is None and not self._pending:
                 if self._closed:
                     return
                 continue
@@ -131,38 +139,77 @@ class BatchingService:
                 self.batches_run += 1
                 self.frames_run += len(batch)
                 for part in ([r for r in batch if isinstance(r.frame, bytes)], [r for r in batch if not isinstance(r.frame, bytes)]):
-                    if not part:
-                        continue
-                    encoded = isinstance(part[0].frame, bytes)
-                    try:
-                        if pipelined:
-                            if not free:
-                                slot, old = pending.popleft()
-                                free.append(slot)
-                                self._deliver(slot, old)
-                            slot = free.pop(0)
-                            try:
-                                if encoded:
-                                    self.detector.submit_jpegs(slot, [r.frame for r in part], part[0].threshold)
-                                else:
-                                    self.detector.submit_frames(slot, np.stack([r.frame for r in part]), part[0].threshold)
-                            except Exception:
-                                free.insert(0, slot)
-                                raise
-                            pending.append((slot, part))
-                        elif encoded:
-                            self._finish(part, self.detector.perform_jpegs([r.frame for r in part], threshold=part[0].threshold))
-                        else:
-                            self._finish(part, self.detector.perform_frames(np.stack([r.frame for r in part]), threshold=part[0].threshold))
-                    except Exception as e:  # every caller of the part sees the failure, the worker lives on
-                        self._finish(part, error=e)
+                    if part:
+                        self._run_part(part)
             else:
-                slot, old = pending.popleft()
-                free.append(slot)
+                slot, old = self._pending.popleft()
+                self._free.append(slot)
                 self._deliver(slot, old)
+
+    def _run_part(self, part):
+        """One homogeneous group of requests (all encoded payloads, or all decoded frames) as one batch."""
+        encoded = isinstance(part[0].frame, bytes)
+        thr = part[0].threshold
+        try:
+            if self._pipelined:
+                if not self._free:
+                    slot, old = self._pending.popleft()
+                    self._free.append(slot)
+                    self._deliver(slot, old)
+                slot = self._free.pop(0)
+                try:
+                    if encoded and self._strict:
+                        self.detector.submit_jpegs(slot, [r.frame for r in part], thr, strict=True)
+                    elif encoded:
+                        self.detector.submit_jpegs(slot, [r.frame for r in part], thr)
+                    else:
+                        self.detector.submit_frames(slot, np.stack([r.frame for r in part]), thr)
+                except Exception:
+                    self._free.insert(0, slot)
+                    raise
+                self._pending.append((slot, part))
+            elif encoded and self._ret_exc:
+                res = self.detector.perform_jpegs([r.frame for r in part], threshold=thr, return_exceptions=True)
+                for r, out in zip(part, res):
+                    if isinstance(out, BaseException):
+                        self.isolated += 1
+                        self._finish([r], error=out)
+                    else:
+                        self._finish([r], [out])
+            elif encoded:
+                self._finish(part, self.detector.perform_jpegs([r.frame for r in part], threshold=thr))
+            else:
+                self._finish(part, self.detector.perform_frames(np.stack([r.frame for r in part]), threshold=thr))
+        except Exception as e:  # noqa: BLE001
+            self._isolate(part, e)
+
+    def _isolate(self, part, err):
+        """A batch was refused or failed before anything ran: answer the offenders on their own — each gets its own result
+        or its own exception — and run the others as a batch again.  The refusal's per-frame status (JpegRefused.status)
+        names the offenders; without one every request of the part is answered on its own."""
+        if len(part) == 1:
+            self._finish(part, error=err)
+            return
+        status = getattr(err, "status", None)
+        good, bad = [], list(part)
+        if status is not None and len(status) == len(part) and any(int(st) != 0 for st in status):
+            good = [r for r, st in zip(part, status) if int(st) == 0]
+            bad = [r for r, st in zip(part, status) if int(st) != 0]
+        for r in bad:
+            self.isolated += 1
+            try:
+                if isinstance(r.frame, bytes):
+                    out = self.detector.perform_jpegs([r.frame], threshold=r.threshold)[0]
+                else:
+                    out = self.detector.perform_frames(r.frame[None], threshold=r.threshold)[0]
+                self._finish([r], [out])
+            except Exception as e:  # noqa: BLE001 — this caller's own failure
+                self._finish([r], error=e)
+        if good:
+            self._run_part(good)
 
     def _deliver(self, slot, part):
         try:
             self._finish(part, self.detector.collect(slot))
-        except Exception as e:
+        except Exception as e:  # noqa: BLE001 — a device-side failure of a batch that did run: nobody to single out
             self._finish(part, error=e)

@@ -47,7 +47,7 @@ extern "C" {
 
 #define FD_MAX_HEADS 4
 #define FD_MAX_SLOTS 2 /* batches in flight through fd_submit / fd_collect */
-#define FD_ABI_VERSION 3
+#define FD_ABI_VERSION 4
 
 typedef struct fd_model fd_model;
 
@@ -85,8 +85,33 @@ typedef struct fd_layer_desc {
     char out_name[96];              /* ONNX tensor name the output corresponds to */
 } fd_layer_desc;
 
+/* How one fused layer executes at a given batch size (the kernel form is chosen per batch-size bucket when the
+ * execution state is built): lets tests assert that the configuration they check is the one that is timed. */
+#define FD_KERNEL_CONV0 0         /* conv0_ws_kernel: normalise + first conv (pre.cu) */
+#define FD_KERNEL_TC_SINGLE 1     /* conv_tc_kernel, one CTA per 128 x block_n tile */
+#define FD_KERNEL_TC_PAIR 2       /* conv_tc_kernel, CTA pair (cta_group::2), 256 x 256 tiles, im2col / tiled A */
+#define FD_KERNEL_TC_PAIR_STRIP 3 /* conv_tc_kernel, CTA pair, strip form (3x3 s1 p1) */
+#define FD_KERNEL_TC_SWAPPED 4    /* conv_tc_kernel, channels on the MMA's M side (Cout 65..128) */
+#define FD_KERNEL_HALO 5          /* conv_halo_kernel (narrow 3x3 on large maps) */
+#define FD_KERNEL_MAXPOOL 6
+#define FD_KERNEL_COPY 7
+#define FD_KERNEL_BLOCK 8         /* conv_block_kernel: 1x1 reduce + 3x3 expand + residual of a Darknet block in one launch */
+typedef struct fd_layer_exec {
+    int32_t kernel;       /* FD_KERNEL_* */
+    int32_t bucket;       /* batch-size bucket whose execution state answered (n rounded up) */
+    int32_t block_n, split_k, grid, num_stages, kb_per_stage, b_resident;
+    int32_t smem_bytes;
+    int32_t chunk_frames; /* frames per launch of this layer (< bucket: the layer belongs to an L2-resident chunked segment) */
+    int32_t launches;     /* launches of this layer per forward pass */
+    int32_t reserved[5];
+} fd_layer_exec;
+
 const char* fd_last_error(void);
 int fd_abi_version(void);
+/* Plan-time options (process-wide; read when a model's execution state for a batch size is first built, so set them
+ * before the first call at that size).  Names and defaults: csrc/options.h.  Unknown names return FD_ERR_ARG. */
+int fd_set_option(const char* name, int value);
+int fd_get_option(const char* name, int* value);
 /* Number of CUDA devices visible; 0 when there is no driver/GPU (never fails). */
 int fd_device_count(void);
 
@@ -96,6 +121,8 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
 void fd_model_destroy(fd_model* m);
 int fd_model_info(const fd_model* m, fd_info* out);
 int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out);
+/* Builds (if needed) the execution state for batch size n and reports the kernel form of `layer` in it. */
+int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out);
 
 /* Stage `n` RGB u8 HWC frames for the next fd_forward.  src_w x src_h must equal the network size unless
  * allow_resize != 0, in which case the frames are letterboxed on the device (extension).  on_device: frames

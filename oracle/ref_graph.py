@@ -1,4 +1,4 @@
-"""oracle/ref_graph.py — CPU fp32/fp64 executor for the ONNX operator subset of the YOLOv3 graphs.
+"""oracle/ref_graph.py — CPU fp32/fp64 (and bf16-operand) executor for the ONNX operator subset of the YOLOv3 graphs.
 
 TEST INFRASTRUCTURE ONLY: imported by tests/, __graft_entry__.smoke() and bench.py's CPU-baseline
 legs, never by the product path.
@@ -15,6 +15,15 @@ Operators (ONNX opset 9-13 forms): Conv, BatchNormalization (inference), LeakyRe
 Resize / Upsample (nearest, asymmetric, floor), Concat, Pad (constant), Constant, Identity and the integer
 shape-arithmetic ops torch's exporter emits around Resize/Pad (Shape, Gather, Cast, Slice, Unsqueeze,
 Squeeze, Floor, Div, Sub, ConstantOfShape, Reshape, Transpose).
+
+``dtype="bf16"`` evaluates the arithmetic BASELINE.json's north_star prescribes for the new implementation —
+bf16 operands, fp32 accumulation — on the CPU: BatchNormalization is folded into the preceding Conv in fp32
+(w' = w * gamma / sqrt(var + eps), b' = beta + (b - mean) * gamma / sqrt(var + eps)), the folded weights and every
+convolution input are rounded to bf16 (round-to-nearest-even), products are summed in fp32, and every stored
+activation (the value after LeakyRelu, and after a residual Add) is rounded to bf16; graph outputs stay fp32.
+It separates the two sources of difference from the fp32 oracle: what the prescribed operand precision costs
+(bf16 oracle vs fp32 oracle, a CPU-only comparison: tests/test_oracle_graph.py::test_bf16_operand_floor) and what
+the CUDA kernels add on top (GPU vs bf16 oracle: fp32 summation order only).
 """
 from __future__ import annotations
 
@@ -27,6 +36,11 @@ import torch.nn.functional as F
 from . import onnx_min
 
 
+def _bf16(t: torch.Tensor) -> torch.Tensor:
+    """Round-to-nearest-even to bf16, kept in fp32 storage."""
+    return t.to(torch.bfloat16).to(torch.float32)
+
+
 def _t(x, dtype=None):
     if isinstance(x, torch.Tensor):
         return x
@@ -36,10 +50,14 @@ def _t(x, dtype=None):
 
 
 class GraphExecutor:
-    """Runs a parsed graph on torch-CPU.  ``dtype`` = torch.float32 (what ORT computes in) or float64."""
+    """Runs a parsed graph on torch-CPU.  ``dtype`` = torch.float32 (what ORT computes in), float64, or "bf16"
+    (bf16 operands / fp32 accumulation, see the module docstring)."""
 
     def __init__(self, onnx_bytes: bytes, dtype=torch.float32):
         self.graph = onnx_min.load(onnx_bytes)
+        self.bf16 = dtype == "bf16"
+        if self.bf16:
+            dtype = torch.float32
         self.dtype = dtype
         self.consts: Dict[str, torch.Tensor] = {}
         for k, v in self.graph.initializers.items():
@@ -50,6 +68,49 @@ class GraphExecutor:
         if "input" not in self.graph.inputs:
             # reference server/detector.py:135 feeds {'input': a}; any other name makes ORT raise
             raise KeyError(f"graph has no input named 'input' (inputs: {self.graph.inputs})")
+        self.folded: Dict[str, tuple] = {}   # Conv output name -> (bf16-rounded folded weight, fp32 bias)
+        self.bn_identity = set()             # BatchNormalization nodes folded into their producer
+        self.round_after = set()             # node outputs that are stored activations (rounded to bf16)
+        if self.bf16:
+            self._prepare_bf16()
+
+    def _prepare_bf16(self):
+        g = self.graph
+        consumers: Dict[str, list] = {}
+        for n in g.nodes:
+            for i in n.inputs:
+                consumers.setdefault(i, []).append(n)
+        outputs = set(g.outputs)
+
+        def sole(name):
+            c = consumers.get(name, [])
+            return c[0] if len(c) == 1 and name not in outputs else None
+
+        for n in g.nodes:
+            if n.op == "Conv":
+                w = self.consts[n.inputs[1]].to(torch.float32)
+                b = self.consts[n.inputs[2]].to(torch.float32) if len(n.inputs) > 2 and n.inputs[2] else torch.zeros(w.shape[0])
+                last = n
+                nx = sole(n.outputs[0])
+                if nx is not None and nx.op == "BatchNormalization" and nx.inputs[0] == n.outputs[0]:
+                    sc, bb, mean, var = (self.consts[k].to(torch.float32) for k in nx.inputs[1:5])
+                    eps = torch.tensor(nx.attrs.get("epsilon", 1e-5), dtype=torch.float32)
+                    inv = sc / torch.sqrt(var + eps)
+                    w = w * inv.view(-1, 1, 1, 1)
+                    b = bb + (b - mean) * inv
+                    self.bn_identity.add(id(nx))
+                    last = nx
+                self.folded[n.outputs[0]] = (_bf16(w), b)
+                nx = sole(last.outputs[0])
+                if nx is not None and nx.op in ("LeakyRelu", "Relu"):
+                    last = nx
+                # the value after the activation is what the conv kernel's epilogue rounds and stores; a graph output
+                # (head tensor) is written in fp32
+                if last.outputs[0] not in outputs:
+                    self.round_after.add(last.outputs[0])
+            elif n.op == "Add":
+                if n.inputs[0] not in self.consts and n.inputs[1] not in self.consts and n.outputs[0] not in outputs:
+                    self.round_after.add(n.outputs[0])  # residual add: bf16 + bf16, rounded once
 
     # -- single-op semantics -------------------------------------------------
     def _conv(self, n, x, w, b=None):
@@ -147,8 +208,13 @@ class GraphExecutor:
             for n in self.graph.nodes:
                 ins = [vals.get(i) if i else None for i in n.inputs]
                 op = n.op
-                if op == "Conv":
+                if op == "Conv" and self.bf16:
+                    w16, bias = self.folded[n.outputs[0]]
+                    out = self._conv(n, _bf16(ins[0]), w16, bias)
+                elif op == "Conv":
                     out = self._conv(n, *ins)
+                elif op == "BatchNormalization" and id(n) in self.bn_identity:
+                    out = ins[0]
                 elif op == "BatchNormalization":
                     xx, sc, bb, mean, var = ins
                     eps = n.attrs.get("epsilon", 1e-5)
@@ -237,6 +303,8 @@ class GraphExecutor:
                     out = ins[0].permute(n.attrs["perm"])
                 else:
                     raise NotImplementedError(f"oracle: ONNX op {op}")
+                if n.outputs[0] in self.round_after:
+                    out = _bf16(out)
                 vals[n.outputs[0]] = out
         if all_values or keep is not None:
             names = keep if keep is not None else [k for k in vals if k and k not in self.consts]

@@ -281,14 +281,14 @@ def _class_gap(heads, box, nc):
     raise IndexError(box)
 
 
-def _kept_after_nudge(heads, nc, thr, box, delta):
+def _kept_after_nudge(heads, nc, thr, box, delta, size=416):
     """Oracle Soft-NMS re-run with candidate `box`'s score moved by `delta`: its decayed score if it is selected,
     else None.  Soft-NMS is order-sensitive: two overlapping boxes whose scores are closer than the bf16 noise swap
     roles (the one picked first suppresses the other), which is the 'near-threshold tie' the spec allows."""
     cands, first = [], 0
     for anchors, out in zip(ref_post.ANCHORS[len(heads)], heads):
         m = np.ascontiguousarray(out[0].transpose(1, 2, 0))
-        cands.extend(ref_post.decode_head_fast(anchors, m, nc, (416, 416), thr - abs(delta), first))
+        cands.extend(ref_post.decode_head_fast(anchors, m, nc, (size, size), thr - abs(delta), first))
         first += m.shape[0] * m.shape[1] * 3
     cands = [(c[0], c[1], c[2] + (delta if c[0] == box else 0.0)) + tuple(c[3:]) for c in cands]
     cands = [c for c in cands if c[2] >= thr or c[0] == box]
@@ -298,22 +298,80 @@ def _kept_after_nudge(heads, nc, thr, box, delta):
     return None
 
 
+class DetectionTally:
+    """Compares one frame's GPU detections with the oracle's on the oracle's own head tensors and accumulates the
+    IoU / |dconf| statistics.  Rules (BASELINE.json north_star): every reference detection whose score and
+    Soft-NMS-decayed score clear the threshold by `margin` must be found at the SAME anchor box with the same class
+    (unless its two best class logits are a near-tie); anything else that differs must be a near-threshold case on the
+    reference side (the oracle's own decision flips under a score nudge of the margin)."""
+
+    def __init__(self, nc, thr=0.1, margin=2e-2, size=416):
+        self.nc, self.thr, self.margin, self.size = nc, thr, margin, size
+        self.ious, self.dconfs = [], []
+        self.n_solid = self.n_soft = 0
+
+    def add(self, heads, dets):
+        """heads: oracle head tensors of ONE frame ([1, C, H, W] each); dets: that frame's fd_det records."""
+        nc, thr, margin = self.nc, self.thr, self.margin
+        gpu = {int(d["box"]): d for d in dets}
+        left = {}
+        want, want_idx, decayed = ref_post.detect_from_heads(heads, 0, nc, (self.size, self.size), thr, leftovers=left)
+        ref = dict(zip(want_idx, zip(want, decayed)))
+        for box, (w, dec) in ref.items():
+            solid = min(w[1], dec) >= thr + margin
+            g = gpu.get(box)
+            if g is None:
+                # lost on the GPU: allowed when the reference's own decision flips under a score nudge of the margin
+                nudged = _kept_after_nudge(heads, nc, thr, box, -margin, self.size) if solid else None
+                assert not solid or nudged is None or nudged < thr + margin, ("reference detection lost", w, dec, nudged)
+                self.n_soft += 1
+                continue
+            if int(g["klass"]) != w[0]:
+                assert _class_gap(heads, box, nc) < 0.1, ("class differs without a near-tie", w, g)
+                self.n_soft += 1
+                continue
+            self.n_solid += solid
+            self.ious.append(iou((g["x"], g["y"], g["w"], g["h"]), w[2:]))
+            self.dconfs.append(abs(float(g["conf"]) - w[1]))
+        for box, g in gpu.items():
+            if box in ref:
+                continue
+            # not kept by the reference: either it never cleared the threshold there, or Soft-NMS decayed it away
+            final = left.get(box)
+            ok = float(g["conf"]) <= thr + margin or (final is not None and final >= thr - margin)
+            if not ok:  # Soft-NMS order flip between near-equal overlapping boxes?
+                nudged = _kept_after_nudge(heads, nc, thr, box, margin, self.size)
+                ok = nudged is not None and nudged >= thr - margin
+            assert ok, ("spurious detection", dict(zip(g.dtype.names, g.tolist())), final)
+            self.n_soft += 1
+
+    def check(self, label, min_solid=5, iou_min=0.95, iou_median=0.98, dconf_max=2e-2, dconf_frac=0.9):
+        ious, dconfs = np.array(self.ious), np.array(self.dconfs)
+        assert self.n_solid >= min_solid, self.n_solid
+        print(f"{label}: {len(ious)} matched ({self.n_solid} solid), {self.n_soft} near-threshold/tie cases, IoU min {ious.min():.4f} "
+              f"median {np.median(ious):.4f}, >=0.99: {np.mean(ious >= 0.99):.2f}, max dconf {dconfs.max():.4f}, "
+              f"<=1e-2: {np.mean(dconfs <= 1e-2):.2f}")
+        assert ious.min() >= iou_min and np.median(ious) >= iou_median, (ious.min(), np.median(ious))
+        assert dconfs.max() <= dconf_max and np.mean(dconfs <= 1e-2) >= dconf_frac, (dconfs.max(), np.mean(dconfs <= 1e-2))
+
+
 @pytest.mark.parametrize("arch,nc,seed", [("tiny", 80, 1), ("rsu", 9, 3), ("full", 80, 2)])
 def test_detections_match_oracle(arch, nc, seed):
     """ONNXDetector.perform (PNG bytes in, tuples out) against the oracle's restatement of the reference's perform
-    on the same frames and the same .onnx.  bf16 operands leave ~0.6 % RMS noise on the head logits of these
-    random-init nets (a CPU emulation of bf16 rounding shows the same), so: every reference detection whose
-    score and Soft-NMS-decayed score clear the threshold by 2e-2 must be found at the SAME anchor box with the
-    same class (unless its two best class logits are a near-tie), |dconf| <= 2e-2 (>= 90 % within the 1e-2 the
-    spec asks), IoU >= 0.95 (median >= 0.98; 0.99 for every box is out of bf16's reach here); anything else that
-    differs must be a near-threshold case on the reference side."""
+    on the same frames and the same .onnx.  Two comparisons:
+      * against the bf16-operand oracle (oracle/ref_graph.py, dtype="bf16": the arithmetic the north_star prescribes —
+        bf16 operands, fp32 accumulation — evaluated on the CPU): the spec's bounds, IoU >= 0.99 and |dconf| <= 1e-2;
+      * against the fp32 oracle: bf16 operands leave ~0.6 % RMS noise on the head logits of these random-init nets, and
+        tests/test_oracle_graph.py::test_bf16_operand_floor shows on the CPU alone that this noise already takes the
+        fp32-vs-bf16 IoU of some boxes below 0.99, so here the bounds are the measured floor (IoU >= 0.95, median
+        >= 0.98, |dconf| <= 2e-2 with >= 90 % within 1e-2)."""
     from PIL import Image
-    thr, margin = 0.1, 2e-2
+    thr = 0.1
     data = modelgen.build_onnx(arch, nc, 416, seed)
     det = fdet.ONNXDetector(data, num_classes=nc)
     exe = ref_graph.GraphExecutor(data)
-    ious, dconfs = [], []
-    n_solid = n_soft = 0
+    exe16 = ref_graph.GraphExecutor(data, dtype="bf16")
+    t32, t16 = DetectionTally(nc, thr), DetectionTally(nc, thr)
     for s in range(3):
         frame = modelgen.synthetic_frame(200 + s, 416)
         buf = io.BytesIO()
@@ -322,44 +380,11 @@ def test_detections_match_oracle(arch, nc, seed):
         assert all(isinstance(g[0], int) and 1 <= g[0] <= nc and isinstance(g[1], float) for g in got)
         dets, counts = det.model.detect(frame[None], thr)  # same call, structured (carries the box index)
         assert counts[0] == len(got)
-        gpu = {int(d["box"]): d for d in dets[0, :counts[0]]}
-        heads = exe.run(ref_post.normalise(frame))
-        left = {}
-        want, want_idx, decayed = ref_post.detect_from_heads(heads, 0, nc, (416, 416), thr, leftovers=left)
-        ref = dict(zip(want_idx, zip(want, decayed)))
-        for box, (w, dec) in ref.items():
-            solid = min(w[1], dec) >= thr + margin
-            g = gpu.get(box)
-            if g is None:
-                # lost on the GPU: allowed when the reference's own decision flips under a score nudge of the margin
-                nudged = _kept_after_nudge(heads, nc, thr, box, -margin) if solid else None
-                assert not solid or nudged is None or nudged < thr + margin, ("reference detection lost", w, dec, nudged)
-                n_soft += 1
-                continue
-            if int(g["klass"]) != w[0]:
-                assert _class_gap(heads, box, nc) < 0.1, ("class differs without a near-tie", w, g)
-                n_soft += 1
-                continue
-            n_solid += solid
-            ious.append(iou((g["x"], g["y"], g["w"], g["h"]), w[2:]))
-            dconfs.append(abs(float(g["conf"]) - w[1]))
-        for box, g in gpu.items():
-            if box in ref:
-                continue
-            # not kept by the reference: either it never cleared the threshold there, or Soft-NMS decayed it away
-            final = left.get(box)
-            ok = float(g["conf"]) <= thr + margin or (final is not None and final >= thr - margin)
-            if not ok:  # Soft-NMS order flip between near-equal overlapping boxes?
-                nudged = _kept_after_nudge(heads, nc, thr, box, margin)
-                ok = nudged is not None and nudged >= thr - margin
-            assert ok, ("spurious detection", dict(zip(g.dtype.names, g.tolist())), final)
-            n_soft += 1
-    assert n_solid >= 5
-    ious, dconfs = np.array(ious), np.array(dconfs)
-    assert ious.min() >= 0.95 and np.median(ious) >= 0.98, (ious.min(), np.median(ious))
-    assert dconfs.max() <= 2e-2 and np.mean(dconfs <= 1e-2) >= 0.9, (dconfs.max(), np.mean(dconfs <= 1e-2))
-    print(f"{arch}: {len(ious)} matched ({n_solid} solid), {n_soft} near-threshold/tie cases, IoU min {ious.min():.4f} "
-          f"median {np.median(ious):.4f}, >=0.99: {np.mean(ious >= 0.99):.2f}, max dconf {dconfs.max():.4f}")
+        x = ref_post.normalise(frame)
+        t32.add(exe.run(x), dets[0, :counts[0]])
+        t16.add(exe16.run(x), dets[0, :counts[0]])
+    t32.check(f"{arch} vs fp32 oracle")
+    t16.check(f"{arch} vs bf16-operand oracle", iou_min=0.99, iou_median=0.995, dconf_max=1e-2, dconf_frac=1.0)
 
 
 def test_detector_interface_errors():

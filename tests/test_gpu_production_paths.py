@@ -1,0 +1,135 @@
+"""GPU parity tests of the kernel forms the BENCHMARKED configurations run (-m gpu).
+
+The library picks a kernel form per layer and per batch-size bucket (fd_layer_exec_info): small batches take the
+im2col / split-K forms, the batch-64 serving configuration takes the strip form of the CTA-pair kernel for every 3x3
+stride-1 layer with >= 64-channel inputs (29 of YOLOv3's 75 convolutions, about half of the step's device time) and, in
+the first stages, the fused residual-block kernel.  These tests put exactly those forms under the CPU oracle:
+  * the strip form forced at a small batch (option strip=2), per layer, for the 416 and the 608 grids
+    (strip widths W+1 = 53 / 27 / 14 and 77 / 39 / 20);
+  * the default plan at batch 8 per layer (52x52 strips by the library's own choice);
+  * the production batch 64 (rsu-416-9, BASELINE config 3): heads and detections of 8 of the 64 frames;
+  * full-608 at a batch whose 76x76 layers take strips by default (BASELINE config 4's per-GPU shard, reduced);
+  * the stand-alone kernel checker (csrc/dev/test_conv.cu: every kernel form against a float64 CPU loop).
+Every test first asserts, through fd_layer_exec_info, that the layers really took the form it means to check.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from fastdet_b200 import _native, modelgen
+from oracle import ref_graph, ref_post
+from tests.test_gpu_parity import DetectionTally, _check_heads, frames_for
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def strip_candidates(m):
+    """Layers the strip form is built for: 3x3, stride 1, Cin % 64 == 0, Cout > 128, bf16 output."""
+    return [i for i, L in enumerate(m.layers())
+            if L["kind"] == 1 and L["ksize"] == 3 and L["stride"] == 1 and L["cin"] % 64 == 0 and L["c"] > 128 and not L["out_fp32"]]
+
+
+def forms(m, n):
+    return [e["kernel_name"] for e in m.exec_info(n)]
+
+
+@pytest.mark.parametrize("size,batch", [(416, 2), (608, 1)])
+def test_strip_form_forced_small_batch_per_layer(size, batch):
+    data = modelgen.build_onnx("full", 80, size, seed=2)
+    with _native.option("strip", 2), _native.option("fuse_block", 0):
+        m = _native.Model(data, 80, (size, size), device=0)
+        f = forms(m, batch)
+        cands = strip_candidates(m)
+        assert len(cands) == 29
+        assert all(f[i] == "tc_pair_strip" for i in cands), [(i, f[i]) for i in cands if f[i] != "tc_pair_strip"]
+        _check_heads(data, m, frames_for(batch, size, first_seed=140), per_layer=True)
+    m.close()
+
+
+def test_default_plan_batch8_per_layer():
+    """Batch 8, default options: the library itself puts the 52x52 3x3 layers on strips (88 strip tiles >= 74 CTA pairs)
+    and the first residual blocks on the fused block kernel; every layer's output against the oracle."""
+    data = modelgen.build_onnx("full", 80, 416, seed=2)
+    m = _native.Model(data, 80, (416, 416), device=0)
+    f = forms(m, 8)
+    L = m.layers()
+    strips52 = [i for i in strip_candidates(m) if L[i]["h"] == 52]
+    assert len(strips52) == 14 and all(f[i] == "tc_pair_strip" for i in strips52)
+    _check_heads(data, m, frames_for(8, 416, first_seed=150), per_layer=True)
+    m.close()
+
+
+def test_production_batch64_against_oracle():
+    """BASELINE config 3 (rsu-416-9, batch 64) — the configuration bench.py times: all 29 strip layers in strip form by
+    the library's own choice; heads of 8 of the 64 frames against the fp32 oracle (2e-2 * max|ref|) and their
+    detections against the fp32 and the bf16-operand oracle (see test_detections_match_oracle)."""
+    nc = 9
+    data = modelgen.build_onnx("rsu", nc, 416, seed=3)
+    m = _native.Model(data, nc, (416, 416), device=0)
+    f = forms(m, 64)
+    cands = strip_candidates(m)
+    assert len(cands) == 29 and all(f[i] == "tc_pair_strip" for i in cands), [(i, f[i]) for i in cands]
+    frames = frames_for(64, 416, first_seed=100)  # 64 distinct frames, seeds 100..163
+    m.preprocess(frames, 64, (416, 416))
+    m.forward(64)
+    heads = m.heads(64)
+    m.postprocess(64, 0.1, max_det=512)
+    dets, counts, total = m.fetch(64)
+    assert (total == counts).all()
+    exe, exe16 = ref_graph.GraphExecutor(data), ref_graph.GraphExecutor(data, dtype="bf16")
+    t32, t16 = DetectionTally(nc), DetectionTally(nc)
+    picks = [0, 7, 13, 21, 30, 42, 55, 63]
+    for fidx in picks:
+        x = ref_post.normalise(frames[fidx])
+        want = exe.run(x)
+        for g, r in zip(heads, want):
+            err = np.abs(g[fidx] - r[0]).max()
+            assert err <= 2e-2 * np.abs(r).max(), (fidx, err, np.abs(r).max())
+        t32.add(want, dets[fidx, :counts[fidx]])
+        t16.add(exe16.run(x), dets[fidx, :counts[fidx]])
+    t32.check("rsu bs64 vs fp32 oracle")
+    t16.check("rsu bs64 vs bf16-operand oracle", iou_min=0.99, iou_median=0.995, dconf_max=1e-2, dconf_frac=1.0)
+    m.close()
+
+
+def test_full_608_batch_with_strips_against_oracle():
+    """full-608-80 (BASELINE config 4) at batch 4: the fourteen 76x76 3x3 layers (27 % of the FLOPs) take strips of
+    128 + 2*77 + 2 = 284 positions by the library's own choice; heads of every frame against the oracle."""
+    data = modelgen.build_onnx("full", 80, 608, seed=2)
+    m = _native.Model(data, 80, (608, 608), device=0)
+    f = forms(m, 4)
+    L = m.layers()
+    s76 = [i for i in strip_candidates(m) if L[i]["h"] == 76]
+    assert len(s76) == 14 and all(f[i] == "tc_pair_strip" for i in s76), [(i, f[i]) for i in s76]
+    _check_heads(data, m, frames_for(4, 608, first_seed=1000))
+    m.close()
+
+
+def test_nms_general_path_equals_register_path():
+    """Option nms_general forces the global-memory Soft-NMS loop: same records as the one-candidate-per-thread path."""
+    data = modelgen.build_onnx("tiny", 80, 416, seed=1)
+    m = _native.Model(data, 80, (416, 416), device=0)
+    frames = frames_for(3, 416, first_seed=210)
+    a, ca = m.detect(frames, 0.1, max_det=256)
+    with _native.option("nms_general", 1):
+        b, cb = m.detect(frames, 0.1, max_det=256)
+    assert np.array_equal(ca, cb) and ca.sum() > 0
+    for i in range(3):
+        assert np.array_equal(a[i, :ca[i]], b[i, :cb[i]])
+    m.close()
+
+
+def test_kernel_checker_all_forms():
+    """csrc/dev/test_conv: every conv kernel form (single CTA, CTA pair, swapped, split-K, strips incl. the 608 widths,
+    halo-patch, fused block) against a float64 CPU loop on small shapes."""
+    exe = os.path.join(ROOT, "build", "test_conv")
+    if not os.path.exists(exe):
+        from fastdet_b200 import build
+        exe = build.build_dev_harness()
+    r = subprocess.run([exe, "check"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    tail = "\n".join(r.stdout.splitlines()[-60:])
+    assert r.returncode == 0 and "check: 0 failing case(s)" in r.stdout, tail
+    assert "x2 strip" in r.stdout  # the strip cases really took the strip form

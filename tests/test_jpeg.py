@@ -419,3 +419,54 @@ def test_refused_batches_launch_nothing_and_detector_takes_the_reference_route()
     assert type(ei.value).__name__ == 'UnidentifiedImageError'
     outs = list(det.perform_stream([[good, good], [good]], threshold=0.05))
     assert outs == [[want, want], [want]]
+
+
+@pytest.mark.gpu
+def test_bad_payload_in_a_batch_is_isolated_on_device():
+    """One entropy-damaged JPEG (valid header, so it is queued for the device path) and one progressive JPEG among good
+    ones: perform_jpegs(return_exceptions=True) and BatchingService answer every good payload exactly as perform() does and
+    hand the damaged one's exception (what PIL raises for it) to its own caller only."""
+    from fastdet_b200 import detector as fdet
+    onnx, m = gpu_model()
+    det = fdet.ONNXDetector(onnx, num_classes=80, image_size=(416, 416), max_det=256)
+    good = [encode(modelgen.synthetic_frame(410 + i, 416), quality=80) for i in range(5)]
+    prog = encode(modelgen.synthetic_frame(420, 416), quality=80, progressive=True)
+    # cut the entropy data short: the header still parses, libjpeg/PIL raise on the truncated stream
+    broken = good[0][:len(good[0]) // 3]
+    try:
+        np.array(Image.open(io.BytesIO(broken)))
+        pil_raises = None
+    except Exception as e:  # noqa: BLE001
+        pil_raises = type(e)
+    assert pil_raises is not None and _native.jpeg_probe(broken).status == _native.FD_JPEG_OK
+    want = {d: det.perform(d, threshold=0.05) for d in good + [prog]}
+    batch = [good[0], good[1], broken, good[2], prog, good[3], good[4]]
+    res = det.perform_jpegs(batch, threshold=0.05, return_exceptions=True)
+    for d, r in zip(batch, res):
+        if d is broken:
+            assert isinstance(r, pil_raises)
+        else:
+            assert r == want[d]
+    with pytest.raises(pil_raises):
+        det.perform_jpegs(batch, threshold=0.05)
+    svc = BatchingService(det, max_batch=8, max_delay=0.2)
+    out = {}
+
+    def call(i):
+        try:
+            out[i] = svc.perform(batch[i], threshold=0.05)
+        except Exception as e:  # noqa: BLE001
+            out[i] = e
+
+    threads = [threading.Thread(target=call, args=(i,)) for i in range(len(batch))]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    svc.close()
+    for i, d in enumerate(batch):
+        if d is broken:
+            assert isinstance(out[i], pil_raises)
+        else:
+            assert out[i] == want[d], i
+    assert svc.isolated >= 1

@@ -24,7 +24,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in the header but not exported"
     assert declared == set(_native._PROTOS), "ctypes prototypes and header disagree"
-    assert lib.fd_abi_version() == 3
+    assert lib.fd_abi_version() == 4
     assert ctypes.sizeof(_native.FdDet) == 48
 
 

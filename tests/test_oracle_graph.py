@@ -63,3 +63,66 @@ def test_missing_input_name_is_rejected():
     data = modelgen.build_onnx("tiny", 3, 64, seed=1).replace(b"\x0a\x05input", b"\x0a\x05inpux")
     with pytest.raises(KeyError):
         ref_graph.GraphExecutor(data)
+
+
+def _iou(a, b):
+    iw = min(a[0] + a[2], b[0] + b[2]) - max(a[0], b[0])
+    ih = min(a[1] + a[3], b[1] + b[3]) - max(a[1], b[1])
+    if iw <= 0 or ih <= 0:
+        return 0.0
+    return iw * ih / (a[2] * a[3] + b[2] * b[3] - iw * ih)
+
+
+def test_bf16_operand_mode_follows_the_planner():
+    """dtype="bf16": BatchNormalization folded before the rounding (both exporter forms give the same heads bit for bit
+    only if the fold is the planner's), stored activations are bf16 values, heads stay fp32."""
+    x = (modelgen.synthetic_frame(3, 96)[None] / 255).astype(np.float32).transpose(0, 3, 1, 2)
+    folded = modelgen.build_onnx("tiny", 3, 96, seed=5)
+    exe = ref_graph.GraphExecutor(folded, dtype="bf16")
+    vals = exe.run(x, all_values=True)
+    acts = [v for k, v in vals.items() if k in exe.round_after]
+    assert len(acts) >= 11
+    for v in acts:
+        assert np.array_equal(v, torch.from_numpy(v).to(torch.bfloat16).to(torch.float32).numpy())
+    heads = exe.run(x)
+    assert any(not np.array_equal(h, torch.from_numpy(h).to(torch.bfloat16).to(torch.float32).numpy()) for h in heads)
+    ref = ref_graph.GraphExecutor(folded).run(x)
+    for a, b in zip(heads, ref):
+        assert 0 < np.abs(a - b).max() <= 2e-2 * np.abs(b).max()
+    # the unfolded export (BatchNormalization nodes present) folds to the same operands up to the exporter's own fp32
+    # fold of the folded form: heads agree far inside one bf16 step of the activations
+    alt = modelgen.ExportOptions(fold_bn=False)
+    heads_bn = ref_graph.GraphExecutor(modelgen.build_onnx("tiny", 3, 96, seed=5, opts=alt), dtype="bf16").run(x)
+    for a, b in zip(heads, heads_bn):
+        assert np.abs(a - b).max() <= 1e-2 * np.abs(b).max()
+
+
+def test_bf16_operand_floor():
+    """What BASELINE.json's prescribed arithmetic (bf16 operands, fp32 accumulation) costs against the fp32 oracle, with
+    no GPU involved: raw heads stay inside the spec's 2e-2 * max|ref|, scores inside 1e-2, but the box IoU of matched
+    detections does NOT stay above 0.99 — exp(tw), exp(th) amplify the ~1 % logit noise of these random-init nets.  The
+    GPU tests therefore hold the CUDA path to IoU >= 0.99 / |dconf| <= 1e-2 against the bf16-operand oracle and to the
+    floor measured here against the fp32 oracle (tests/test_gpu_parity.py::test_detections_match_oracle)."""
+    from oracle import ref_post
+    ious, dconfs, herr = [], [], []
+    for arch, nc, seed, frames in (("tiny", 80, 1, 3), ("rsu", 9, 3, 2)):
+        data = modelgen.build_onnx(arch, nc, 416, seed)
+        e32, e16 = ref_graph.GraphExecutor(data), ref_graph.GraphExecutor(data, dtype="bf16")
+        for s in range(frames):
+            x = ref_post.normalise(modelgen.synthetic_frame(200 + s, 416))
+            h32, h16 = e32.run(x), e16.run(x)
+            herr.append(max(float(np.abs(a - b).max() / np.abs(a).max()) for a, b in zip(h32, h16)))
+            w32, i32, _ = ref_post.detect_from_heads(h32, 0, nc, (416, 416), 0.1)
+            w16, i16, _ = ref_post.detect_from_heads(h16, 0, nc, (416, 416), 0.1)
+            d16 = dict(zip(i16, w16))
+            for box, w in zip(i32, w32):
+                if box in d16 and d16[box][0] == w[0]:
+                    ious.append(_iou(w[2:], d16[box][2:]))
+                    dconfs.append(abs(w[1] - d16[box][1]))
+    ious, dconfs = np.array(ious), np.array(dconfs)
+    print(f"bf16-operand oracle vs fp32 oracle: head err max {max(herr):.4f}; {len(ious)} matched boxes, IoU min {ious.min():.4f} "
+          f"median {np.median(ious):.4f} >=0.99: {np.mean(ious >= 0.99):.2f}; |dconf| max {dconfs.max():.4f}")
+    assert max(herr) <= 2e-2
+    assert len(ious) >= 60 and dconfs.max() <= 1e-2
+    assert ious.min() >= 0.95 and np.median(ious) >= 0.98
+    assert np.mean(ious >= 0.99) < 0.9  # the floor: bf16 operands alone miss the 0.99 bound on a good share of the boxes

@@ -97,6 +97,78 @@ def test_batching_service_groups_concurrent_callers():
         svc.perform(_png(1))
 
 
+class _RefusingDetector:
+    """Pipelined stand-in whose submit refuses batches that contain a 'bad' payload, naming it in a per-frame status
+    like fastdet_b200._native.JpegRefused does; on its own the bad payload raises OSError (what PIL raises)."""
+    image_size = (8, 8)
+
+    class Refused(RuntimeError):
+        def __init__(self, status):
+            super().__init__("refused")
+            self.status = status
+
+    def __init__(self):
+        self.slots, self.submitted, self.single = {}, [], []
+
+    def jpeg_probe(self, data):
+        return 'device'
+
+    def _answer(self, d):
+        return [(1, 0.5, float(len(d)), 0.0, 1.0, 1.0)]
+
+    def perform_jpegs(self, datas, threshold=0.1):
+        self.single.append(len(datas))
+        for d in datas:
+            if d.startswith(b"bad"):
+                raise OSError("cannot identify image file")
+        return [self._answer(d) for d in datas]
+
+    def perform_frames(self, frames, threshold=0.1):
+        raise AssertionError("not used")
+
+    def submit_jpegs(self, slot, datas, threshold=0.1, strict=False):
+        assert strict and slot not in self.slots
+        status = [2 if d.startswith(b"bad") else 0 for d in datas]
+        if any(status):
+            raise self.Refused(status)
+        self.submitted.append(len(datas))
+        self.slots[slot] = [self._answer(d) for d in datas]
+
+    def submit_frames(self, slot, frames, threshold=0.1):
+        raise AssertionError("not used")
+
+    def collect(self, slot):
+        return self.slots.pop(slot)
+
+
+def test_one_bad_payload_fails_only_its_own_caller():
+    """a damaged payload queued with 15 good ones must not fail (or serialise) the others: the refusal's
+    per-frame status singles it out, its caller alone gets the reference's exception, the rest runs as ONE batch."""
+    det = _RefusingDetector()
+    svc = service.BatchingService(det, max_batch=16, max_delay=0.3)
+    out, errs = {}, {}
+
+    def call(i):
+        data = (b"bad" if i == 5 else b"ok") + bytes(i)
+        try:
+            out[i] = svc.perform(data)
+        except Exception as e:  # noqa: BLE001
+            errs[i] = e
+
+    threads = [threading.Thread(target=call, args=(i,)) for i in range(16)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    svc.close()
+    assert list(errs) == [5] and isinstance(errs[5], OSError)
+    assert sorted(out) == [i for i in range(16) if i != 5]
+    for i, res in out.items():
+        assert res == [(1, 0.5, float(2 + i), 0.0, 1.0, 1.0)]
+    assert svc.isolated == 1 and det.single == [1]           # only the offender went through the one-by-one route
+    assert sum(det.submitted) == 15 and len(det.submitted) <= 3  # the good ones were re-batched, not serialised
+
+
 def test_letterbox_geometry_and_unmapping():
     """Extension: frames of another size are letterboxed; fd_unmap_letterbox takes the boxes back to
     the caller's pixels.  Restated here: scale = min(net/src) with the long side filling the network, centred."""
