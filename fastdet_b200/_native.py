@@ -58,6 +58,22 @@ KERNEL_NAMES = {0: "conv0", 1: "tc_single", 2: "tc_pair", 3: "tc_pair_strip", 4:
                 7: "copy", 8: "block"}
 
 
+FD_SERVER_MAX_MODELS, FD_SERVER_MAX_DEVICES = 8, 16
+
+
+class FdServerModel(C.Structure):
+    _fields_ = [("onnx_bytes", C.c_void_p), ("len", C.c_size_t), ("num_classes", C.c_int32), ("net_w", C.c_int32),
+                ("net_h", C.c_int32)]
+
+
+class FdServeStats(C.Structure):
+    _fields_ = [("seconds", C.c_double), ("frames", C.c_int64), ("frames_per_second", C.c_double),
+                ("latency_ms_p50", C.c_double), ("latency_ms_p90", C.c_double), ("latency_ms_p99", C.c_double),
+                ("latency_ms_mean", C.c_double), ("latency_ms_max", C.c_double), ("batches", C.c_int64),
+                ("mean_batch", C.c_double), ("detections", C.c_int64), ("streams", C.c_int32), ("reserved", C.c_int32),
+                ("frames_per_device", C.c_int64 * FD_SERVER_MAX_DEVICES), ("frames_per_model", C.c_int64 * FD_SERVER_MAX_MODELS)]
+
+
 class FdJpegInfo(C.Structure):
     _fields_ = [("status", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("components", C.c_int32),
                 ("h_samp", C.c_int32), ("v_samp", C.c_int32), ("restart_interval", C.c_int32),
@@ -93,6 +109,16 @@ _PROTOS = {
     "fd_letterbox_geometry": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int] + [C.POINTER(C.c_int32)] * 4),
     "fd_unmap_letterbox": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "fd_pack_wire": (C.c_int, [C.c_void_p, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "fd_server_create": (C.c_int, [C.POINTER(FdServerModel), C.c_int, C.POINTER(C.c_int32), C.c_int, C.c_int, C.c_int, C.c_double,
+                                   C.POINTER(C.c_void_p)]),
+    "fd_server_create_fake": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_double, C.c_int, C.POINTER(C.c_void_p)]),
+    "fd_server_destroy": (None, [C.c_void_p]),
+    "fd_server_perform": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
+                                    C.POINTER(C.c_int32)]),
+    "fd_server_lane_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
+    "fd_server_closed_loop": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
+                                        C.c_double, C.c_double, C.POINTER(FdServeStats)]),
+    "fd_server_last_error": (C.c_char_p, []),
     "fd_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_set_heads_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),
     "fd_layer_output_fp32": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int]),

@@ -205,6 +205,59 @@ int fd_unmap_letterbox(fd_det* dets, int count, int src_w, int src_h, int net_w,
 int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, int saturate, uint8_t* out, size_t cap,
                  size_t* len);
 
+/* ---- multi-model, multi-GPU serving (BASELINE config 5) ----------------------------------------------------------
+ * The reference keeps one detector object per model spec and shares it between all sessions (server/server.py:295,
+ * 311-312), each payload served by one blocking detector.perform() on a single select loop (:156-163, :232).  fd_server
+ * is that dict of detectors replicated on every device: one LANE per (device, model) = a model replica with its own
+ * streams + a worker thread + a queue of micro-batches (two in flight through fd_submit / fd_collect).  A stream is
+ * pinned to device slot (stream_id mod n_devices).  fd_server_perform has the call shape of perform() — one decoded RGB
+ * frame in, that frame's records out, blocking — and may be called from any number of threads at once; concurrent calls
+ * for the same (device, model) ride in one batch.  Results are those of fd_detect on the same frame (to the batch-size
+ * dependence documented for split-K).  No collective, no cross-device traffic: frames are independent. */
+#define FD_SERVER_MAX_MODELS 8
+#define FD_SERVER_MAX_DEVICES 16
+typedef struct fd_server fd_server;
+typedef struct fd_server_model {
+    const void* onnx_bytes;
+    size_t len;
+    int32_t num_classes, net_w, net_h;
+} fd_server_model;
+typedef struct fd_serve_stats {
+    double seconds;
+    int64_t frames;
+    double frames_per_second;
+    double latency_ms_p50, latency_ms_p90, latency_ms_p99, latency_ms_mean, latency_ms_max;
+    int64_t batches;    /* batches the lanes ran inside the measured window */
+    double mean_batch;  /* frames per batch */
+    int64_t detections;
+    int32_t streams;
+    int32_t reserved;
+    int64_t frames_per_device[FD_SERVER_MAX_DEVICES];
+    int64_t frames_per_model[FD_SERVER_MAX_MODELS];
+} fd_serve_stats;
+/* devices[n_devices]: CUDA device ordinals (device slot d serves the streams with stream_id % n_devices == d).
+ * max_batch: frames per micro-batch at most; max_det: records kept per frame; max_delay_ms: how long a lane with NOTHING
+ * in flight waits for more callers before it runs a partial batch (0: not at all). */
+int fd_server_create(const fd_server_model* models, int n_models, const int32_t* devices, int n_devices, int max_batch,
+                     int max_det, double max_delay_ms, fd_server** out);
+void fd_server_destroy(fd_server* s);
+/* Blocking, thread-safe.  frame: host RGB u8 [src_h, src_w, 3] (copied before the call sleeps); src size must be the
+ * model's (FD_ERR_SIZE otherwise, reference detector.py:132).  out[max_det], *count: the frame's records. */
+int fd_server_perform(fd_server* s, int stream_id, int model, const uint8_t* frame, int src_w, int src_h, double threshold,
+                      fd_det* out, int max_det, int32_t* count);
+int fd_server_lane_stats(fd_server* s, int device_slot, int model, int64_t* batches, int64_t* frames);
+/* Load generator (measurement tool): n_streams caller threads, stream i -> model stream_model[i] and device slot
+ * i % n_devices, each sending its next frame (from frames[n_frames][src_h][src_w][3], host) as soon as the previous result
+ * is back; statistics over `seconds` after `warmup_seconds`.  Latency = wall time of one fd_server_perform call. */
+int fd_server_closed_loop(fd_server* s, int n_streams, const int32_t* stream_model, const uint8_t* frames, int n_frames,
+                          int src_w, int src_h, double threshold, double warmup_seconds, double seconds, fd_serve_stats* out);
+/* Host-only stand-in backend (tests of routing / batching without a GPU): every frame "detects" one record that says where
+ * it was served: klass = the frame's first byte, box = size of the batch it rode in, conf = device slot, x = model, y = ring
+ * slot; collect sleeps latency_us. */
+int fd_server_create_fake(int n_models, int n_devices, int net_w, int net_h, int max_batch, double max_delay_ms, int latency_us,
+                          fd_server** out);
+const char* fd_server_last_error(void);
+
 /* ---- parity / profiling hooks (synchronous; host pointers) ---- */
 /* Raw head tensor `head` of the last forward as f32 NCHW [n, C, H, W] — what model.run returns. */
 int fd_heads_fp32(fd_model* m, int head, float* dst_nchw, int n);
