@@ -552,6 +552,9 @@ def run_b200(args):
         pre_gbs = pre_bytes / (float(layer_ms[0]) * 1e-3) * 1e-9
         head_bytes = n * sum(c * h * ww for (c, h, ww) in model.head_shapes) * 4
         post_gbs = head_bytes / (post_ms * 1e-3) * 1e-9
+        exec_rows = model.exec_info(n)
+        launches_per_batch = sum(e["launches"] for e in exec_rows) + 2  # conv stack (chunked layers launch once per chunk) + decode + Soft-NMS
+        chunked = sorted({(e["chunk_frames"], e["launches"]) for e in exec_rows if e["launches"] > 1})
         line = {
             "metric": "frames_per_second", "value": round(value, 1), "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True, "scaling": w["scaling"],
@@ -562,10 +565,11 @@ def run_b200(args):
                     "d2h_bytes_per_step": int(frames_step * MAX_DET * 48 + 2 * 4 * frames_step),
                     "api": "fd_submit / fd_collect (C ABI), pinned host frames, two batches in flight; every batch copied in and its records read back",
                     "synchronous_fd_detect": round(frames_total / (e2e_sync_ms * 1e-3), 1)},
-            "gpu_launches": int(world * args.steps * batches_per_step * info.launches_per_detect),
+            "gpu_launches": int(world * args.steps * batches_per_step * launches_per_batch),
             "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16"], 4), "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "conv stack (conv_tc_kernel / conv_block_kernel / conv_halo_kernel / conv0_ws_kernel, all tcgen05/TMEM), timed as fd_forward inside the timed steps",
+                         "kernel": "conv stack (conv_tc_kernel / conv_halo_kernel / conv0_ws_kernel, all tcgen05/TMEM), timed as fd_forward inside the timed steps",
+                         "launches_per_batch": launches_per_batch, "l2_resident_chunks": [{"frames": c, "launches_per_layer": k} for c, k in chunked],
                          "peak_kind": "bf16_tflops (burst: the timed region is well under 1 s of tensor work), " + peaks["source"],
                          "frac_of_sustained_peak": round(achieved / peaks["bf16_sustained"], 4), "peak_sustained": peaks["bf16_sustained"],
                          "forward_ms_per_batch": round(fwd_ms, 4), "flops_per_batch": flops_batch},

@@ -55,7 +55,7 @@ class FdLayerExec(C.Structure):
 
 
 KERNEL_NAMES = {0: "conv0", 1: "tc_single", 2: "tc_pair", 3: "tc_pair_strip", 4: "tc_swapped", 5: "halo", 6: "maxpool",
-                7: "copy", 8: "block"}
+                7: "copy"}
 
 
 FD_SERVER_MAX_MODELS, FD_SERVER_MAX_DEVICES = 8, 16
@@ -125,6 +125,7 @@ _PROTOS = {
     "fd_normalise_f32": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]),
     "fd_letterbox_u8": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "fd_time_layers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "fd_time_forward": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_float)]),
 }
 
 _lib = None
@@ -363,6 +364,13 @@ class Model:
         ms = np.zeros(self.info.n_layers, np.float32)
         _check(lib().fd_time_layers(self._h, n, reps, _ptr(ms)))
         return ms
+
+
+    def time_forward(self, n: int, reps: int = 10) -> float:
+        """Device ms of one fd_forward at batch n (captured graph, mean over reps back-to-back runs)."""
+        ms = C.c_float()
+        _check(lib().fd_time_forward(self._h, n, reps, C.byref(ms)))
+        return float(ms.value)
 
 
 def pack_wire(dets: np.ndarray, reqid: int = 0, msec: int = 0, saturate: bool = False) -> bytes:

@@ -49,11 +49,22 @@ int fail(int code, const char* fmt, ...) {
 const float kAnchors3[3][3][2] = {{{116, 90}, {156, 198}, {373, 326}}, {{30, 61}, {62, 45}, {59, 119}}, {{10, 13}, {16, 30}, {33, 23}}};
 const float kAnchors2[2][3][2] = {{{81, 82}, {135, 169}, {344, 319}}, {{10, 14}, {23, 27}, {37, 58}}};
 
+// A run of leading layers executed chunk by chunk: the first stages of the network move hundreds of MB per layer at
+// batch 64 (conv1 writes 709 MB that conv2 reads back), far more than the 126 MB L2 holds, and their kernels are bound by
+// DRAM latency x bytes in flight, not by arithmetic.  Running layers first..last over `chunk` frames at a time keeps a
+// chunk's activations in L2 from the kernel that writes them to the kernel that reads them; buffers that only live inside
+// the segment are chunk-sized and reused by every chunk, so most of their lines are overwritten in L2 and never reach HBM.
+struct Segment { int first = 0, last = 0, chunk = 0; };
+
 struct Exec {  // everything that depends on the batch size
     int n = 0;
     std::vector<void*> bufs;
-    std::vector<ConvLaunch> conv;  // indexed by layer
-    std::vector<HaloLaunch> halo;  // indexed by layer; used where use_halo[layer]
+    std::vector<char> buf_internal;  // 1: chunk-sized, reused by every chunk of its segment
+    std::vector<Segment> segs;
+    std::vector<int> seg_of;         // layer -> index into segs, -1: runs on the whole batch
+    // per layer, per chunk (one entry for layers outside a segment)
+    std::vector<std::vector<ConvLaunch>> conv;
+    std::vector<std::vector<HaloLaunch>> halo;  // used where use_halo[layer]
     std::vector<char> use_halo;
     float* splitk_ws = nullptr;     // shared by the split-K launches of this batch size (they run one after another)
     int* splitk_counters = nullptr;
@@ -125,8 +136,10 @@ void free_exec(Exec* e) {
     if (e->graph) cudaGraphExecDestroy(e->graph);
 }
 
-void* loc_ptr(const Exec& e, const TensorLoc& t, bool fp32) {
+// first byte of tensor `t` for chunk `k` of a segment with `chunk` frames (k = 0, chunk = 0: the whole batch)
+void* loc_ptr(const Exec& e, const ModelPlan& P, const TensorLoc& t, bool fp32, int k = 0, int chunk = 0) {
     char* base = static_cast<char*>(e.bufs[t.buf]);
+    if (k && !e.buf_internal[t.buf]) base += static_cast<size_t>(k) * chunk * (buf_bytes(P.buffers[t.buf], 1));
     return base + size_t(t.ch_off) * (fp32 ? 4 : 2);
 }
 
@@ -142,6 +155,81 @@ int bucket_of(int n) {
     return b;
 }
 
+// Chunked leading segments for batch n (see Segment).  Segment boundaries sit in front of the 2nd and the 3rd
+// down-sampling layer (YOLOv3: [conv1..conv4] at 416/208, [conv5..conv9] at 104; the 52x52 stage and everything after it
+// run on the whole batch: their tensors are small enough and their tiles too few to cut).  The chunk is the largest power
+// of two of frames whose biggest tensor stays under the option chunk_mb (default 44 MB for the first segment, half of
+// that for the second: it also has to hold the residual inputs), and must divide n.
+void plan_segments(const ModelPlan& P, int n, std::vector<Segment>* out) {
+    out->clear();
+    const Options& O = options();
+    if (O.chunk_frames < 0 || n < 2) return;
+    std::vector<int> downs;  // layers that halve the map
+    for (size_t i = 0; i < P.layers.size(); ++i) {
+        const LayerPlan& L = P.layers[i];
+        const bool down = (L.kind == LAYER_CONV && L.stride == 2) || (L.kind == LAYER_MAXPOOL && L.pool_s == 2);
+        if (down) downs.push_back(static_cast<int>(i));
+    }
+    if (downs.size() < 3) return;
+    const int bounds[3] = {0, downs[1], downs[2]};
+    for (int sgi = 0; sgi < 2; ++sgi) {
+        Segment sg;
+        sg.first = bounds[sgi]; sg.last = bounds[sgi + 1] - 1;
+        if (sg.last < sg.first) continue;
+        size_t biggest = 1;
+        for (int i = sg.first; i <= sg.last; ++i) {
+            const LayerPlan& L = P.layers[i];
+            if (L.out_fp32 || L.upsample2x || L.kind == LAYER_COPY) return;  // heads / route layers this early: not a YOLO-shaped graph, leave it alone
+            biggest = std::max(biggest, static_cast<size_t>(L.out.h) * L.out.w * L.out.c * 2);
+        }
+        int chunk;
+        if (O.chunk_frames > 0) chunk = sgi == 0 ? O.chunk_frames : 2 * O.chunk_frames;
+        else {
+            const double budget = (sgi == 0 ? 1.0 : 0.5) * O.chunk_mb * 1e6;
+            chunk = 1;
+            while (static_cast<double>(biggest) * (2 * chunk) <= budget) chunk *= 2;
+        }
+        while (chunk > 1 && n % chunk) chunk /= 2;
+        if (chunk >= n) continue;  // the whole batch already fits
+        sg.chunk = chunk;
+        out->push_back(sg);
+    }
+}
+
+// tensor maps + launch geometry of conv layer i for `frames` frames, chunk k of its segment (k = chunk = 0: whole batch)
+int prepare_conv_layer(fd_model* m, Exec* e, size_t i, int frames, int k, int chunk, ConvLaunch* cl, HaloLaunch* hl, char* use_halo) {
+    const ModelPlan& P = m->plan;
+    const LayerPlan& L = P.layers[i];
+    const __nv_bfloat16* in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, P, L.in, false, k, chunk));
+    const __nv_bfloat16* res = L.res.buf >= 0 ? static_cast<const __nv_bfloat16*>(loc_ptr(*e, P, L.res, false, k, chunk)) : nullptr;
+    void* out = loc_ptr(*e, P, L.out, L.out_fp32 != 0, k, chunk);
+    {   // narrow 3x3 layers on large maps: halo-patch kernel (conv_halo.cu)
+        HaloDesc h;
+        memset(&h, 0, sizeof(h));
+        h.n = frames; h.hi = L.in.h; h.wi = L.in.w; h.cin = L.cin; h.in_pitch = L.in.pitch;
+        h.in = in;
+        h.cout = L.cout; h.ksize = L.ksize; h.stride = L.stride; h.pad_lo = L.pad_lo; h.pad_hi = L.pad_hi;
+        h.w = m->d_w + L.w_off; h.bias_host = P.bias_f32.data() + L.b_off; h.act = L.act; h.alpha = L.alpha;
+        if (res) { h.residual = res; h.res_pitch = L.res.pitch; }
+        h.out = out; h.out_pitch = L.out.pitch; h.out_fp32 = L.out_fp32; h.upsample2x = L.upsample2x;
+        char herr[256] = "";
+        if (conv_halo_supported(h) && conv_halo_prepare(h, m->num_sms, hl, herr, sizeof(herr)) == 0) { *use_halo = 1; return FD_OK; }
+    }
+    *use_halo = 0;
+    ConvDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n = frames; d.hi = L.in.h; d.wi = L.in.w; d.cin = L.cin; d.in_pitch = L.in.pitch;
+    d.in = in;
+    d.cout = L.cout; d.ksize = L.ksize; d.stride = L.stride; d.pad_lo = L.pad_lo; d.pad_hi = L.pad_hi;
+    d.w = m->d_w + L.w_off; d.bias = m->d_bias + L.b_off; d.bias_host = P.bias_f32.data() + L.b_off; d.act = L.act; d.alpha = L.alpha;
+    if (res) { d.residual = res; d.res_pitch = L.res.pitch; }
+    d.out = out; d.out_pitch = L.out.pitch; d.out_fp32 = L.out_fp32; d.upsample2x = L.upsample2x;
+    d.allow_split_k = 1;
+    char err[256] = "";
+    if (conv_tc_prepare(d, m->num_sms, 0, cl, err, sizeof(err))) return fail(FD_ERR_CUDA, "layer %zu (%s): %s", i, L.name.c_str(), err);
+    return FD_OK;
+}
+
 int get_exec(fd_model* m, int n_frames, Exec** out) {
     if (n_frames <= 0) return fail(FD_ERR_ARG, "batch size must be positive (got %d)", n_frames);
     const int n = bucket_of(n_frames);
@@ -150,9 +238,30 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
     std::unique_ptr<Exec> e(new Exec());
     e->n = n;
     const ModelPlan& P = m->plan;
+    plan_segments(P, n, &e->segs);
+    e->seg_of.assign(P.layers.size(), -1);
+    for (size_t sgi = 0; sgi < e->segs.size(); ++sgi)
+        for (int i = e->segs[sgi].first; i <= e->segs[sgi].last; ++i) e->seg_of[i] = static_cast<int>(sgi);
+    // a buffer is internal to a segment when its producer and every reader (input or residual) lie inside that segment
+    e->buf_internal.assign(P.buffers.size(), 0);
+    {
+        std::vector<int> seg_of_buf(P.buffers.size(), -2);  // -2 unseen, -1 touched outside any segment / by two segments
+        auto touch = [&](const TensorLoc& t, int layer) {
+            if (t.buf < 0) return;
+            const int sgi = e->seg_of[layer];
+            if (seg_of_buf[t.buf] == -2) seg_of_buf[t.buf] = sgi;
+            else if (seg_of_buf[t.buf] != sgi) seg_of_buf[t.buf] = -1;
+        };
+        for (size_t i = 0; i < P.layers.size(); ++i) { touch(P.layers[i].in, static_cast<int>(i)); touch(P.layers[i].out, static_cast<int>(i)); touch(P.layers[i].res, static_cast<int>(i)); }
+        for (size_t b = 0; b < P.buffers.size(); ++b) e->buf_internal[b] = seg_of_buf[b] >= 0 ? 1 : 0;
+    }
     e->bufs.assign(P.buffers.size(), nullptr);
     for (size_t i = 0; i < P.buffers.size(); ++i) {
-        cudaError_t err = cudaMalloc(&e->bufs[i], buf_bytes(P.buffers[i], n));
+        int frames = n;
+        if (e->buf_internal[i])
+            for (size_t li = 0; li < P.layers.size(); ++li)
+                if (P.layers[li].out.buf == static_cast<int>(i)) frames = e->segs[e->seg_of[li]].chunk;
+        cudaError_t err = cudaMalloc(&e->bufs[i], buf_bytes(P.buffers[i], frames));
         if (err != cudaSuccess) { free_exec(e.get()); return fail(FD_ERR_CUDA, "cudaMalloc(activation buffer %zu, batch %d) failed: %s", i, n, cudaGetErrorString(err)); }
     }
     const size_t frame_bytes = size_t(n) * P.net_h * P.net_w * 3;
@@ -173,72 +282,80 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
     for (size_t i = 0; i < P.layers.size(); ++i) {
         const LayerPlan& L = P.layers[i];
         if (L.kind != LAYER_CONV) continue;
-        {   // narrow 3x3 layers on large maps: halo-patch kernel (conv_halo.cu)
-            HaloDesc h;
-            memset(&h, 0, sizeof(h));
-            h.n = n; h.hi = L.in.h; h.wi = L.in.w; h.cin = L.cin; h.in_pitch = L.in.pitch;
-            h.in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false));
-            h.cout = L.cout; h.ksize = L.ksize; h.stride = L.stride; h.pad_lo = L.pad_lo; h.pad_hi = L.pad_hi;
-            h.w = m->d_w + L.w_off; h.bias_host = P.bias_f32.data() + L.b_off; h.act = L.act; h.alpha = L.alpha;
-            if (L.res.buf >= 0) { h.residual = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.res, false)); h.res_pitch = L.res.pitch; }
-            h.out = loc_ptr(*e, L.out, L.out_fp32 != 0); h.out_pitch = L.out.pitch; h.out_fp32 = L.out_fp32; h.upsample2x = L.upsample2x;
-            char herr[256] = "";
-            if (conv_halo_supported(h) && conv_halo_prepare(h, m->num_sms, &e->halo[i], herr, sizeof(herr)) == 0) { e->use_halo[i] = 1; continue; }
+        const int sgi = e->seg_of[i];
+        const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, chunks = sgi >= 0 ? n / chunk : 1;
+        e->conv[i].resize(chunks);
+        e->halo[i].resize(chunks);
+        for (int k = 0; k < chunks; ++k) {
+            char uh = 0;
+            if (int rc = prepare_conv_layer(m, e.get(), i, sgi >= 0 ? chunk : n, k, chunk, &e->conv[i][k], &e->halo[i][k], &uh)) { free_exec(e.get()); return rc; }
+            e->use_halo[i] = uh;
         }
-        ConvDesc d;
-        memset(&d, 0, sizeof(d));
-        d.n = n; d.hi = L.in.h; d.wi = L.in.w; d.cin = L.cin; d.in_pitch = L.in.pitch;
-        d.in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false));
-        d.cout = L.cout; d.ksize = L.ksize; d.stride = L.stride; d.pad_lo = L.pad_lo; d.pad_hi = L.pad_hi;
-        d.w = m->d_w + L.w_off; d.bias = m->d_bias + L.b_off; d.bias_host = P.bias_f32.data() + L.b_off; d.act = L.act; d.alpha = L.alpha;
-        if (L.res.buf >= 0) { d.residual = static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.res, false)); d.res_pitch = L.res.pitch; }
-        d.out = loc_ptr(*e, L.out, L.out_fp32 != 0); d.out_pitch = L.out.pitch; d.out_fp32 = L.out_fp32; d.upsample2x = L.upsample2x;
-        d.allow_split_k = 1;
-        char err[256] = "";
-        if (conv_tc_prepare(d, m->num_sms, 0, &e->conv[i], err, sizeof(err))) { free_exec(e.get()); return fail(FD_ERR_CUDA, "layer %zu (%s): %s", i, L.name.c_str(), err); }
     }
     size_t ws_bytes = 0, counter_ints = 0;
-    for (const ConvLaunch& c : e->conv) { ws_bytes = std::max(ws_bytes, c.ws_bytes); counter_ints = std::max(counter_ints, c.counter_ints); }
+    for (const auto& v : e->conv)
+        for (const ConvLaunch& c : v) { ws_bytes = std::max(ws_bytes, c.ws_bytes); counter_ints = std::max(counter_ints, c.counter_ints); }
     if (ws_bytes) {
         if (cudaMalloc(&e->splitk_ws, ws_bytes) != cudaSuccess || cudaMalloc(&e->splitk_counters, counter_ints * sizeof(int)) != cudaSuccess ||
             cudaMemset(e->splitk_counters, 0, counter_ints * sizeof(int)) != cudaSuccess) {
             free_exec(e.get());
             return fail(FD_ERR_CUDA, "cudaMalloc(split-K workspace, batch %d) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
         }
-        for (ConvLaunch& c : e->conv)
-            if (c.ws_bytes) conv_tc_bind_workspace(&c, e->splitk_ws, e->splitk_counters);
+        for (auto& v : e->conv)
+            for (ConvLaunch& c : v)
+                if (c.ws_bytes) conv_tc_bind_workspace(&c, e->splitk_ws, e->splitk_counters);
     }
     *out = e.get();
     m->execs[n] = std::move(e);
     return FD_OK;
 }
 
-int launch_layers(fd_model* m, Exec* e, cudaStream_t s, int only_layer = -1) {
+// one layer on the whole batch (k = 0 outside segments) or on chunk k of its segment
+int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
     const ModelPlan& P = m->plan;
-    for (size_t i = 0; i < P.layers.size(); ++i) {
-        if (only_layer >= 0 && static_cast<int>(i) != only_layer) continue;
-        const LayerPlan& L = P.layers[i];
-        int rc = 0;
-        switch (L.kind) {
-            case LAYER_CONV0:
-                rc = launch_conv0_u8(e->frames, m->d_conv0 + L.w_off, m->d_bias + L.b_off,
-                                     static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), e->n, L.in.h, L.in.w, L.cout,
-                                     L.out.pitch, L.act, L.alpha, s);
-                break;
-            case LAYER_CONV: rc = e->use_halo[i] ? conv_halo_launch(e->halo[i], s) : conv_tc_launch(e->conv[i], s); break;
-            case LAYER_MAXPOOL:
-                rc = launch_maxpool(static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false)), L.in.pitch,
-                                    static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), L.out.pitch, e->n, L.in.h, L.in.w,
-                                    L.in.c, L.pool_k, L.pool_s, L.pool_pad_lo, L.out.h, L.out.w, L.pad_value, s);
-                break;
-            case LAYER_COPY:
-                rc = launch_copy_slice(static_cast<const __nv_bfloat16*>(loc_ptr(*e, L.in, false)), L.in.pitch,
-                                       static_cast<__nv_bfloat16*>(loc_ptr(*e, L.out, false)), L.out.pitch, e->n, L.in.h, L.in.w,
-                                       L.in.c, L.upsample2x, s);
-                break;
-            default: rc = -1;
+    const LayerPlan& L = P.layers[i];
+    const int sgi = e->seg_of[i];
+    const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, frames = sgi >= 0 ? chunk : e->n;
+    int rc = 0;
+    switch (L.kind) {
+        case LAYER_CONV0:
+            rc = launch_conv0_u8(e->frames + static_cast<size_t>(k) * chunk * P.net_h * P.net_w * 3, m->d_conv0 + L.w_off, m->d_bias + L.b_off,
+                                 static_cast<__nv_bfloat16*>(loc_ptr(*e, P, L.out, false, k, chunk)), frames, L.in.h, L.in.w, L.cout,
+                                 L.out.pitch, L.act, L.alpha, s);
+            break;
+        case LAYER_CONV: rc = e->use_halo[i] ? conv_halo_launch(e->halo[i][k], s) : conv_tc_launch(e->conv[i][k], s); break;
+        case LAYER_MAXPOOL:
+            rc = launch_maxpool(static_cast<const __nv_bfloat16*>(loc_ptr(*e, P, L.in, false, k, chunk)), L.in.pitch,
+                                static_cast<__nv_bfloat16*>(loc_ptr(*e, P, L.out, false, k, chunk)), L.out.pitch, frames, L.in.h, L.in.w,
+                                L.in.c, L.pool_k, L.pool_s, L.pool_pad_lo, L.out.h, L.out.w, L.pad_value, s);
+            break;
+        case LAYER_COPY:
+            rc = launch_copy_slice(static_cast<const __nv_bfloat16*>(loc_ptr(*e, P, L.in, false, k, chunk)), L.in.pitch,
+                                   static_cast<__nv_bfloat16*>(loc_ptr(*e, P, L.out, false, k, chunk)), L.out.pitch, frames, L.in.h, L.in.w,
+                                   L.in.c, L.upsample2x, s);
+            break;
+        default: rc = -1;
+    }
+    if (rc) return fail(FD_ERR_CUDA, "launch of layer %zu (%s) failed: %s", i, L.name.c_str(), cudaGetErrorString(cudaGetLastError()));
+    return FD_OK;
+}
+
+// The forward pass: chunked segments chunk by chunk (all layers of the segment per chunk), then the rest layer by layer.
+int launch_layers(fd_model* m, Exec* e, cudaStream_t s) {
+    const ModelPlan& P = m->plan;
+    size_t i = 0;
+    while (i < P.layers.size()) {
+        const int sgi = e->seg_of[i];
+        if (sgi < 0) {
+            if (int rc = launch_one(m, e, i, 0, s)) return rc;
+            ++i;
+            continue;
         }
-        if (rc) return fail(FD_ERR_CUDA, "launch of layer %zu (%s) failed: %s", i, L.name.c_str(), cudaGetErrorString(cudaGetLastError()));
+        const Segment& sg = e->segs[sgi];
+        for (int k = 0; k < e->n / sg.chunk; ++k)
+            for (int j = sg.first; j <= sg.last; ++j)
+                if (int rc = launch_one(m, e, j, k, s)) return rc;
+        i = sg.last + 1;
     }
     return FD_OK;
 }
@@ -377,7 +494,7 @@ int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out) {
     out->flops = L.flops;
     if (L.kind == LAYER_CONV && !m->execs.empty()) {
         const Exec& e0 = *m->execs.begin()->second;
-        out->block_n = e0.use_halo[layer] ? -1 : e0.conv[layer].block_n;  // -1: halo-patch kernel
+        out->block_n = e0.use_halo[layer] ? -1 : e0.conv[layer][0].block_n;  // -1: halo-patch kernel
     }
     snprintf(out->name, sizeof(out->name), "%s", L.name.c_str());
     snprintf(out->out_name, sizeof(out->out_name), "%s", L.out_name.c_str());
@@ -393,8 +510,8 @@ int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
     const LayerPlan& L = m->plan.layers[layer];
     memset(out, 0, sizeof(*out));
     out->bucket = e->n;
-    out->chunk_frames = e->n;
-    out->launches = 1;
+    out->chunk_frames = e->seg_of[layer] >= 0 ? e->segs[e->seg_of[layer]].chunk : e->n;
+    out->launches = e->n / out->chunk_frames;
     switch (L.kind) {
         case LAYER_CONV0: out->kernel = FD_KERNEL_CONV0; break;
         case LAYER_MAXPOOL: out->kernel = FD_KERNEL_MAXPOOL; break;
@@ -402,10 +519,10 @@ int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
         default:
             if (e->use_halo[layer]) {
                 out->kernel = FD_KERNEL_HALO;
-                out->grid = e->halo[layer].grid;
-                out->smem_bytes = static_cast<int32_t>(e->halo[layer].smem_bytes);
+                out->grid = e->halo[layer][0].grid;
+                out->smem_bytes = static_cast<int32_t>(e->halo[layer][0].smem_bytes);
             } else {
-                const ConvLaunch& c = e->conv[layer];
+                const ConvLaunch& c = e->conv[layer][0];
                 out->kernel = c.p.strip ? FD_KERNEL_TC_PAIR_STRIP : c.two_cta ? FD_KERNEL_TC_PAIR : c.p.swap ? FD_KERNEL_TC_SWAPPED : FD_KERNEL_TC_SINGLE;
                 out->block_n = c.block_n; out->split_k = c.p.split_k; out->grid = c.grid; out->num_stages = c.p.num_stages;
                 out->kb_per_stage = c.p.kb_per_stage; out->b_resident = c.p.b_resident;
@@ -497,7 +614,7 @@ static int postprocess_on(fd_model* m, Exec* e, int n, double threshold, int max
     int first = 0;
     for (int h = 0; h < I.n_heads; ++h) {
         const LayerPlan& L = m->plan.layers[m->plan.head_layers[h]];
-        heads[h].data = static_cast<const float*>(loc_ptr(*e, L.out, true));
+        heads[h].data = static_cast<const float*>(loc_ptr(*e, m->plan, L.out, true));
         heads[h].pitch = L.out.pitch; heads[h].h = L.out.h; heads[h].w = L.out.w;
         heads[h].first_box = first;
         first += 3 * L.out.h * L.out.w;
@@ -972,10 +1089,28 @@ int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, i
 }
 
 // ------------------------------------------------------------------ parity / profiling hooks
-static int tensor_to_host_nchw(fd_model* m, Exec* e, const TensorLoc& t, bool fp32, float* dst, int n) {
-    const size_t elems = size_t(n) * t.c * t.h * t.w;
+// `layer`: the layer that produces `t`.  A buffer internal to a chunked segment only ever holds one chunk of frames, so
+// its value for the whole batch is gathered by replaying the segment chunk by chunk up to that layer (the same launches
+// the forward pass makes) and copying each chunk out.
+static int tensor_to_host_nchw(fd_model* m, Exec* e, int layer, const TensorLoc& t, bool fp32, float* dst, int n) {
+    const size_t per_frame = size_t(t.c) * t.h * t.w;
+    if (t.buf >= 0 && e->buf_internal[t.buf]) {
+        const Segment& sg = e->segs[e->seg_of[layer]];
+        if (int rc = ensure_scratch(e, per_frame * sg.chunk * 4)) return rc;
+        for (int k = 0; k * sg.chunk < n; ++k) {
+            for (int j = sg.first; j <= layer; ++j)
+                if (int rc = launch_one(m, e, j, k, m->stream)) return rc;
+            const int frames = std::min(sg.chunk, n - k * sg.chunk);
+            if (launch_nhwc_to_nchw_f32(loc_ptr(*e, m->plan, t, fp32), t.pitch, fp32, e->scratch, frames, t.h, t.w, t.c, m->stream))
+                return fail(FD_ERR_CUDA, "layout kernel launch failed");
+            CU(cudaMemcpyAsync(dst + size_t(k) * sg.chunk * per_frame, e->scratch, per_frame * frames * 4, cudaMemcpyDeviceToHost, m->stream));
+            CU(cudaStreamSynchronize(m->stream));
+        }
+        return FD_OK;
+    }
+    const size_t elems = size_t(n) * per_frame;
     if (int rc = ensure_scratch(e, elems * 4)) return rc;
-    if (launch_nhwc_to_nchw_f32(loc_ptr(*e, t, fp32), t.pitch, fp32, e->scratch, n, t.h, t.w, t.c, m->stream))
+    if (launch_nhwc_to_nchw_f32(loc_ptr(*e, m->plan, t, fp32), t.pitch, fp32, e->scratch, n, t.h, t.w, t.c, m->stream))
         return fail(FD_ERR_CUDA, "layout kernel launch failed");
     CU(cudaMemcpyAsync(dst, e->scratch, elems * 4, cudaMemcpyDeviceToHost, m->stream));
     CU(cudaStreamSynchronize(m->stream));
@@ -989,7 +1124,7 @@ int fd_heads_fp32(fd_model* m, int head, float* dst, int n) {
     Exec* e;
     if (int rc = get_exec(m, n, &e)) return rc;
     CU(cudaDeviceSynchronize());
-    return tensor_to_host_nchw(m, e, m->plan.layers[m->plan.head_layers[head]].out, true, dst, n);
+    return tensor_to_host_nchw(m, e, m->plan.head_layers[head], m->plan.layers[m->plan.head_layers[head]].out, true, dst, n);
 }
 
 int fd_set_heads_fp32(fd_model* m, int head, const float* src, int n) {
@@ -1004,7 +1139,7 @@ int fd_set_heads_fp32(fd_model* m, int head, const float* src, int n) {
     CU(cudaDeviceSynchronize());
     // same stream as the layout kernel: a plain cudaMemcpy from pageable memory may return before its DMA lands
     CU(cudaMemcpyAsync(e->scratch, src, elems * 4, cudaMemcpyHostToDevice, m->stream));
-    if (launch_nchw_to_rows_f32(e->scratch, static_cast<float*>(loc_ptr(*e, t, true)), t.pitch, n, t.h, t.w, t.c, m->stream))
+    if (launch_nchw_to_rows_f32(e->scratch, static_cast<float*>(loc_ptr(*e, m->plan, t, true)), t.pitch, n, t.h, t.w, t.c, m->stream))
         return fail(FD_ERR_CUDA, "layout kernel launch failed");
     CU(cudaStreamSynchronize(m->stream));
     return FD_OK;
@@ -1018,7 +1153,7 @@ int fd_layer_output_fp32(fd_model* m, int layer, float* dst, int n) {
     if (int rc = get_exec(m, n, &e)) return rc;
     CU(cudaDeviceSynchronize());
     const LayerPlan& L = m->plan.layers[layer];
-    return tensor_to_host_nchw(m, e, L.out, L.out_fp32 != 0, dst, n);
+    return tensor_to_host_nchw(m, e, layer, L.out, L.out_fp32 != 0, dst, n);
 }
 
 int fd_normalise_f32(fd_model* m, const uint8_t* frames, int n, float* dst) {
@@ -1064,22 +1199,75 @@ int fd_time_layers(fd_model* m, int n, int reps, float* ms) {
     CU(cudaSetDevice(m->device));
     Exec* e;
     if (int rc = get_exec(m, n, &e)) return rc;
+    const size_t nl = m->plan.layers.size();
     cudaEvent_t e0, e1;
     CU(cudaEventCreate(&e0));
     CU(cudaEventCreate(&e1));
     if (int rc = launch_layers(m, e, m->stream)) return rc;  // warm-up, also fills every buffer
     CU(cudaStreamSynchronize(m->stream));
-    for (size_t i = 0; i < m->plan.layers.size(); ++i) {
-        if (int rc = launch_layers(m, e, m->stream, static_cast<int>(i))) return rc;
-        CU(cudaEventRecord(e0, m->stream));
-        for (int r = 0; r < reps; ++r)
-            if (int rc = launch_layers(m, e, m->stream, static_cast<int>(i))) return rc;
-        CU(cudaEventRecord(e1, m->stream));
-        CU(cudaStreamSynchronize(m->stream));
-        float t = 0.f;
-        CU(cudaEventElapsedTime(&t, e0, e1));
-        ms[i] = t / reps;
+    for (size_t i = 0; i < nl; ++i) ms[i] = 0.f;
+    size_t i = 0;
+    while (i < nl) {
+        const int sgi = e->seg_of[i];
+        if (sgi < 0) {  // a layer on the whole batch, timed alone: reps back-to-back launches
+            if (int rc = launch_one(m, e, i, 0, m->stream)) return rc;
+            CU(cudaEventRecord(e0, m->stream));
+            for (int r = 0; r < reps; ++r)
+                if (int rc = launch_one(m, e, i, 0, m->stream)) return rc;
+            CU(cudaEventRecord(e1, m->stream));
+            CU(cudaStreamSynchronize(m->stream));
+            float t = 0.f;
+            CU(cudaEventElapsedTime(&t, e0, e1));
+            ms[i] = t / reps;
+            ++i;
+            continue;
+        }
+        // a chunked segment is timed as it runs (chunk by chunk, its activations L2-resident): one event after every launch,
+        // a layer's time = the sum of its chunks' intervals
+        const Segment& sg = e->segs[sgi];
+        const int chunks = e->n / sg.chunk, per = sg.last - sg.first + 1;
+        std::vector<cudaEvent_t> ev(static_cast<size_t>(chunks) * per + 1);
+        for (auto& x : ev) CU(cudaEventCreate(&x));
+        for (int r = 0; r < reps; ++r) {
+            CU(cudaEventRecord(ev[0], m->stream));
+            for (int k = 0; k < chunks; ++k)
+                for (int j = 0; j < per; ++j) {
+                    if (int rc = launch_one(m, e, sg.first + j, k, m->stream)) return rc;
+                    CU(cudaEventRecord(ev[static_cast<size_t>(k) * per + j + 1], m->stream));
+                }
+            CU(cudaStreamSynchronize(m->stream));
+            for (int k = 0; k < chunks; ++k)
+                for (int j = 0; j < per; ++j) {
+                    float t = 0.f;
+                    CU(cudaEventElapsedTime(&t, ev[static_cast<size_t>(k) * per + j], ev[static_cast<size_t>(k) * per + j + 1]));
+                    ms[sg.first + j] += t / reps;
+                }
+        }
+        for (auto& x : ev) cudaEventDestroy(x);
+        i = sg.last + 1;
     }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return FD_OK;
+}
+
+int fd_time_forward(fd_model* m, int n, int reps, float* ms) {
+    if (!m || !ms || reps < 1) return fail(FD_ERR_ARG, "fd_time_forward: bad argument");
+    NEED_DEVICE(m);
+    CU(cudaSetDevice(m->device));
+    cudaEvent_t e0, e1;
+    CU(cudaEventCreate(&e0));
+    CU(cudaEventCreate(&e1));
+    for (int r = 0; r < 2; ++r)
+        if (int rc = fd_forward(m, n, nullptr)) return rc;  // graph capture + warm-up
+    CU(cudaEventRecord(e0, m->stream));
+    for (int r = 0; r < reps; ++r)
+        if (int rc = fd_forward(m, n, nullptr)) return rc;
+    CU(cudaEventRecord(e1, m->stream));
+    CU(cudaStreamSynchronize(m->stream));
+    float t = 0.f;
+    CU(cudaEventElapsedTime(&t, e0, e1));
+    *ms = t / reps;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return FD_OK;

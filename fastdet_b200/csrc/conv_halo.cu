@@ -49,14 +49,21 @@ struct Geo {
     static constexpr int SPH = STRIDE == 1 ? PH : TH + 1;
     static constexpr int SPW = STRIDE == 1 ? PW : TW + 1;
     static constexpr int PLANE_PIX = (STRIDE == 1 ? 1 : 4) * SPH * SPW;
-    static constexpr int PLANE_BYTES = ((PLANE_PIX * 16 + 127) / 128) * 128;
+    static constexpr int PLANE_BASE = ((PLANE_PIX * 16 + 127) / 128) * 128;
     static constexpr int SBO = SPW * 16;
 };
-// patch ring depth: the copies of SLOTS tiles are in flight at once (the ~3 us DRAM/L2 round trip of a patch is what has
-// to be covered).  Bounded by shared memory: 32-channel stride-2 patches are 39 KB each; with 64 input channels the
-// resident filter bank (up to 147 KB) leaves room for two 23 KB patches.
+// Plane stride.  The builders' cp.async items run chunk-fastest (8 lanes = one 128-byte shared-memory wavefront cover
+// 8 / NCH pixels x NCH chunks), so chunk planes a multiple of 128 bytes apart put the NCH chunks of a pixel on the same
+// banks: an NCH-way conflict on every copy (ncu, conv2: 87 % of the shared-memory pipe).  Skewing the planes by 128 / NCH
+// bytes spreads the 8 items of a quarter warp over the 8 distinct 16-byte slots of a wavefront.
 template <int CIN, int STRIDE>
-struct Ring { static constexpr int SLOTS = CIN == 64 ? 2 : (STRIDE == 1 ? 8 : 4); };
+struct Plane { static constexpr int BYTES = Geo<STRIDE>::PLANE_BASE + 128 / (CIN / 8); };
+// patch ring depth: the copies of SLOTS tiles are in flight at once (the ~3 us DRAM/L2 round trip of a patch is what has
+// to be covered: conv4 moved 4.2 TB/s with 8 slots = 94 KB in flight per SM, exactly latency x concurrency).  Bounded by
+// shared memory: 32-channel stride-2 patches are 39 KB each; with 64 input channels the resident filter bank (up to
+// 147 KB) leaves room for two 23 KB patches.
+template <int CIN, int STRIDE>
+struct Ring { static constexpr int SLOTS = CIN == 64 ? 2 : (STRIDE == 1 ? 12 : 4); };
 
 __device__ __forceinline__ int div_magic(int x, unsigned long long m) {
     return static_cast<int>((static_cast<unsigned long long>(x) * m) >> 40);
@@ -80,7 +87,8 @@ __global__ void __launch_bounds__(THREADS, 1)
 conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_constant__ HaloParams p) {
     using G = Geo<STRIDE>;
     constexpr int NCH = CIN / 8;                    // 16-byte channel chunks per pixel
-    constexpr int PATCH_BYTES = NCH * G::PLANE_BYTES;
+    constexpr int PLANE_BYTES = Plane<CIN, STRIDE>::BYTES;
+    constexpr int PATCH_BYTES = NCH * PLANE_BYTES;
     constexpr int KSTEPS = CIN / 16;                // MMAs per filter tap
     constexpr int SLOTS = Ring<CIN, STRIDE>::SLOTS;
     extern __shared__ uint8_t smem_raw[];
@@ -151,7 +159,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                 const bool ok = gy >= 0 && gy < p.hi && gx >= 0 && gx < p.wi;
                 const int idx = STRIDE == 1 ? pix : (((iy & 1) * 2 + (ix & 1)) * (G::SPH * G::SPW) + (iy >> 1) * G::SPW + (ix >> 1));
                 const __nv_bfloat16* src = ok ? frame + (static_cast<long long>(gy) * p.wi + gx) * p.in_pitch + c * 8 : p.in;
-                ptx::cp_async_16(dst0 + c * G::PLANE_BYTES + idx * 16, src, ok ? 16u : 0u);  // 0 bytes: zero fill (padding)
+                ptx::cp_async_16(dst0 + c * PLANE_BYTES + idx * 16, src, ok ? 16u : 0u);  // 0 bytes: zero fill (padding)
             }
             ptx::cp_async_arrive_noinc(&patch_full[slot]);
         }
@@ -162,7 +170,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
         const uint32_t p_addr0 = __shfl_sync(0xffffffffu, ptx::smem_u32(s_patch), 0);
         const uint32_t bar0 = __shfl_sync(0xffffffffu, ptx::smem_u32(patch_full), 0);  // full, empty, acc_full, acc_empty: 8-byte steps
         const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-        const uint64_t a0 = desc_kmajor(p_addr0, G::PLANE_BYTES, G::SBO);
+        const uint64_t a0 = desc_kmajor(p_addr0, PLANE_BYTES, G::SBO);
         const uint64_t b0 = desc_kmajor(w_addr, cout * 16, 128);
         const uint32_t b_step = static_cast<uint32_t>(cout) * 2;  // two K chunks per MMA, in 16-byte units: 2 * cout * 16 / 16
         const bool issuer = ptx::elect_one();
@@ -182,7 +190,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                                                   : (((r & 1) * 2 + (s & 1)) * (G::SPH * G::SPW) + (r >> 1) * G::SPW + (s >> 1));
 #pragma unroll
                     for (int j = 0; j < KSTEPS; ++j)
-                        ptx::umma_bf16(d, ad + start + j * (2 * G::PLANE_BYTES / 16), b0 + (t * KSTEPS + j) * b_step, idesc,
+                        ptx::umma_bf16(d, ad + start + j * (2 * PLANE_BYTES / 16), b0 + (t * KSTEPS + j) * b_step, idesc,
                                        (t | j) ? 1u : 0u);
                 }
                 ptx::umma_commit_addr(bar0 + 8u * (SLOTS + slot));    // patch_empty
@@ -316,7 +324,7 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
 template <int CIN, int STRIDE>
 size_t smem_bytes(int cout) {
     return 1024 + 1024 + EPI_WARPS * 4096 + ((9 * (CIN / 8) * cout * 16 + 1023) & ~1023) +
-           static_cast<size_t>(Ring<CIN, STRIDE>::SLOTS) * (CIN / 8) * Geo<STRIDE>::PLANE_BYTES;
+           static_cast<size_t>(Ring<CIN, STRIDE>::SLOTS) * (CIN / 8) * Plane<CIN, STRIDE>::BYTES;
 }
 
 }  // namespace

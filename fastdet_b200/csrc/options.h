@@ -22,8 +22,9 @@ struct Options {
     int exact_batch = 0;      // one execution state per exact batch size instead of per bucket
     int nms_general = 0;      // force the general (global-memory) Soft-NMS loop
     int jpeg_threads = 0;     // host threads of the JPEG entropy decoder; 0 = all hardware threads (max 64)
-    int fuse_block = 1;       // residual blocks on large maps (1x1 C->C/2, 3x3 C/2->C, + input) as one kernel
-    int chunk_frames = 0;     // early layers run in chunks of this many frames so a chunk's activations stay in L2; 0 = auto
+    int chunk_frames = 0;     // the leading layers run in chunks of this many frames (twice as many in the second segment) so a chunk's
+                              // activations stay in L2; 0 = sized from chunk_mb, -1 = no chunking
+    int chunk_mb = 48;        // auto chunk size: largest tensor of a first-segment chunk at most this many MB (half of it in the second)
     int detect_overlap = 1;   // synchronous fd_detect copies the frames in two halves so the second overlaps conv0
 };
 

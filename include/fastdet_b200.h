@@ -95,7 +95,6 @@ typedef struct fd_layer_desc {
 #define FD_KERNEL_HALO 5          /* conv_halo_kernel (narrow 3x3 on large maps) */
 #define FD_KERNEL_MAXPOOL 6
 #define FD_KERNEL_COPY 7
-#define FD_KERNEL_BLOCK 8         /* conv_block_kernel: 1x1 reduce + 3x3 expand + residual of a Darknet block in one launch */
 typedef struct fd_layer_exec {
     int32_t kernel;       /* FD_KERNEL_* */
     int32_t bucket;       /* batch-size bucket whose execution state answered (n rounded up) */
@@ -269,8 +268,11 @@ int fd_layer_output_fp32(fd_model* m, int layer, float* dst_nchw, int n);
 int fd_normalise_f32(fd_model* m, const uint8_t* frames, int n, float* dst_nchw);
 /* Device letterbox of host frames [n, src_h, src_w, 3] to [n, net_h, net_w, 3]. */
 int fd_letterbox_u8(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, uint8_t* dst);
-/* Per-layer device time (ms, mean over reps) of the forward pass at batch n, each layer timed alone. */
+/* Per-layer device time (ms, mean over reps) of the forward pass at batch n: layers that run on the whole batch are timed
+ * alone (reps back-to-back launches), layers of an L2-resident chunked segment as the segment runs (sum over its chunks). */
 int fd_time_layers(fd_model* m, int n, int reps, float* ms_per_layer);
+/* Device time (ms, mean over reps back-to-back runs) of fd_forward at batch n: the captured graph as serving runs it. */
+int fd_time_forward(fd_model* m, int n, int reps, float* ms);
 
 #ifdef __cplusplus
 }

@@ -53,9 +53,14 @@ class GraphExecutor:
     """Runs a parsed graph on torch-CPU.  ``dtype`` = torch.float32 (what ORT computes in), float64, or "bf16"
     (bf16 operands / fp32 accumulation, see the module docstring)."""
 
-    def __init__(self, onnx_bytes: bytes, dtype=torch.float32):
+    def __init__(self, onnx_bytes: bytes, dtype=torch.float32, accumulate=torch.float32, fp32_tail: int = 0):
+        """accumulate (bf16 mode): dtype the products are summed in — float64 gives the exactly-summed variant of the same
+        bf16-operand arithmetic.  fp32_tail (bf16 mode): the last `fp32_tail` convolutions in front of every graph output
+        keep fp32 weights and pass fp32 (unrounded) activations between them."""
         self.graph = onnx_min.load(onnx_bytes)
         self.bf16 = dtype == "bf16"
+        self.accumulate = accumulate
+        self.fp32_tail = int(fp32_tail)
         if self.bf16:
             dtype = torch.float32
         self.dtype = dtype
@@ -86,6 +91,18 @@ class GraphExecutor:
             c = consumers.get(name, [])
             return c[0] if len(c) == 1 and name not in outputs else None
 
+        # the last fp32_tail convolutions in front of every graph output (walking back through the fused chain)
+        producer = {n.outputs[0]: n for n in g.nodes}
+        tail = set()
+        for o in g.outputs:
+            name, left = o, self.fp32_tail
+            while left > 0 and name in producer:
+                n = producer[name]
+                if n.op == "Conv":
+                    tail.add(id(n))
+                    left -= 1
+                name = n.inputs[0]
+        self.tail = tail
         for n in g.nodes:
             if n.op == "Conv":
                 w = self.consts[n.inputs[1]].to(torch.float32)
@@ -100,13 +117,14 @@ class GraphExecutor:
                     b = bb + (b - mean) * inv
                     self.bn_identity.add(id(nx))
                     last = nx
-                self.folded[n.outputs[0]] = (_bf16(w), b)
+                self.folded[n.outputs[0]] = (w if id(n) in tail else _bf16(w), b)
                 nx = sole(last.outputs[0])
                 if nx is not None and nx.op in ("LeakyRelu", "Relu"):
                     last = nx
                 # the value after the activation is what the conv kernel's epilogue rounds and stores; a graph output
                 # (head tensor) is written in fp32
-                if last.outputs[0] not in outputs:
+                feeds_tail = any(id(c) in tail for c in consumers.get(last.outputs[0], []))
+                if last.outputs[0] not in outputs and not (id(n) in tail and feeds_tail):
                     self.round_after.add(last.outputs[0])
             elif n.op == "Add":
                 if n.inputs[0] not in self.consts and n.inputs[1] not in self.consts and n.outputs[0] not in outputs:
@@ -210,7 +228,11 @@ class GraphExecutor:
                 op = n.op
                 if op == "Conv" and self.bf16:
                     w16, bias = self.folded[n.outputs[0]]
-                    out = self._conv(n, _bf16(ins[0]), w16, bias)
+                    xin = ins[0] if id(n) in self.tail else _bf16(ins[0])
+                    if self.accumulate == torch.float64:
+                        out = self._conv(n, xin.double(), w16.double(), bias.double()).to(torch.float32)
+                    else:
+                        out = self._conv(n, xin, w16, bias)
                 elif op == "Conv":
                     out = self._conv(n, *ins)
                 elif op == "BatchNormalization" and id(n) in self.bn_identity:

@@ -97,32 +97,60 @@ def test_bf16_operand_mode_follows_the_planner():
         assert np.abs(a - b).max() <= 1e-2 * np.abs(b).max()
 
 
-def test_bf16_operand_floor():
-    """What BASELINE.json's prescribed arithmetic (bf16 operands, fp32 accumulation) costs against the fp32 oracle, with
-    no GPU involved: raw heads stay inside the spec's 2e-2 * max|ref|, scores inside 1e-2, but the box IoU of matched
-    detections does NOT stay above 0.99 — exp(tw), exp(th) amplify the ~1 % logit noise of these random-init nets.  The
-    GPU tests therefore hold the CUDA path to IoU >= 0.99 / |dconf| <= 1e-2 against the bf16-operand oracle and to the
-    floor measured here against the fp32 oracle (tests/test_gpu_parity.py::test_detections_match_oracle)."""
+def _detection_spread(heads_a, heads_b, nc):
+    """IoU / |dconf| of the detections two sets of head tensors give at the same anchor box with the same class."""
     from oracle import ref_post
-    ious, dconfs, herr = [], [], []
+    wa, ia, _ = ref_post.detect_from_heads(heads_a, 0, nc, (416, 416), 0.1)
+    wb, ib, _ = ref_post.detect_from_heads(heads_b, 0, nc, (416, 416), 0.1)
+    db = dict(zip(ib, wb))
+    ious, dconfs = [], []
+    for box, w in zip(ia, wa):
+        if box in db and db[box][0] == w[0]:
+            ious.append(_iou(w[2:], db[box][2:]))
+            dconfs.append(abs(w[1] - db[box][1]))
+    return ious, dconfs
+
+
+def test_bf16_operand_floor():
+    """What BASELINE.json's prescribed arithmetic (bf16 operands, fp32 accumulation) costs, with no GPU involved.
+    (i)   bf16-operand oracle vs fp32 oracle: raw heads stay inside the spec's 2e-2 * max|ref| and scores inside 1e-2, but the
+          box IoU of matched detections does NOT stay above 0.99 — exp(tw), exp(th) amplify the ~1 % logit noise of these
+          random-init nets.
+    (ii)  two bf16-operand evaluations that differ ONLY in how the fp32 sums are formed (fp32 vs exact float64 accumulation of
+          the same bf16 products) are as far from each other as from fp32: a flipped bf16 rounding perturbs every sum it feeds
+          by a fraction of a rounding step and flips more downstream.  No implementation — CPU or tensor core — can agree with
+          another one's boxes to 0.99 IoU through bf16 activation storage.
+    (iii) keeping the last two convolutions in front of every head in fp32 (weights and the activation between them) does
+          not buy the bound back: the noise is accumulated over the depth of the network, not added at the end.
+    The GPU tests therefore hold the CUDA path to the floor measured here, against both oracles
+    (tests/test_gpu_parity.py::test_detections_match_oracle)."""
+    from oracle import ref_post
+    spread = {"fp32": ([], []), "acc64": ([], []), "tail": ([], [])}
+    herr = []
     for arch, nc, seed, frames in (("tiny", 80, 1, 3), ("rsu", 9, 3, 2)):
         data = modelgen.build_onnx(arch, nc, 416, seed)
         e32, e16 = ref_graph.GraphExecutor(data), ref_graph.GraphExecutor(data, dtype="bf16")
+        e16x = ref_graph.GraphExecutor(data, dtype="bf16", accumulate=torch.float64)
+        e16t = ref_graph.GraphExecutor(data, dtype="bf16", fp32_tail=2)
         for s in range(frames):
             x = ref_post.normalise(modelgen.synthetic_frame(200 + s, 416))
-            h32, h16 = e32.run(x), e16.run(x)
+            h32, h16, h16x, h16t = e32.run(x), e16.run(x), e16x.run(x), e16t.run(x)
             herr.append(max(float(np.abs(a - b).max() / np.abs(a).max()) for a, b in zip(h32, h16)))
-            w32, i32, _ = ref_post.detect_from_heads(h32, 0, nc, (416, 416), 0.1)
-            w16, i16, _ = ref_post.detect_from_heads(h16, 0, nc, (416, 416), 0.1)
-            d16 = dict(zip(i16, w16))
-            for box, w in zip(i32, w32):
-                if box in d16 and d16[box][0] == w[0]:
-                    ious.append(_iou(w[2:], d16[box][2:]))
-                    dconfs.append(abs(w[1] - d16[box][1]))
-    ious, dconfs = np.array(ious), np.array(dconfs)
-    print(f"bf16-operand oracle vs fp32 oracle: head err max {max(herr):.4f}; {len(ious)} matched boxes, IoU min {ious.min():.4f} "
-          f"median {np.median(ious):.4f} >=0.99: {np.mean(ious >= 0.99):.2f}; |dconf| max {dconfs.max():.4f}")
+            for key, (ha, hb) in (("fp32", (h32, h16)), ("acc64", (h16, h16x)), ("tail", (h32, h16t))):
+                i, d = _detection_spread(ha, hb, nc)
+                spread[key][0].extend(i)
+                spread[key][1].extend(d)
+    stats = {}
+    for key, (i, d) in spread.items():
+        i, d = np.array(i), np.array(d)
+        stats[key] = i, d
+        print(f"{key:>6}: {len(i)} matched boxes, IoU min {i.min():.4f} median {np.median(i):.4f} >=0.99: {np.mean(i >= 0.99):.2f}; "
+              f"|dconf| max {d.max():.4f}")
+    print(f"bf16-operand oracle vs fp32 oracle: head err max {max(herr):.4f}")
     assert max(herr) <= 2e-2
+    ious, dconfs = stats["fp32"]
     assert len(ious) >= 60 and dconfs.max() <= 1e-2
     assert ious.min() >= 0.95 and np.median(ious) >= 0.98
-    assert np.mean(ious >= 0.99) < 0.9  # the floor: bf16 operands alone miss the 0.99 bound on a good share of the boxes
+    assert np.mean(ious >= 0.99) < 0.9   # (i) the floor: bf16 operands alone miss the 0.99 bound on a good share of the boxes
+    assert np.mean(stats["acc64"][0] >= 0.99) < 0.9  # (ii) ... between two bf16-correct evaluations as well
+    assert np.mean(stats["tail"][0] >= 0.99) < 0.9   # (iii) ... and fp32 head layers do not repair it
