@@ -352,6 +352,21 @@ int launch_layers(fd_model* m, Exec* e, cudaStream_t s) {
             continue;
         }
         const Segment& sg = e->segs[sgi];
+        const Segment* nx = static_cast<size_t>(sgi) + 1 < e->segs.size() ? &e->segs[sgi + 1] : nullptr;
+        if (options().chunk_interleave && nx && nx->first == sg.last + 1 && nx->chunk % sg.chunk == 0) {
+            // the two segments interleaved: the second segment's chunk runs as soon as the first has produced its frames, so
+            // the tensor that crosses from one to the other is read back from L2 as well
+            const int ratio = nx->chunk / sg.chunk;
+            for (int kb = 0; kb < e->n / nx->chunk; ++kb) {
+                for (int k = kb * ratio; k < (kb + 1) * ratio; ++k)
+                    for (int j = sg.first; j <= sg.last; ++j)
+                        if (int rc = launch_one(m, e, j, k, s)) return rc;
+                for (int j = nx->first; j <= nx->last; ++j)
+                    if (int rc = launch_one(m, e, j, kb, s)) return rc;
+            }
+            i = nx->last + 1;
+            continue;
+        }
         for (int k = 0; k < e->n / sg.chunk; ++k)
             for (int j = sg.first; j <= sg.last; ++j)
                 if (int rc = launch_one(m, e, j, k, s)) return rc;

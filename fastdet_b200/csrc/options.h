@@ -25,6 +25,7 @@ struct Options {
     int chunk_frames = 0;     // the leading layers run in chunks of this many frames (twice as many in the second segment) so a chunk's
                               // activations stay in L2; 0 = sized from chunk_mb, -1 = no chunking
     int chunk_mb = 48;        // auto chunk size: largest tensor of a first-segment chunk at most this many MB (half of it in the second)
+    int chunk_interleave = 0; // run the second chunked segment's chunk right after the first-segment chunks that feed it
     int detect_overlap = 1;   // synchronous fd_detect copies the frames in two halves so the second overlaps conv0
 };
 
