@@ -9,9 +9,11 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--size", type=int, default=416); ap.add_argument("--batch", type=int, default=64)
 ap.add_argument("--reps", type=int, default=20)
 ap.add_argument("--frames", default="-1,1,2,4,8,0")
+ap.add_argument("--interleave", type=int, default=0)
 a = ap.parse_args()
 onnx = modelgen.build_onnx("full", 80, a.size, 2)
 frames = np.stack([modelgen.synthetic_frame(100 + i, a.size) for i in range(8)])[np.arange(a.batch) % 8]
+_native.set_option("chunk_interleave", a.interleave)
 for cf in [int(x) for x in a.frames.split(",")]:
     _native.set_option("chunk_frames", cf)
     m = _native.Model(onnx, 80, (a.size, a.size), device=0)
