@@ -83,6 +83,14 @@ struct Exec {  // everything that depends on the batch size
     size_t scratch_cap = 0;
     cudaGraphExec_t graph = nullptr;
     bool graph_tried = false;
+    // fd_detect's copy-overlapped front (see forward_overlapping_copy): the layers in front of the second down-sampling
+    // layer get a second set of launch descriptors for quarter batches (same buffers, frame offsets), the rest is graph_tail
+    int ov_layers = 0, ov_chunk = 0;  // 0: not built / not applicable (-1 in ov_layers)
+    std::vector<std::vector<ConvLaunch>> ov_conv;
+    std::vector<std::vector<HaloLaunch>> ov_halo;
+    std::vector<char> ov_use_halo;
+    cudaGraphExec_t graph_tail = nullptr;
+    bool graph_tail_tried = false;
 };
 
 }  // namespace
@@ -116,6 +124,8 @@ struct fd_model {
     float* d_conv0 = nullptr;
     cudaStream_t stream = nullptr;
     std::map<int, std::unique_ptr<Exec>> execs;
+    cudaEvent_t h2d_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // fd_detect: pieces of the frame copy
+    cudaEvent_t idle_ev = nullptr;  // end of the last forward pass on the compute stream (its input tensor may be overwritten)
     fd_info info;
     int last_n = 0;
     int last_max_det = 0;
@@ -134,6 +144,7 @@ void free_exec(Exec* e) {
     if (e->h_dets) cudaFreeHost(e->h_dets);
     if (e->h_count) cudaFreeHost(e->h_count);
     if (e->graph) cudaGraphExecDestroy(e->graph);
+    if (e->graph_tail) cudaGraphExecDestroy(e->graph_tail);
 }
 
 // first byte of tensor `t` for chunk `k` of a segment with `chunk` frames (k = 0, chunk = 0: the whole batch)
@@ -310,12 +321,11 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
     return FD_OK;
 }
 
-// one layer on the whole batch (k = 0 outside segments) or on chunk k of its segment
-int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
+// layer i on frames [k * chunk, (k + 1) * chunk) (chunk = 0: the whole batch) with the given conv launch descriptors
+int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, const ConvLaunch* cl, const HaloLaunch* hl, cudaStream_t s) {
     const ModelPlan& P = m->plan;
     const LayerPlan& L = P.layers[i];
-    const int sgi = e->seg_of[i];
-    const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, frames = sgi >= 0 ? chunk : e->n;
+    const int frames = chunk ? chunk : e->n;
     int rc = 0;
     switch (L.kind) {
         case LAYER_CONV0:
@@ -323,7 +333,7 @@ int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
                                  static_cast<__nv_bfloat16*>(loc_ptr(*e, P, L.out, false, k, chunk)), frames, L.in.h, L.in.w, L.cout,
                                  L.out.pitch, L.act, L.alpha, s);
             break;
-        case LAYER_CONV: rc = e->use_halo[i] ? conv_halo_launch(e->halo[i][k], s) : conv_tc_launch(e->conv[i][k], s); break;
+        case LAYER_CONV: rc = halo ? conv_halo_launch(*hl, s) : conv_tc_launch(*cl, s); break;
         case LAYER_MAXPOOL:
             rc = launch_maxpool(static_cast<const __nv_bfloat16*>(loc_ptr(*e, P, L.in, false, k, chunk)), L.in.pitch,
                                 static_cast<__nv_bfloat16*>(loc_ptr(*e, P, L.out, false, k, chunk)), L.out.pitch, frames, L.in.h, L.in.w,
@@ -340,10 +350,18 @@ int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
     return FD_OK;
 }
 
+// one layer on the whole batch (k = 0 outside segments) or on chunk k of its segment
+int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
+    const int sgi = e->seg_of[i];
+    const bool conv = m->plan.layers[i].kind == LAYER_CONV;
+    return launch_layer(m, e, i, k, sgi >= 0 ? e->segs[sgi].chunk : 0, e->use_halo[i] != 0, conv ? &e->conv[i][k] : nullptr,
+                        conv ? &e->halo[i][k] : nullptr, s);
+}
+
 // The forward pass: chunked segments chunk by chunk (all layers of the segment per chunk), then the rest layer by layer.
-int launch_layers(fd_model* m, Exec* e, cudaStream_t s) {
+int launch_layers(fd_model* m, Exec* e, cudaStream_t s, int from_layer = 0) {
     const ModelPlan& P = m->plan;
-    size_t i = 0;
+    size_t i = static_cast<size_t>(from_layer);  // 0, or the first layer after a segment
     while (i < P.layers.size()) {
         const int sgi = e->seg_of[i];
         if (sgi < 0) {
@@ -488,6 +506,7 @@ void fd_model_destroy(fd_model* m) {
         if (S.staged) { cudaEventDestroy(S.staged); cudaEventDestroy(S.stage_free); cudaEventDestroy(S.done); }
     }
     cudaFree(m->jpeg_planes);
+    if (m->idle_ev) { cudaEventDestroy(m->idle_ev); for (cudaEvent_t ev : m->h2d_ev) cudaEventDestroy(ev); }
     if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
     if (m->stream) cudaStreamDestroy(m->stream);
     delete m;
@@ -593,6 +612,22 @@ int fd_preprocess(fd_model* m, const uint8_t* frames, int n, int src_w, int src_
     return FD_OK;
 }
 
+// the layers from `from_layer` on as an instantiated CUDA graph (nullptr if capture is not possible: callers then launch directly)
+static cudaGraphExec_t capture_layers(fd_model* m, Exec* e, int from_layer) {
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t exec = nullptr;
+    if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
+        const int rc = launch_layers(m, e, m->stream, from_layer);
+        const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
+        if (rc == FD_OK && ce == cudaSuccess && graph) {
+            if (cudaGraphInstantiate(&exec, graph, 0) != cudaSuccess) exec = nullptr;
+        }
+        if (graph) cudaGraphDestroy(graph);
+    }
+    cudaGetLastError();
+    return exec;
+}
+
 int fd_forward(fd_model* m, int n, void* stream) {
     if (!m) return fail(FD_ERR_ARG, "fd_forward: null model");
     NEED_DEVICE(m);
@@ -603,16 +638,7 @@ int fd_forward(fd_model* m, int n, void* stream) {
     m->last_n = n;
     if (m->use_graph && !e->graph_tried) {
         e->graph_tried = true;
-        cudaGraph_t graph = nullptr;
-        if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
-            const int rc = launch_layers(m, e, m->stream);
-            const cudaError_t ce = cudaStreamEndCapture(m->stream, &graph);
-            if (rc == FD_OK && ce == cudaSuccess && graph) {
-                if (cudaGraphInstantiate(&e->graph, graph, 0) != cudaSuccess) e->graph = nullptr;
-            }
-            if (graph) cudaGraphDestroy(graph);
-        }
-        cudaGetLastError();
+        e->graph = capture_layers(m, e, 0);
     }
     if (e->graph) {
         CU(cudaGraphLaunch(e->graph, s));
@@ -688,8 +714,97 @@ int fd_fetch(fd_model* m, int n, fd_det* out, int32_t* counts, int32_t* total, v
     return FD_OK;
 }
 
+// fd_detect with host frames of the network's own size: the synchronous call used to pay the whole PCIe copy (33 MB,
+// 0.66 ms at batch 64) in front of every batch.  Here the copy is cut into four pieces on the copy stream, and the layers
+// in front of the second down-sampling layer (YOLOv3: conv1..conv4, the 416 / 208 stages: 0.8 ms) run quarter by quarter,
+// each quarter behind the piece that carries its frames, so all but the first piece hides behind them.  The rest of the
+// network follows as one captured graph.  Same kernels on the same frames: results are those of the plain path bit for bit.
+static int build_overlap_plan(fd_model* m, Exec* e) {
+    const ModelPlan& P = m->plan;
+    e->ov_layers = -1;
+    if (!e->segs.empty() || e->n < 16 || e->n % 4) return FD_OK;
+    int downs = 0, depth = 0;
+    for (size_t i = 0; i < P.layers.size(); ++i) {
+        const LayerPlan& L = P.layers[i];
+        const bool down = (L.kind == LAYER_CONV && L.stride == 2) || (L.kind == LAYER_MAXPOOL && L.pool_s == 2);
+        if (down && ++downs == 2) break;
+        if (L.out_fp32 || L.upsample2x || L.kind == LAYER_COPY) return FD_OK;
+        // every tensor these layers touch must be written inside the front (or be the input frames): nothing may reach back
+        depth = static_cast<int>(i) + 1;
+    }
+    if (downs < 2 || depth < 1 || P.layers[0].kind != LAYER_CONV0) return FD_OK;
+    const int chunk = e->n / 4;
+    e->ov_conv.assign(depth, {});
+    e->ov_halo.assign(depth, {});
+    e->ov_use_halo.assign(depth, 0);
+    for (int i = 0; i < depth; ++i) {
+        if (P.layers[i].kind != LAYER_CONV) continue;
+        e->ov_conv[i].resize(4);
+        e->ov_halo[i].resize(4);
+        for (int k = 0; k < 4; ++k) {
+            char uh = 0;
+            if (int rc = prepare_conv_layer(m, e, i, chunk, k, chunk, &e->ov_conv[i][k], &e->ov_halo[i][k], &uh)) return rc;
+            if (e->ov_conv[i][k].ws_bytes) return FD_OK;  // (a split-K layer this early would need its own workspace: leave the plain path)
+            e->ov_use_halo[i] = uh;
+        }
+    }
+    e->ov_chunk = chunk;
+    e->ov_layers = depth;
+    return FD_OK;
+}
+
+static int forward_overlapping_copy(fd_model* m, Exec* e, const uint8_t* frames, int n) {
+    const ModelPlan& P = m->plan;
+    cudaStream_t s = m->stream;
+    if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+    if (!m->idle_ev) {
+        CU(cudaEventCreateWithFlags(&m->idle_ev, cudaEventDisableTiming));
+        for (cudaEvent_t& ev : m->h2d_ev) CU(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+    }
+    const size_t frame_bytes = size_t(P.net_h) * P.net_w * 3;
+    const int chunk = e->ov_chunk;
+    // everything queued on the compute stream so far (a previous pass that reads this input tensor) comes first
+    CU(cudaEventRecord(m->idle_ev, s));
+    CU(cudaStreamWaitEvent(m->copy_stream, m->idle_ev, 0));
+    for (int p = 0; p < 4; ++p) {
+        const int f0 = p * chunk, f1 = std::min(n, f0 + chunk);
+        if (f1 > f0) CU(cudaMemcpyAsync(e->frames + f0 * frame_bytes, frames + f0 * frame_bytes, (f1 - f0) * frame_bytes, cudaMemcpyHostToDevice, m->copy_stream));
+        CU(cudaEventRecord(m->h2d_ev[p], m->copy_stream));
+    }
+    for (int k = 0; k < 4; ++k) {
+        CU(cudaStreamWaitEvent(s, m->h2d_ev[k], 0));
+        for (int i = 0; i < e->ov_layers; ++i) {
+            const bool conv = P.layers[i].kind == LAYER_CONV;
+            if (int rc = launch_layer(m, e, i, k, chunk, e->ov_use_halo[i] != 0, conv ? &e->ov_conv[i][k] : nullptr, conv ? &e->ov_halo[i][k] : nullptr, s))
+                return rc;
+        }
+    }
+    if (m->use_graph && !e->graph_tail_tried) {
+        e->graph_tail_tried = true;
+        e->graph_tail = capture_layers(m, e, e->ov_layers);
+    }
+    m->last_n = n;
+    if (e->graph_tail) {
+        CU(cudaGraphLaunch(e->graph_tail, s));
+        return FD_OK;
+    }
+    return launch_layers(m, e, s, e->ov_layers);
+}
+
 int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, int on_device, int allow_resize,
               double threshold, int max_det, fd_det* out, int32_t* counts) {
+    if (m && frames && m->device >= 0 && !on_device && src_w == m->plan.net_w && src_h == m->plan.net_h && options().detect_overlap) {
+        CU(cudaSetDevice(m->device));
+        Exec* e;
+        if (int rc = get_exec(m, n, &e)) return rc;
+        if (e->ov_layers == 0)
+            if (int rc = build_overlap_plan(m, e)) return rc;
+        if (e->ov_layers > 0) {
+            if (int rc = forward_overlapping_copy(m, e, frames, n)) return rc;
+            if (int rc = fd_postprocess(m, n, threshold, max_det, nullptr)) return rc;
+            return fd_fetch(m, n, out, counts, nullptr, nullptr);
+        }
+    }
     if (int rc = fd_preprocess(m, frames, n, src_w, src_h, on_device, allow_resize, nullptr)) return rc;
     if (int rc = fd_forward(m, n, nullptr)) return rc;
     if (int rc = fd_postprocess(m, n, threshold, max_det, nullptr)) return rc;

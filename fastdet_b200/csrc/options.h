@@ -22,11 +22,12 @@ struct Options {
     int exact_batch = 0;      // one execution state per exact batch size instead of per bucket
     int nms_general = 0;      // force the general (global-memory) Soft-NMS loop
     int jpeg_threads = 0;     // host threads of the JPEG entropy decoder; 0 = all hardware threads (max 64)
-    int chunk_frames = 0;     // the leading layers run in chunks of this many frames (twice as many in the second segment) so a chunk's
-                              // activations stay in L2; 0 = sized from chunk_mb, -1 = no chunking
+    int chunk_frames = -1;    // experiment kept as an option (measured SLOWER on B200): the leading layers run in chunks
+                              // of this many frames (twice as many in the second segment) so a chunk's activations stay in L2;
+                              // 0 = sized from chunk_mb, -1 = no chunking (default)
     int chunk_mb = 48;        // auto chunk size: largest tensor of a first-segment chunk at most this many MB (half of it in the second)
     int chunk_interleave = 0; // run the second chunked segment's chunk right after the first-segment chunks that feed it
-    int detect_overlap = 1;   // synchronous fd_detect copies the frames in two halves so the second overlaps conv0
+    int detect_overlap = 1;   // synchronous fd_detect: the frame copy in four pieces, overlapped with the first layers
 };
 
 Options& options();

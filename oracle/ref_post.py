@@ -166,6 +166,29 @@ def detect_from_heads(heads: Sequence[np.ndarray], frame: int, num_classes: int,
     return results, [c[0] for (_, c) in kept], [s for (s, _) in kept]
 
 
+def box_iou(a: Sequence[float], b: Sequence[float]) -> float:
+    """True IoU of two (x, y, w, h) boxes (the parity metric of BASELINE.json's north_star; NOT the reference's overlap)."""
+    iw = min(a[0] + a[2], b[0] + b[2]) - max(a[0], b[0])
+    ih = min(a[1] + a[3], b[1] + b[3]) - max(a[1], b[1])
+    if iw <= 0 or ih <= 0:
+        return 0.0
+    return iw * ih / (a[2] * a[3] + b[2] * b[3] - iw * ih)
+
+
+def detection_spread(heads_a, heads_b, num_classes: int, net_wh, threshold: float):
+    """Test aid: IoU and |dconf| of the detections two sets of head tensors (one frame each) give at the same anchor box
+    with the same class — how far two evaluations of the same network are apart in the spec's own metric."""
+    wa, ia, _ = detect_from_heads(heads_a, 0, num_classes, net_wh, threshold)
+    wb, ib, _ = detect_from_heads(heads_b, 0, num_classes, net_wh, threshold)
+    db = dict(zip(ib, wb))
+    ious, dconfs = [], []
+    for box, w in zip(ia, wa):
+        if box in db and db[box][0] == w[0]:
+            ious.append(box_iou(w[2:], db[box][2:]))
+            dconfs.append(abs(w[1] - db[box][1]))
+    return ious, dconfs
+
+
 def letterbox_u8(src: np.ndarray, net_w: int, net_h: int, fill: int = 128) -> Tuple[np.ndarray, Tuple[int, int, int, int]]:
     """Integer-exact restatement of the repo's letterbox kernel (an EXTENSION — the reference server rejects
     frames that are not already net-sized, detector.py:131-132; parity for this function is pinned only

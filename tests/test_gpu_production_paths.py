@@ -2,13 +2,13 @@
 
 The library picks a kernel form per layer and per batch-size bucket (fd_layer_exec_info): small batches take the
 im2col / split-K forms, the batch-64 serving configuration takes the strip form of the CTA-pair kernel for every 3x3
-stride-1 layer with >= 64-channel inputs (29 of YOLOv3's 75 convolutions, about half of the step's device time) and runs
-the first nine layers chunk by chunk so that a chunk's activations stay in L2.  These tests put exactly those forms under
-the CPU oracle:
+stride-1 layer with >= 64-channel inputs (29 of YOLOv3's 75 convolutions, about half of the step's device time); the
+synchronous fd_detect call runs the first four layers quarter batch by quarter batch behind the pieces of its frame copy.
+These tests put exactly those forms under the CPU oracle:
   * the strip form forced at a small batch (option strip=2), per layer, for the 416 and the 608 grids
     (strip widths W+1 = 53 / 27 / 14 and 77 / 39 / 20);
-  * the default plan at batch 8 per layer (52x52 strips by the library's own choice, conv1..conv4 in two chunks) and at
-    batch 16 for the chunked layers (conv1..conv4 in chunks of 4 frames, conv5..conv9 in chunks of 8);
+  * the default plan at batch 8 per layer (52x52 strips by the library's own choice);
+  * the optional L2-resident chunked execution of the leading layers (option chunk_frames; off by default) at batch 16;
   * the production batch 64 (rsu-416-9, BASELINE config 3): heads and detections of 8 of the 64 frames;
   * full-608 at a batch whose 76x76 layers take strips by default (BASELINE config 4's per-GPU shard, reduced);
   * the stand-alone kernel checker (csrc/dev/test_conv.cu: every kernel form against a float64 CPU loop).
@@ -52,41 +52,40 @@ def test_strip_form_forced_small_batch_per_layer(size, batch):
 
 
 def test_default_plan_batch8_per_layer():
-    """Batch 8, default options: the library itself puts the 52x52 3x3 layers on strips (88 strip tiles >= 74 CTA pairs)
-    and runs conv1..conv4 in two chunks of 4 frames; every layer's output against the oracle (the parity hook gathers a
-    chunked layer's output by replaying the segment's launches chunk by chunk)."""
+    """Batch 8, default options: the library itself puts the 52x52 3x3 layers on strips (88 strip tiles >= 74 CTA pairs);
+    every layer's output against the oracle."""
     data = modelgen.build_onnx("full", 80, 416, seed=2)
     m = _native.Model(data, 80, (416, 416), device=0)
     f = forms(m, 8)
     L = m.layers()
     strips52 = [i for i in strip_candidates(m) if L[i]["h"] == 52]
-    assert len(strips52) == 14 and all(f[i] == "tc_pair_strip" for i in strips52)
-    info = m.exec_info(8)
-    assert [e["chunk_frames"] for e in info[:5]] == [4, 4, 4, 4, 8] and all(e["launches"] == 2 for e in info[:4])
+    assert len(strips52) == 11 and all(f[i] == "tc_pair_strip" for i in strips52)
+    assert all(e["launches"] == 1 for e in m.exec_info(8))  # no chunking by default
     _check_heads(data, m, frames_for(8, 416, first_seed=150), per_layer=True)
     m.close()
 
 
 def test_chunked_segments_batch16_per_layer():
-    """Batch 16, default options: both leading segments are chunked (conv1..conv4: 4 chunks of 4 frames; conv5..conv9:
-    2 chunks of 8) — the layer outputs of the chunked region and the heads against the oracle, and the same heads bit
-    for bit with chunking switched off (a chunk runs the same kernels on the same frames)."""
+    """Option chunk_frames=0 (auto-sized L2-resident chunks; off by default because it measured slower), batch 16: both
+    leading segments are chunked (conv1..conv4: 4 chunks of 4 frames; conv5..conv9: 2 chunks of 8) — the layer outputs of
+    the chunked region (the parity hook replays the segment's launches chunk by chunk) and the heads against the oracle,
+    and the same heads bit for bit as the default plan (a chunk runs the same kernels on the same frames)."""
     data = modelgen.build_onnx("full", 80, 416, seed=2)
-    m = _native.Model(data, 80, (416, 416), device=0)
-    info = m.exec_info(16)
-    assert [e["chunk_frames"] for e in info[:10]] == [4, 4, 4, 4, 8, 8, 8, 8, 8, 16]
-    assert [e["launches"] for e in info[:10]] == [4, 4, 4, 4, 2, 2, 2, 2, 2, 1]
     frames = frames_for(16, 416, first_seed=170)
-    got, _ = _check_heads(data, m, frames, per_layer=True, layers=range(10))
-    m.close()
-    with _native.option("chunk_frames", -1):
-        m2 = _native.Model(data, 80, (416, 416), device=0)
-        assert all(e["launches"] == 1 for e in m2.exec_info(16))
-        m2.preprocess(frames, 16, (416, 416))
-        m2.forward(16)
-        for a, b in zip(got, m2.heads(16)):
-            assert np.array_equal(a, b)
-        m2.close()
+    with _native.option("chunk_frames", 0):
+        m = _native.Model(data, 80, (416, 416), device=0)
+        info = m.exec_info(16)
+        assert [e["chunk_frames"] for e in info[:10]] == [4, 4, 4, 4, 8, 8, 8, 8, 8, 16]
+        assert [e["launches"] for e in info[:10]] == [4, 4, 4, 4, 2, 2, 2, 2, 2, 1]
+        got, _ = _check_heads(data, m, frames, per_layer=True, layers=range(10))
+        m.close()
+    m2 = _native.Model(data, 80, (416, 416), device=0)
+    assert all(e["launches"] == 1 for e in m2.exec_info(16))
+    m2.preprocess(frames, 16, (416, 416))
+    m2.forward(16)
+    for a, b in zip(got, m2.heads(16)):
+        assert np.array_equal(a, b)
+    m2.close()
 
 
 def test_production_batch64_against_oracle():
@@ -99,8 +98,6 @@ def test_production_batch64_against_oracle():
     f = forms(m, 64)
     cands = strip_candidates(m)
     assert len(cands) == 29 and all(f[i] == "tc_pair_strip" for i in cands), [(i, f[i]) for i in cands]
-    info = m.exec_info(64)
-    assert [e["chunk_frames"] for e in info[:10]] == [4, 4, 4, 4, 8, 8, 8, 8, 8, 64]  # the L2-resident leading segments
     frames = frames_for(64, 416, first_seed=100)  # 64 distinct frames, seeds 100..163
     m.preprocess(frames, 64, (416, 416))
     m.forward(64)
@@ -117,22 +114,31 @@ def test_production_batch64_against_oracle():
         for g, r in zip(heads, want):
             err = np.abs(g[fidx] - r[0]).max()
             assert err <= 2e-2 * np.abs(r).max(), (fidx, err, np.abs(r).max())
+        h16 = exe16.run(x)
         t32.add(want, dets[fidx, :counts[fidx]])
-        t16.add(exe16.run(x), dets[fidx, :counts[fidx]])
+        t32.add_floor(want, h16)
+        t16.add(h16, dets[fidx, :counts[fidx]])
     t32.check("rsu bs64 vs fp32 oracle")
     t16.check("rsu bs64 vs bf16-operand oracle")
+    # the synchronous call (frame copy in four pieces overlapped with conv1..conv4 quarter by quarter, then the captured
+    # tail graph) and the pipelined pair return the very same records as the staged path above
+    d2, c2 = m.detect(frames, 0.1, max_det=512)
+    assert np.array_equal(c2, counts) and all(np.array_equal(d2[f, :c2[f]], dets[f, :counts[f]]) for f in range(64))
+    m.submit(0, frames, 0.1, max_det=512)
+    d3, c3, _ = m.collect(0)
+    assert np.array_equal(c3, counts) and all(np.array_equal(d3[f, :c3[f]], dets[f, :counts[f]]) for f in range(64))
     m.close()
 
 
 def test_full_608_batch_with_strips_against_oracle():
-    """full-608-80 (BASELINE config 4) at batch 4: the fourteen 76x76 3x3 layers (27 % of the FLOPs) take strips of
+    """full-608-80 (BASELINE config 4) at batch 4: the eleven 76x76 3x3 layers (27 % of the FLOPs) take strips of
     128 + 2*77 + 2 = 284 positions by the library's own choice; heads of every frame against the oracle."""
     data = modelgen.build_onnx("full", 80, 608, seed=2)
     m = _native.Model(data, 80, (608, 608), device=0)
     f = forms(m, 4)
     L = m.layers()
     s76 = [i for i in strip_candidates(m) if L[i]["h"] == 76]
-    assert len(s76) == 14 and all(f[i] == "tc_pair_strip" for i in s76), [(i, f[i]) for i in s76]
+    assert len(s76) == 11 and all(f[i] == "tc_pair_strip" for i in s76), [(i, f[i]) for i in s76]
     _check_heads(data, m, frames_for(4, 608, first_seed=1000))
     m.close()
 

@@ -65,14 +65,6 @@ def test_missing_input_name_is_rejected():
         ref_graph.GraphExecutor(data)
 
 
-def _iou(a, b):
-    iw = min(a[0] + a[2], b[0] + b[2]) - max(a[0], b[0])
-    ih = min(a[1] + a[3], b[1] + b[3]) - max(a[1], b[1])
-    if iw <= 0 or ih <= 0:
-        return 0.0
-    return iw * ih / (a[2] * a[3] + b[2] * b[3] - iw * ih)
-
-
 def test_bf16_operand_mode_follows_the_planner():
     """dtype="bf16": BatchNormalization folded before the rounding (both exporter forms give the same heads bit for bit
     only if the fold is the planner's), stored activations are bf16 values, heads stay fp32."""
@@ -95,20 +87,6 @@ def test_bf16_operand_mode_follows_the_planner():
     heads_bn = ref_graph.GraphExecutor(modelgen.build_onnx("tiny", 3, 96, seed=5, opts=alt), dtype="bf16").run(x)
     for a, b in zip(heads, heads_bn):
         assert np.abs(a - b).max() <= 1e-2 * np.abs(b).max()
-
-
-def _detection_spread(heads_a, heads_b, nc):
-    """IoU / |dconf| of the detections two sets of head tensors give at the same anchor box with the same class."""
-    from oracle import ref_post
-    wa, ia, _ = ref_post.detect_from_heads(heads_a, 0, nc, (416, 416), 0.1)
-    wb, ib, _ = ref_post.detect_from_heads(heads_b, 0, nc, (416, 416), 0.1)
-    db = dict(zip(ib, wb))
-    ious, dconfs = [], []
-    for box, w in zip(ia, wa):
-        if box in db and db[box][0] == w[0]:
-            ious.append(_iou(w[2:], db[box][2:]))
-            dconfs.append(abs(w[1] - db[box][1]))
-    return ious, dconfs
 
 
 def test_bf16_operand_floor():
@@ -137,7 +115,7 @@ def test_bf16_operand_floor():
             h32, h16, h16x, h16t = e32.run(x), e16.run(x), e16x.run(x), e16t.run(x)
             herr.append(max(float(np.abs(a - b).max() / np.abs(a).max()) for a, b in zip(h32, h16)))
             for key, (ha, hb) in (("fp32", (h32, h16)), ("acc64", (h16, h16x)), ("tail", (h32, h16t))):
-                i, d = _detection_spread(ha, hb, nc)
+                i, d = ref_post.detection_spread(ha, hb, nc, (416, 416), 0.1)
                 spread[key][0].extend(i)
                 spread[key][1].extend(d)
     stats = {}

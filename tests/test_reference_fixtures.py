@@ -74,8 +74,11 @@ def test_reference_images_on_device():
         assert res == det.perform_frames(pixels[n][None], threshold=0.05)[0]  # JPEG route == the reference's route
         dets, counts = det.model.detect(pixels[n][None], 0.05)
         x = ref_post.normalise(pixels[n])
-        t32.add(exe.run(x), dets[0, :counts[0]])
-        t16.add(exe16.run(x), dets[0, :counts[0]])
+        h32, h16 = exe.run(x), exe16.run(x)
+        t32.add(h32, dets[0, :counts[0]])
+        t32.add_floor(h32, h16)  # photographs drive these random-init nets harder than the synthetic frames: bounds follow the CPU floor
+        t16.add(h16, dets[0, :counts[0]])
+        t16.add_floor(h32, h16)
     assert det.jpeg_device_frames == len(NAMES) and det.jpeg_host_frames == 0
     t32.check("reference images vs fp32 oracle", min_solid=3)
     t16.check("reference images vs bf16-operand oracle", min_solid=3)
