@@ -1066,6 +1066,13 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     int swap = (d.cout > 64 && d.cout <= 128 && !d.out_fp32 && M >= 256 && O.swap) ? 1 : 0;
     if (block_n_hint == 1024) { swap = 1; block_n_hint = 0; }
     else if (block_n_hint) swap = 0;
+    // Small batches (option latency_bn, 64 or 128; 0 = off): a layer whose 256-wide tiles would occupy less than a quarter
+    // of the SMs is cut into 128 x latency_bn single-CTA tiles instead — four to eight times as many CTAs, each with a
+    // proportionally shorter main loop: the launch is as long as ONE CTA's work, and at batch 1 that is what a layer costs.
+    if (O.latency_bn && !block_n_hint && d.cout > O.latency_bn && !d.out_fp32) {
+        const long long tiles256 = ((M + 255) / 256) * ((d.cout + 255) / 256);
+        if (tiles256 * 4 <= num_sms) { swap = 0; block_n_hint = O.latency_bn; }
+    }
     if (swap) block_n_hint = 257;
     int two = -1;  // -1: decide below
     if (block_n_hint == 512) { two = 1; block_n_hint = 256; }
