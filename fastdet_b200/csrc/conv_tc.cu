@@ -1066,12 +1066,18 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     int swap = (d.cout > 64 && d.cout <= 128 && !d.out_fp32 && M >= 256 && O.swap) ? 1 : 0;
     if (block_n_hint == 1024) { swap = 1; block_n_hint = 0; }
     else if (block_n_hint) swap = 0;
-    // Small batches (option latency_bn, 64 or 128; 0 = off): a layer whose 256-wide tiles would occupy less than a quarter
-    // of the SMs is cut into 128 x latency_bn single-CTA tiles instead — four to eight times as many CTAs, each with a
-    // proportionally shorter main loop: the launch is as long as ONE CTA's work, and at batch 1 that is what a layer costs.
-    if (O.latency_bn && !block_n_hint && d.cout > O.latency_bn && !d.out_fp32) {
+    // Small batches (option latency_bn: 1 = choose, 64 / 128 = forced, 0 = off): a layer whose 256-wide tiles would occupy
+    // less than a quarter of the SMs is cut into 128 x 64 (or 128 x 128) single-CTA tiles instead — up to eight times as
+    // many CTAs, each with a proportionally shorter main loop.  A launch is as long as ONE CTA's work, and at batch 1 that
+    // is what a layer costs: full-416 batch 1 0.90 -> 0.64 ms.  64-wide tiles where they still fit the GPU in one wave,
+    // 128-wide otherwise (measured: 64 everywhere makes batch 4 slower than the 256-wide default, 128 faster).
+    if (O.latency_bn && !block_n_hint && !d.out_fp32) {
         const long long tiles256 = ((M + 255) / 256) * ((d.cout + 255) / 256);
-        if (tiles256 * 4 <= num_sms) { swap = 0; block_n_hint = O.latency_bn; }
+        if (tiles256 * 4 <= num_sms) {
+            int lb = O.latency_bn;
+            if (lb == 1) lb = ((M + BLOCK_M - 1) / BLOCK_M) * ((d.cout + 63) / 64) <= num_sms ? 64 : 128;
+            if (d.cout > lb) { swap = 0; block_n_hint = lb; }
+        }
     }
     if (swap) block_n_hint = 257;
     int two = -1;  // -1: decide below

@@ -15,7 +15,8 @@ struct Options {
     int split_k = 1;          // split long K loops when a launch cannot fill the GPU (small batches)
     int split_k_min_kb = 32;  // ... only with at least this many K blocks
     int split_k_max = 4;      // ... into at most this many parts
-    int latency_bn = 0;       // small batches: layers that would fill < 1/4 of the SMs use 128 x latency_bn single-CTA tiles (0: off)
+    int latency_bn = 1;       // small batches: layers that would fill < 1/4 of the SMs use 128 x 64 / 128 x 128 single-CTA tiles
+                              // (1: chosen per layer, 64 / 128: forced, 0: off)
     int b_resident = 1;       // keep a narrow layer's whole filter bank in shared memory
     int halo = 1;             // halo-patch kernel for 16/32/64-channel 3x3 layers on large maps
     int halo_skew = 1;        // ... with chunk planes skewed against shared-memory bank conflicts
