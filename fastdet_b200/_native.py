@@ -244,8 +244,9 @@ class Model:
         _check(lib().fd_fetch(self._h, n, _ptr(dets), _ptr(counts), _ptr(total), C.c_void_p(stream)))
         return dets, counts, total
 
-    def detect(self, frames: np.ndarray, threshold: float, allow_resize=False, max_det: int = 2048):
-        """frames: [n, h, w, 3] u8 (host).  Returns (dets[n, max_det] structured, counts[n])."""
+    def detect(self, frames: np.ndarray, threshold: float, allow_resize=False, max_det: int = 2048, with_total=False):
+        """frames: [n, h, w, 3] u8 (host).  Returns (dets[n, max_det] structured, counts[n]) and, with_total, the number of
+        detections each frame had before the cut at max_det."""
         if frames.dtype != np.uint8 or frames.ndim != 4 or frames.shape[3] != 3:
             raise ValueError("invalid image size")
         frames = np.ascontiguousarray(frames)
@@ -254,6 +255,10 @@ class Model:
         counts = np.zeros(n, np.int32)
         _check(lib().fd_detect(self._h, _ptr(frames), n, w, h, 0, int(allow_resize), float(threshold), max_det,
                                _ptr(dets), _ptr(counts)))
+        if with_total:
+            total = np.zeros(n, np.int32)
+            _check(lib().fd_fetch(self._h, n, _ptr(dets), _ptr(counts), _ptr(total), None))  # the same records again + the totals
+            return dets, counts, total
         return dets, counts
 
     # -- pipelined serving: two batches in flight, the H2D copy of one overlaps the compute of the other

@@ -429,7 +429,9 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     OnnxGraph g;
     std::string err;
     if (!onnx_parse(onnx_bytes, len, &g, &err)) return fail(FD_ERR_MODEL, "ONNX parse error: %s", err.c_str());
-    std::unique_ptr<fd_model> m(new fd_model());
+    struct Cleanup { void operator()(fd_model* p) const { fd_model_destroy(p); } };  // frees whatever a failed create had already allocated
+    std::unique_ptr<fd_model, Cleanup> m(new fd_model());
+    m->device = -1;  // until a device is attached: destroy then only frees host state
     if (!build_plan(g, net_w, net_h, num_classes, &m->plan, &err)) return fail(FD_ERR_MODEL, "unsupported ONNX graph: %s", err.c_str());
     ModelPlan& P = m->plan;
     if (P.head_layers.size() > FD_MAX_HEADS) return fail(FD_ERR_MODEL, "graph has %zu outputs (max %d)", P.head_layers.size(), FD_MAX_HEADS);
@@ -468,8 +470,8 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
         return fail(FD_ERR_CUDA, "no CUDA device available: fastdet_b200 has no CPU fallback");
     }
     if (device < 0 || device >= ndev) return fail(FD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
-    m->device = device;
     CU(cudaSetDevice(device));
+    m->device = device;
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(FD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
@@ -682,7 +684,7 @@ int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stre
     if (int rc = get_exec(m, n, &e)) return rc;
     cudaStream_t s = pick(m, stream);
     if (e->max_det != max_det || !e->h_dets) {
-        CU(cudaStreamSynchronize(s));
+        CU(cudaDeviceSynchronize());  // (rare) the record buffers may be in use on the compute or the copy stream
         cudaFree(e->dets); e->dets = nullptr;
         if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
         CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(e->n) * max_det));
@@ -813,6 +815,19 @@ int fd_detect(fd_model* m, const uint8_t* frames, int n, int src_w, int src_h, i
 
 namespace {
 
+// A submit that fails after it has queued work (a copy from the slot's pinned staging buffer, kernels on its tensors)
+// leaves the slot free (busy stays false): the queued work must have drained before the caller can reuse the slot's
+// buffers.  The error text of the failing call is kept.
+int quiesce_after_failure(fd_model* m, int rc) {
+    char keep[sizeof(g_err)];
+    memcpy(keep, g_err, sizeof(keep));
+    if (m->copy_stream) cudaStreamSynchronize(m->copy_stream);
+    if (m->stream) cudaStreamSynchronize(m->stream);
+    cudaGetLastError();
+    memcpy(g_err, keep, sizeof(keep));
+    return rc;
+}
+
 // common front of fd_submit / fd_submit_jpeg: argument checks, the Exec of this batch size, the slot's events and
 // pinned result buffers
 int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s_out) {
@@ -845,7 +860,7 @@ int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s
         S.h_count_cap = cnt_bytes;
     }
     if (e->max_det != max_det) {
-        CU(cudaStreamSynchronize(m->stream));
+        CU(cudaDeviceSynchronize());  // (rare) the record buffers may be in use on the compute or the copy stream
         cudaFree(e->dets); e->dets = nullptr;
         if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
         CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(e->n) * max_det));
@@ -1055,7 +1070,8 @@ int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, in
         return fail(FD_ERR_CUDA, "letterbox launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     }
     CU(cudaEventRecord(S.stage_free, s));
-    return slot_finish(m, e, S, n, threshold, max_det);
+    if (int rc = slot_finish(m, e, S, n, threshold, max_det)) return quiesce_after_failure(m, rc);
+    return FD_OK;
 }
 
 int fd_collect(fd_model* m, int slot, fd_det* out, int32_t* counts, int32_t* total) {
@@ -1133,9 +1149,10 @@ int fd_submit_jpeg(fd_model* m, int slot, const uint8_t* const* data, const size
     if (int rc = slot_begin(m, slot, n, max_det, &e, &sp)) return rc;
     size_t bytes = 0;
     int max_blocks = 0, sw = 0, sh = 0;
-    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;
-    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks, sw, sh)) return rc;
-    return slot_finish(m, e, *sp, n, threshold, max_det);
+    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;  // nothing queued yet
+    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks, sw, sh)) return quiesce_after_failure(m, rc);
+    if (int rc = slot_finish(m, e, *sp, n, threshold, max_det)) return quiesce_after_failure(m, rc);
+    return FD_OK;
 }
 
 int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, int n, int allow_resize, double threshold, int max_det,
@@ -1146,9 +1163,9 @@ int fd_detect_jpeg(fd_model* m, const uint8_t* const* data, const size_t* lens, 
     if (int rc = slot_begin(m, FD_MAX_SLOTS, n, max_det, &e, &sp)) return rc;
     size_t bytes = 0;
     int max_blocks = 0, sw = 0, sh = 0;
-    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;
-    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks, sw, sh)) return rc;
-    if (int rc = slot_finish(m, e, *sp, n, threshold, max_det)) return rc;
+    if (int rc = jpeg_host_stage(m, *sp, data, lens, n, allow_resize, status, &bytes, &max_blocks, &sw, &sh)) return rc;  // nothing queued yet
+    if (int rc = jpeg_device_stage(m, e, *sp, n, bytes, max_blocks, sw, sh)) return quiesce_after_failure(m, rc);
+    if (int rc = slot_finish(m, e, *sp, n, threshold, max_det)) return quiesce_after_failure(m, rc);
     return slot_collect(m, *sp, out, counts, nullptr);
 }
 

@@ -14,7 +14,9 @@ Additive extras (not in the reference): ``image_size=`` and ``device=`` keyword 
 ``perform_batch`` / ``perform_frames`` for decoded RGB frames, ``perform_stream`` (pipelined batches),
 ``perform_wire`` (results already in the server's wire format),
 ``forward_raw`` for parity tests.
-``mode`` is accepted and stored like the reference does; every mode runs on the B200 — there is no
+``max_det`` bounds the records copied back per frame (2048 by default); a frame with more detections than that is run
+again uncapped, so results never differ from the reference's (which has no cap) — with a logged warning, because it costs
+a second pass.  ``mode`` is accepted and stored like the reference does; every mode runs on the B200 — there is no
 CPU execution provider here and no fallback.
 """
 import io
@@ -175,7 +177,11 @@ class ONNXDetector(Detector):
         pixels of the frames that were passed in with source_coords=True."""
         self.ANCHORS[self.model.n_heads]  # KeyError exactly where the reference raises it (:136)
         frames = np.asarray(frames)
-        dets, counts = self.model.detect(frames, threshold, allow_resize=allow_resize, max_det=self.max_det)
+        dets, counts, total = self.model.detect(frames, threshold, allow_resize=allow_resize, max_det=self.max_det, with_total=True)
+        if (total > counts).any():
+            # the reference has no cap (at threshold 0 it returns one object per anchor box): run again with room for all
+            self.logger.warning(f'perform: {int(total.max())} detections exceed max_det={self.max_det}; re-running uncapped')
+            dets, counts = self.model.detect(frames, threshold, allow_resize=allow_resize, max_det=int(self.model.info.boxes_per_frame))
         if source_coords and allow_resize and frames.shape[1:3] != (self.image_size[1], self.image_size[0]):
             src = (frames.shape[2], frames.shape[1])
             for f in range(dets.shape[0]):

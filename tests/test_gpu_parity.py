@@ -435,6 +435,12 @@ def test_detector_interface_errors():
     # extension: letterboxed input of another size
     out = det.perform_frames(np.full((2, 480, 640, 3), 90, np.uint8), allow_resize=True)
     assert len(out) == 2
+    # no cap on the result list, like the reference: a detector built with a tiny max_det still returns everything
+    # (perform_frames notices the truncation and runs the frame again uncapped)
+    frame = modelgen.synthetic_frame(200, 416)[None]
+    full = det.perform_frames(frame, threshold=0.02)[0]
+    small = fdet.ONNXDetector(data, num_classes=80, max_det=4)
+    assert len(full) > 4 and small.perform_frames(frame, threshold=0.02)[0] == full
 
 
 def test_full_size_batch64_properties():
