@@ -479,6 +479,7 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     char cerr[256] = "";
     if (conv_tc_init(cerr, sizeof(cerr))) return fail(FD_ERR_CUDA, "conv_tc_init: %s", cerr);
     if (kernels_init()) return fail(FD_ERR_CUDA, "kernels_init failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (conv_halo_init()) return fail(FD_ERR_CUDA, "conv_halo_init failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&m->d_w, std::max<size_t>(P.weights_bf16.size(), 64) * 2));
     CU(cudaMalloc(&m->d_bias, std::max<size_t>(P.bias_f32.size(), 64) * 4));

@@ -383,19 +383,19 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
     if (L->smem_bytes > static_cast<size_t>(SMEM_LIMIT)) { if (err && errlen) snprintf(err, errlen, "conv_halo: %zu bytes of shared memory", L->smem_bytes); return -1; }
     L->grid = p.total < num_sms ? p.total : num_sms;
     L->flops = 2.0 * d.n * p.ho * p.wo * d.cout * 9.0 * d.cin;
-    static bool attr_done = false;
-    if (!attr_done) {
-        if (cudaFuncSetAttribute(conv_halo_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_halo_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_halo_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess ||
-            cudaFuncSetAttribute(conv_halo_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) != cudaSuccess) {
-            if (err && errlen) snprintf(err, errlen, "conv_halo: cudaFuncSetAttribute failed");
-            return -1;
-        }
-        attr_done = true;
-    }
     return 0;
+}
+
+// One-time per DEVICE (the attribute belongs to the device's context: a process that drives several GPUs must set it on
+// each — a once-per-process guard here made every halo launch on the second and later GPUs of fd_server fail).
+int conv_halo_init() {
+    return (cudaFuncSetAttribute(conv_halo_kernel<32, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess &&
+            cudaFuncSetAttribute(conv_halo_kernel<32, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess &&
+            cudaFuncSetAttribute(conv_halo_kernel<64, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess &&
+            cudaFuncSetAttribute(conv_halo_kernel<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess &&
+            cudaFuncSetAttribute(conv_halo_kernel<16, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT) == cudaSuccess)
+               ? 0
+               : -1;
 }
 
 int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream) {

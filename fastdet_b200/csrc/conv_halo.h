@@ -45,6 +45,8 @@ struct HaloLaunch {
     double flops;
 };
 
+// One-time per device: opt in to the large dynamic shared memory the kernels need.
+int conv_halo_init();
 bool conv_halo_supported(const HaloDesc& d);
 int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* out, char* err, size_t errlen);
 int conv_halo_launch(const HaloLaunch& L, cudaStream_t stream);

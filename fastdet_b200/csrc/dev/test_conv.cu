@@ -262,6 +262,7 @@ int main(int argc, char** argv) {
     printf("device: %s, %d SMs, cc %d.%d\n", prop.name, prop.multiProcessorCount, prop.major, prop.minor);
     char err[256] = {0};
     if (conv_tc_init(err, sizeof(err))) { printf("init failed: %s\n", err); return 2; }
+    if (conv_halo_init()) { printf("conv_halo_init failed\n"); return 2; }
     const int sms = prop.multiProcessorCount;
     int fails = 0;
     if (!strcmp(mode, "check") || !strcmp(mode, "all")) {

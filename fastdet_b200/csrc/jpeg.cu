@@ -665,7 +665,7 @@ int launch_jpeg_idct(const int16_t* coefs, const JpegFrameDev* frames, uint8_t* 
     if (n < 1 || max_blocks < 1) return -1;
     const dim3 grid((max_blocks + IDCT_BLOCKS - 1) / IDCT_BLOCKS, n);
     jpeg_idct_kernel<<<grid, IDCT_BLOCKS * 8, 0, s>>>(coefs, frames, planes, plane_stride);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 int launch_jpeg_rgb(const uint8_t* planes, size_t plane_stride, const JpegFrameDev* frames, uint8_t* rgb, int n, int h,
@@ -674,7 +674,7 @@ int launch_jpeg_rgb(const uint8_t* planes, size_t plane_stride, const JpegFrameD
     const int pairs = (w + 1) / 2;
     const dim3 grid((pairs + 63) / 64, (h + 3) / 4, n);
     jpeg_rgb_kernel<<<grid, 256, 0, s>>>(planes, plane_stride, frames, rgb, h, w);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 }  // namespace fd

@@ -57,7 +57,7 @@ int launch_maxpool(const __nv_bfloat16* in, int in_pitch, __nv_bfloat16* out, in
     const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     maxpool_kernel<<<blocks, 256, 0, s>>>(in, in_pitch, out, out_pitch, n, hi, wi, c / 8, k, stride, pad_lo, ho, wo,
                                           pad_value);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 __global__ void __launch_bounds__(256)
@@ -84,7 +84,7 @@ int launch_copy_slice(const __nv_bfloat16* in, int in_pitch, __nv_bfloat16* out,
     const long long total = 1LL * n * hi * wi * (upsample2x ? 4 : 1) * (c / 8);
     const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     copy_slice_kernel<<<blocks, 256, 0, s>>>(in, in_pitch, out, out_pitch, n, hi, wi, c / 8, upsample2x);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 __global__ void __launch_bounds__(256)
@@ -107,7 +107,7 @@ int launch_nhwc_to_nchw_f32(const void* in, int in_pitch, int in_fp32, float* ou
     const long long total = 1LL * n * c * h * w;
     const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     nhwc_to_nchw_f32_kernel<<<blocks, 256, 0, s>>>(in, in_pitch, in_fp32, out, n, h * w, c);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 __global__ void __launch_bounds__(256)
@@ -126,7 +126,7 @@ int launch_nchw_to_rows_f32(const float* in, float* out, int out_pitch, int n, i
     const long long total = 1LL * n * c * h * w;
     const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     nchw_to_rows_f32_kernel<<<blocks, 256, 0, s>>>(in, out, out_pitch, n, h * w, c);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 }  // namespace fd

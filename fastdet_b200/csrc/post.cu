@@ -128,7 +128,7 @@ int launch_decode(const HeadDesc* heads, int n_heads, int num_classes, int n, in
     const long long boxes = 1LL * n * boxes_per_frame;
     const int blocks = static_cast<int>((boxes + 255) / 256);
     decode_kernel<<<blocks, 256, 0, s>>>(p, cand, cand_count);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 // ------------------------------------------------------------------------------------ Soft-NMS
@@ -305,7 +305,7 @@ int launch_soft_nms(Candidate* cand, const int* cand_count, double* score_scratc
     const int allow_fast = options().nms_general ? 0 : 1;  // option nms_general: force the general loop (tests run both)
     soft_nms_kernel<<<n, NMS_THREADS, 0, s>>>(cand, cand_count, score_scratch, boxes_per_frame, net_w, net_h, threshold,
                                               out, out_count, total_count, max_det, allow_fast);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 }  // namespace fd

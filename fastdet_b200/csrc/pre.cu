@@ -59,7 +59,7 @@ int launch_normalise_f32_nchw(const uint8_t* frames, float* out, int n, int h, i
     const int blocks = static_cast<int>(work / 256 + 1 < 148 * 16 ? work / 256 + 1 : 148 * 16);
     if (vec) normalise_f32_nchw_kernel<<<blocks, 256, 0, s>>>(frames, out, n, hw);
     else normalise_f32_nchw_scalar_kernel<<<blocks, 256, 0, s>>>(frames, out, n, hw);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 // ------------------------------------------------------------------------------------ letterbox
@@ -119,7 +119,7 @@ int launch_letterbox_u8(const uint8_t* src, uint8_t* dst, int n, int sh, int sw,
     const long long total = 1LL * n * h * w;
     const int blocks = static_cast<int>(total / 256 + 1 < 148 * 16 ? total / 256 + 1 : 148 * 16);
     letterbox_u8_kernel<<<blocks, 256, 0, s>>>(src, dst, n, sh, sw, h, w, new_w, new_h, off_x, off_y, fill);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 // ------------------------------------------------------------------------------------ first conv
@@ -513,14 +513,14 @@ int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __
         const unsigned long long one40 = 1ULL << 40;
         conv0_ws_kernel<<<blocks, C0W_THREADS, C0W_PATCHES * C0D_PATCH_BYTES, s>>>(frames, w, bias, tm, n, h, wd, cout, act_mode, alpha,
                                                                                   (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx);
-        return cudaGetLastError() == cudaSuccess ? 0 : -1;
+        return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
     }
     // any other first layer (Cout up to 64, any pitch): CUDA cores
     const size_t smem = (256 + (C0_TH + 2) * (C0_TW + 2) * 3 + 4 + 27 * cout + cout) * sizeof(float) +
                         static_cast<size_t>(C0_TH) * C0_TW * cout * 2;
     dim3 grid((wd + C0_TW - 1) / C0_TW, (h + C0_TH - 1) / C0_TH, n);
     conv0_u8_kernel<<<grid, C0_THREADS, smem, s>>>(frames, w, bias, out, h, wd, cout, out_pitch, act, alpha);
-    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
 }
 
 }  // namespace fd

@@ -113,3 +113,23 @@ def test_two_models_co_resident_on_one_gpu_match_the_detector():
     st = srv.closed_loop(["a", "b"] * 4, np.stack(frames), seconds=1.0, warmup_seconds=0.3)
     assert st["frames"] > 50 and st["frames_per_model"]["a"] > 0 and st["frames_per_model"]["b"] > 0
     srv.close()
+
+
+@pytest.mark.gpu
+def test_lanes_on_every_visible_gpu():
+    """One process driving several GPUs (config 5): every device needs its own kernel attributes and execution state — a
+    process-wide 'already initialised' guard once made every launch on the second GPU fail.  Skipped on single-GPU boxes."""
+    n_dev = _native.device_count()
+    if n_dev < 2:
+        pytest.skip("needs at least two GPUs")
+    data = modelgen.build_onnx("tiny", 80, 416, 1)
+    devices = list(range(min(n_dev, 8)))
+    srv = DetectServer({"a": (data, 80)}, devices=devices, max_batch=8, max_det=256)
+    frame = modelgen.synthetic_frame(610, 416)
+    want = srv.perform("a", 0, frame, 0.1)
+    assert want
+    for s_id in range(1, len(devices)):
+        assert srv.perform("a", s_id, frame, 0.1) == want  # same frame, same model, another GPU: identical records
+    st = srv.closed_loop(["a"] * (4 * len(devices)), np.stack([frame] * 2), seconds=1.0, warmup_seconds=0.5)
+    assert min(st["frames_per_device"]) > 0
+    srv.close()
