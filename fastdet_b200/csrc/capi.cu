@@ -2,7 +2,10 @@
 // (device buffers, tensor maps, captured CUDA graph) and the call sequence that stands in for
 // ONNXDetector.__init__ / perform (reference server/detector.py:108-146).
 #include <cuda_runtime.h>
+#include <execinfo.h>
 #include <math.h>
+#include <signal.h>
+#include <unistd.h>
 #include <stdarg.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -569,7 +572,23 @@ int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
     return FD_OK;
 }
 
+// developer aid (fd_set_option("segv_backtrace", 1)): a crash inside the library's host threads prints its call stack
+// (module + offset, resolvable with addr2line against the same .so) instead of dying silently under a test runner
+static void segv_backtrace_handler(int sig) {
+    void* frames[64];
+    const int n = backtrace(frames, 64);
+    const char msg[] = "fastdet_b200: fatal signal, call stack:\n";
+    if (write(2, msg, sizeof(msg) - 1) < 0) {}
+    backtrace_symbols_fd(frames, n, 2);
+    _exit(128 + sig);
+}
+
 int fd_set_option(const char* name, int value) {
+    if (name && !strcmp(name, "segv_backtrace")) {
+        signal(SIGSEGV, value ? segv_backtrace_handler : SIG_DFL);
+        signal(SIGBUS, value ? segv_backtrace_handler : SIG_DFL);
+        return FD_OK;
+    }
     int* slot = option_slot(name);
     if (!slot) return fail(FD_ERR_ARG, "fd_set_option: unknown option '%s'", name ? name : "(null)");
     *slot = value;

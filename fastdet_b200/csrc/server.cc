@@ -89,6 +89,7 @@ struct FakeBackend : Backend {
 
 struct Batch {
     uint8_t* pinned = nullptr;
+    int cap = 0;                // frames the pinned buffer holds
     int n = 0;                  // frames claimed by callers
     std::atomic<int> ready{0};  // frames copied in
     double threshold = 0.0;
@@ -112,19 +113,30 @@ struct Lane {
     Batch* open = nullptr;
     std::deque<Batch*> closed, inflight;
     std::vector<Batch*> pool, all;
+    int cur_cap = 8;  // pinned frames per new batch: doubles (up to max_batch) whenever a batch fills up, so a lane's pinned
+                      // footprint follows its load instead of being max_batch x 0.5 MB per batch from the start
     bool stop = false;
     std::thread worker;
     int64_t batches = 0, frames = 0;
 
-    Batch* fresh() {  // mu held
-        Batch* b;
-        if (!pool.empty()) { b = pool.back(); pool.pop_back(); }
-        else {
-            b = new Batch();
-            b->pinned = be->alloc_pinned(frame_bytes * max_batch);
-            b->dets.resize(static_cast<size_t>(max_batch) * max_det);
-            b->counts.resize(max_batch);
-            all.push_back(b);
+    Batch* fresh() {  // mu held; nullptr when pinned memory cannot be had
+        Batch* b = nullptr;
+        for (size_t i = 0; i < pool.size(); ++i)
+            if (pool[i]->cap >= cur_cap) { b = pool[i]; pool.erase(pool.begin() + i); break; }
+        if (!b) {
+            if (!pool.empty()) {  // recycle an object whose buffer has become too small
+                b = pool.back(); pool.pop_back();
+                be->free_pinned(b->pinned);
+                b->pinned = nullptr; b->cap = 0;
+            } else {
+                b = new Batch();
+                all.push_back(b);
+            }
+            b->pinned = be->alloc_pinned(frame_bytes * cur_cap);
+            if (!b->pinned) { pool.push_back(b); return nullptr; }
+            b->cap = cur_cap;
+            b->dets.resize(static_cast<size_t>(b->cap) * max_det);
+            b->counts.resize(b->cap);
         }
         b->n = 0; b->ready.store(0); b->rc = FD_OK; b->err.clear(); b->done = false; b->waiting = 0; b->slot = -1;
         return b;
@@ -142,7 +154,7 @@ struct Lane {
                     // device is the clock — whatever has arrived when a slot is free goes
                     if (inflight.empty() && max_delay_s > 0.0 && !stop) {
                         const double age = std::chrono::duration<double>(Clock::now() - open->t_first).count();
-                        if (age < max_delay_s && open->n < max_batch) {
+                        if (age < max_delay_s && open->n < open->cap) {
                             cv_work.wait_for(lk, std::chrono::duration<double>(max_delay_s - age));
                             continue;
                         }
@@ -233,7 +245,7 @@ int fd_server_create(const fd_server_model* models, int n_models, const int32_t*
             if (int rc = fd_model_create(models[m].onnx_bytes, models[m].len, models[m].num_classes, models[m].net_w, models[m].net_h, devices[d], &be->m))
                 return rc;  // fd_last_error() holds the reason; lanes built so far are destroyed with `s`
             std::unique_ptr<Lane> l(new Lane());
-            l->max_batch = max_batch; l->max_det = max_det; l->max_delay_s = max_delay_ms * 1e-3;
+            l->max_batch = max_batch; l->max_det = max_det; l->max_delay_s = max_delay_ms * 1e-3; l->cur_cap = std::min(8, max_batch);
             l->frame_bytes = static_cast<size_t>(be->w) * be->h * 3;
             l->be = std::move(be);
             s->lanes.push_back(std::move(l));
@@ -254,7 +266,7 @@ int fd_server_create_fake(int n_models, int n_devices, int net_w, int net_h, int
             std::unique_ptr<FakeBackend> be(new FakeBackend());
             be->w = net_w; be->h = net_h; be->device = d; be->model = m; be->latency_us = latency_us;
             std::unique_ptr<Lane> l(new Lane());
-            l->max_batch = max_batch; l->max_det = 1; l->max_delay_s = max_delay_ms * 1e-3;
+            l->max_batch = max_batch; l->max_det = 1; l->max_delay_s = max_delay_ms * 1e-3; l->cur_cap = std::min(8, max_batch);
             l->frame_bytes = static_cast<size_t>(net_w) * net_h * 3;
             l->be = std::move(be);
             s->lanes.push_back(std::move(l));
@@ -274,7 +286,7 @@ void fd_server_destroy(fd_server* s) {
     for (auto& l : s->lanes)
         if (l->worker.joinable()) l->worker.join();
     for (auto& l : s->lanes) {
-        for (Batch* b : l->all) { l->be->free_pinned(b->pinned); delete b; }
+        for (Batch* b : l->all) { if (b->pinned) l->be->free_pinned(b->pinned); delete b; }
         l->be.reset();
     }
     delete s;
@@ -291,19 +303,24 @@ int fd_server_perform(fd_server* s, int stream_id, int model, const uint8_t* fra
     int idx;
     {
         std::unique_lock<std::mutex> lk(L.mu);
-        if (L.open && (L.open->n >= L.max_batch || L.open->threshold != threshold)) {  // one threshold per batch (it is a kernel argument)
+        if (L.open && (L.open->n >= L.open->cap || L.open->threshold != threshold)) {  // one threshold per batch (it is a kernel argument)
             L.closed.push_back(L.open);
             L.open = nullptr;
         }
         if (!L.open) {
             L.open = L.fresh();
+            if (!L.open) return sfail(FD_ERR_CUDA, "fd_server_perform: pinned host memory for a micro-batch could not be allocated");
             L.open->threshold = threshold;
             L.open->t_first = Clock::now();
         }
         b = L.open;
         idx = b->n++;
         ++b->waiting;
-        if (b->n >= L.max_batch) { L.closed.push_back(b); L.open = nullptr; }
+        if (b->n >= b->cap) {  // full: it goes as it is, and the next batches get more room
+            if (b->cap < L.max_batch) L.cur_cap = std::min(L.max_batch, 2 * b->cap);
+            L.closed.push_back(b);
+            L.open = nullptr;
+        }
     }
     L.cv_work.notify_one();
     memcpy(b->pinned + static_cast<size_t>(idx) * L.frame_bytes, frame, L.frame_bytes);  // in the caller's thread: concurrent callers copy in parallel

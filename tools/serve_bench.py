@@ -27,6 +27,7 @@ sys.path.insert(0, ROOT)
 def run(gpus, streams, seconds, max_batch=64, max_delay_ms=0.0, python_clients=False, warmup=2.0, models=("full", "rsu")):
     from fastdet_b200 import _native, modelgen
     from fastdet_b200.server import DetectServer
+    _native.set_option("segv_backtrace", 1)
     have = _native.device_count()
     if have < 1:
         raise SystemExit("serve bench needs a CUDA device (there is no CPU fallback)")
