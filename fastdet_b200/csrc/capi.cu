@@ -15,6 +15,7 @@
 #include <chrono>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -137,6 +138,24 @@ struct fd_model {
 
 namespace {
 
+// One process may drive several models on one device from different threads (fd_server: a lane per model).  CUDA calls
+// that synchronise or reconfigure the whole device — cudaFree, cudaMallocHost, cudaDeviceSynchronize — conflict with a
+// stream capture that another thread has open on the same device ("operation not permitted when stream is capturing",
+// even in thread-local capture mode).  Everything rare that allocates, frees or captures therefore runs under the
+// device's set-up lock; the steady-state enqueue / collect paths never take it.
+std::recursive_mutex& device_setup_mutex(int device) {
+    static std::recursive_mutex mu[64];
+    return mu[device < 0 ? 63 : (device & 63)];
+}
+#define DEVICE_SETUP_LOCK(m) std::lock_guard<std::recursive_mutex> device_setup_lock_((device_setup_mutex((m)->device)))
+
+// the two streams a model owns (never the whole device: another model's thread may be capturing on it)
+int sync_model_streams(fd_model* m) {
+    if (m->copy_stream) CU(cudaStreamSynchronize(m->copy_stream));
+    if (m->stream) CU(cudaStreamSynchronize(m->stream));
+    return FD_OK;
+}
+
 size_t buf_bytes(const BufferPlan& b, int n) { return size_t(n) * b.h * b.w * b.pitch * (b.fp32 ? 4 : 2); }
 
 void free_exec(Exec* e) {
@@ -249,6 +268,7 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
     const int n = bucket_of(n_frames);
     auto it = m->execs.find(n);
     if (it != m->execs.end()) { *out = it->second.get(); return FD_OK; }
+    DEVICE_SETUP_LOCK(m);
     std::unique_ptr<Exec> e(new Exec());
     e->n = n;
     const ModelPlan& P = m->plan;
@@ -405,6 +425,9 @@ cudaStream_t pick(fd_model* m, void* stream) { return stream ? static_cast<cudaS
 
 int ensure_scratch(Exec* e, size_t bytes) {
     if (e->scratch_cap >= bytes) return FD_OK;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    std::lock_guard<std::recursive_mutex> lk(device_setup_mutex(dev));
     cudaFree(e->scratch);
     e->scratch = nullptr; e->scratch_cap = 0;
     CU(cudaMalloc(&e->scratch, bytes));
@@ -413,6 +436,18 @@ int ensure_scratch(Exec* e, size_t bytes) {
 }
 
 }  // namespace
+
+// library-internal (csrc/server.cc): pinned host memory under the device's set-up lock
+void* fd_internal_pinned_alloc(int device, size_t bytes) {
+    std::lock_guard<std::recursive_mutex> lk(device_setup_mutex(device));
+    void* p = nullptr;
+    if (cudaSetDevice(device) != cudaSuccess || cudaMallocHost(&p, bytes) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+void fd_internal_pinned_free(int device, void* p) {
+    std::lock_guard<std::recursive_mutex> lk(device_setup_mutex(device));
+    cudaFreeHost(p);
+}
 
 extern "C" {
 
@@ -475,6 +510,7 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     if (device < 0 || device >= ndev) return fail(FD_ERR_ARG, "device %d out of range (have %d)", device, ndev);
     CU(cudaSetDevice(device));
     m->device = device;
+    DEVICE_SETUP_LOCK(m);
     cudaDeviceProp prop;
     CU(cudaGetDeviceProperties(&prop, device));
     if (prop.major != 10) return fail(FD_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a (B200) only", device, prop.major, prop.minor);
@@ -501,7 +537,8 @@ void fd_model_destroy(fd_model* m) {
     if (!m) return;
     if (m->device < 0) { delete m; return; }
     cudaSetDevice(m->device);
-    cudaDeviceSynchronize();
+    DEVICE_SETUP_LOCK(m);
+    sync_model_streams(m);
     for (auto& kv : m->execs) free_exec(kv.second.get());
     cudaFree(m->d_w); cudaFree(m->d_bias); cudaFree(m->d_conv0);
     for (Slot& S : m->slots) {
@@ -621,6 +658,8 @@ int fd_preprocess(fd_model* m, const uint8_t* frames, int n, int src_w, int src_
         const uint8_t* src = frames;
         if (!on_device) {
             if (e->src_cap < bytes) {
+                DEVICE_SETUP_LOCK(m);
+                if (int rc = sync_model_streams(m)) return rc;
                 cudaFree(e->src); e->src = nullptr; e->src_cap = 0;
                 CU(cudaMalloc(&e->src, bytes));
                 e->src_cap = bytes;
@@ -636,6 +675,7 @@ int fd_preprocess(fd_model* m, const uint8_t* frames, int n, int src_w, int src_
 
 // the layers from `from_layer` on as an instantiated CUDA graph (nullptr if capture is not possible: callers then launch directly)
 static cudaGraphExec_t capture_layers(fd_model* m, Exec* e, int from_layer) {
+    DEVICE_SETUP_LOCK(m);
     cudaGraph_t graph = nullptr;
     cudaGraphExec_t exec = nullptr;
     if (cudaStreamBeginCapture(m->stream, cudaStreamCaptureModeThreadLocal) == cudaSuccess) {
@@ -704,7 +744,8 @@ int fd_postprocess(fd_model* m, int n, double threshold, int max_det, void* stre
     if (int rc = get_exec(m, n, &e)) return rc;
     cudaStream_t s = pick(m, stream);
     if (e->max_det != max_det || !e->h_dets) {
-        CU(cudaDeviceSynchronize());  // (rare) the record buffers may be in use on the compute or the copy stream
+        DEVICE_SETUP_LOCK(m);
+        if (int rc = sync_model_streams(m)) return rc;  // (rare) the record buffers may be in use on the compute or the copy stream
         cudaFree(e->dets); e->dets = nullptr;
         if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
         CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(e->n) * max_det));
@@ -848,6 +889,8 @@ int quiesce_after_failure(fd_model* m, int rc) {
     return rc;
 }
 
+int slot_begin_resize(fd_model* m, Exec* e, Slot& S, int n, int max_det, Exec** e_out, Slot** s_out);
+
 // common front of fd_submit / fd_submit_jpeg: argument checks, the Exec of this batch size, the slot's events and
 // pinned result buffers
 int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s_out) {
@@ -860,12 +903,26 @@ int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s
     if (S.busy) return fail(FD_ERR_ARG, "slot %d still holds uncollected results", slot);
     Exec* e;
     if (int rc = get_exec(m, n, &e)) return rc;
-    if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
-    if (!S.staged) {
-        CU(cudaEventCreateWithFlags(&S.staged, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&S.stage_free, cudaEventDisableTiming));
-        CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+    if (!m->copy_stream || !S.staged) {
+        DEVICE_SETUP_LOCK(m);
+        if (!m->copy_stream) CU(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        if (!S.staged) {
+            CU(cudaEventCreateWithFlags(&S.staged, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&S.stage_free, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&S.done, cudaEventDisableTiming));
+        }
     }
+    if (S.h_dets_cap < sizeof(Detection) * size_t(n) * max_det || S.h_count_cap < sizeof(int) * 2 * size_t(n) || e->max_det != max_det) {
+        DEVICE_SETUP_LOCK(m);
+        return slot_begin_resize(m, e, S, n, max_det, e_out, s_out);
+    }
+    *e_out = e;
+    *s_out = &S;
+    return FD_OK;
+}
+
+// (rare) the slot's pinned result buffers or the Exec's record buffer have to grow: under the device's set-up lock
+int slot_begin_resize(fd_model* m, Exec* e, Slot& S, int n, int max_det, Exec** e_out, Slot** s_out) {
     const size_t det_bytes = sizeof(Detection) * size_t(n) * max_det, cnt_bytes = sizeof(int) * 2 * size_t(n);
     if (S.h_dets_cap < det_bytes) {
         if (S.h_dets) cudaFreeHost(S.h_dets);
@@ -880,7 +937,7 @@ int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s
         S.h_count_cap = cnt_bytes;
     }
     if (e->max_det != max_det) {
-        CU(cudaDeviceSynchronize());  // (rare) the record buffers may be in use on the compute or the copy stream
+        if (int rc = sync_model_streams(m)) return rc;  // the record buffers may be in use on the compute or the copy stream
         cudaFree(e->dets); e->dets = nullptr;
         if (e->h_dets) { cudaFreeHost(e->h_dets); e->h_dets = nullptr; }
         CU(cudaMalloc(&e->dets, sizeof(Detection) * size_t(e->n) * max_det));
@@ -891,9 +948,10 @@ int slot_begin(fd_model* m, int slot, int n, int max_det, Exec** e_out, Slot** s
     return FD_OK;
 }
 
-int slot_stage_reserve(Slot& S, size_t bytes) {
+int slot_stage_reserve(fd_model* m, Slot& S, size_t bytes) {
     if (S.stage_cap >= bytes) return FD_OK;
-    CU(cudaDeviceSynchronize());
+    DEVICE_SETUP_LOCK(m);
+    if (int rc = sync_model_streams(m)) return rc;
     cudaFree(S.stage); S.stage = nullptr; S.stage_cap = 0;
     CU(cudaMalloc(&S.stage, bytes));
     S.stage_cap = bytes;
@@ -976,6 +1034,7 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
     }
     if (off[n] > 0xffffffffull * 2) return fail(FD_ERR_ARG, "JPEG batch too large");
     if (S.h_stage_cap < off[n]) {
+        DEVICE_SETUP_LOCK(m);
         if (S.h_stage) {
             CU(cudaStreamSynchronize(m->copy_stream));
             cudaFreeHost(S.h_stage);
@@ -1019,14 +1078,15 @@ int jpeg_host_stage(fd_model* m, Slot& S, const uint8_t* const* data, const size
 // ending with RGB u8 frames in the Exec's input tensor (where fd_preprocess would have put them).
 int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int max_blocks, int src_w, int src_h) {
     const ModelPlan& P = m->plan;
-    if (int rc = slot_stage_reserve(S, bytes)) return rc;
+    if (int rc = slot_stage_reserve(m, S, bytes)) return rc;
     const bool same = src_w == P.net_w && src_h == P.net_h;
     const size_t plane_stride = size_t(3) * ((src_w + 15) / 16 * 16) * ((src_h + 15) / 16 * 16);
     uint8_t* rgb = e->frames;
     if (!same) {  // decode at the source size, then the letterbox of fd_preprocess
         const size_t src_bytes = size_t(n) * src_w * src_h * 3;
         if (e->src_cap < src_bytes) {
-            CU(cudaDeviceSynchronize());
+            DEVICE_SETUP_LOCK(m);
+            if (int rc = sync_model_streams(m)) return rc;
             cudaFree(e->src); e->src = nullptr; e->src_cap = 0;
             CU(cudaMalloc(&e->src, src_bytes));
             e->src_cap = src_bytes;
@@ -1034,7 +1094,8 @@ int jpeg_device_stage(fd_model* m, Exec* e, Slot& S, int n, size_t bytes, int ma
         rgb = e->src;
     }
     if (m->jpeg_planes_cap < plane_stride * n) {
-        CU(cudaDeviceSynchronize());
+        DEVICE_SETUP_LOCK(m);
+        if (int rc = sync_model_streams(m)) return rc;
         cudaFree(m->jpeg_planes); m->jpeg_planes = nullptr; m->jpeg_planes_cap = 0;
         CU(cudaMalloc(&m->jpeg_planes, plane_stride * n));
         m->jpeg_planes_cap = plane_stride * n;
@@ -1076,7 +1137,7 @@ int fd_submit(fd_model* m, int slot, const uint8_t* frames, int n, int src_w, in
     if (int rc = slot_begin(m, slot, n, max_det, &e, &sp)) return rc;
     Slot& S = *sp;
     const size_t bytes = size_t(n) * src_w * src_h * 3;
-    if (int rc = slot_stage_reserve(S, bytes)) return rc;
+    if (int rc = slot_stage_reserve(m, S, bytes)) return rc;
     cudaStream_t cs = m->copy_stream, s = m->stream;
     // copy stream: wait until the compute stream has consumed this slot's previous contents, then stage the frames
     CU(cudaStreamWaitEvent(cs, S.stage_free, 0));

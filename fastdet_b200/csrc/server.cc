@@ -29,6 +29,9 @@
 
 #include "../../include/fastdet_b200.h"
 
+void* fd_internal_pinned_alloc(int device, size_t bytes);  // capi.cu
+void fd_internal_pinned_free(int device, void* p);
+
 namespace {
 
 using Clock = std::chrono::steady_clock;
@@ -51,12 +54,9 @@ struct ModelBackend : Backend {
         return fd_submit(m, slot, frames, n, w, h, 0, 0, thr, max_det);
     }
     int collect(int slot, fd_det* out, int32_t* counts) override { return fd_collect(m, slot, out, counts, nullptr); }
-    uint8_t* alloc_pinned(size_t bytes) override {
-        void* p = nullptr;
-        cudaSetDevice(device);
-        return cudaMallocHost(&p, bytes) == cudaSuccess ? static_cast<uint8_t*>(p) : nullptr;
-    }
-    void free_pinned(uint8_t* p) override { cudaFreeHost(p); }
+    // (under the device's set-up lock: a pinned allocation must not run into another lane's graph capture, capi.cu)
+    uint8_t* alloc_pinned(size_t bytes) override { return static_cast<uint8_t*>(fd_internal_pinned_alloc(device, bytes)); }
+    void free_pinned(uint8_t* p) override { fd_internal_pinned_free(device, p); }
 };
 
 // Host-only stand-in (tests of the routing / batching logic on machines without a GPU): "detects" one box per frame
