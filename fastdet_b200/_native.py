@@ -115,6 +115,7 @@ _PROTOS = {
     "fd_server_destroy": (None, [C.c_void_p]),
     "fd_server_perform": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_void_p, C.c_int,
                                     C.POINTER(C.c_int32)]),
+    "fd_server_warm": (C.c_int, [C.c_void_p, C.c_int]),
     "fd_server_lane_stats": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]),
     "fd_server_closed_loop": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double,
                                         C.c_double, C.c_double, C.POINTER(FdServeStats)]),

@@ -97,6 +97,10 @@ class DetectServer:
         """The reference's result list for one decoded frame: [(klass, conf, x, y, w, h), ...] (detector.py:142-144)."""
         return self.perform_records(model, stream_id, frame, threshold)[["klass", "conf", "x", "y", "w", "h"]].tolist()
 
+    def warm(self, up_to=64):
+        """Builds every lane's execution state for batches of up to `up_to` frames now (seconds), so no request ever does."""
+        self._check(_native.lib().fd_server_warm(self._h, int(up_to)))
+
     def lane_stats(self):
         out = {}
         b, f = C.c_int64(), C.c_int64()

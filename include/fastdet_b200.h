@@ -244,6 +244,9 @@ void fd_server_destroy(fd_server* s);
  * model's (FD_ERR_SIZE otherwise, reference detector.py:132).  out[max_det], *count: the frame's records. */
 int fd_server_perform(fd_server* s, int stream_id, int model, const uint8_t* frame, int src_w, int src_h, double threshold,
                       fd_det* out, int max_det, int32_t* count);
+/* Build every lane's execution state for the batch-size buckets up to `up_to` frames now (in parallel over the lanes), so
+ * that no request pays for buffer allocation and graph capture later.  Call before serving. */
+int fd_server_warm(fd_server* s, int up_to);
 int fd_server_lane_stats(fd_server* s, int device_slot, int model, int64_t* batches, int64_t* frames);
 /* Load generator (measurement tool): n_streams caller threads, stream i -> model stream_model[i] and device slot
  * i % n_devices, each sending its next frame (from frames[n_frames][src_h][src_w][3], host) as soon as the previous result

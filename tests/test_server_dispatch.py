@@ -72,6 +72,7 @@ def test_thresholds_do_not_share_a_batch_and_slots_alternate():
 
 def test_closed_loop_generator_statistics():
     srv = DetectServer.fake(n_models=2, n_devices=4, max_batch=16, latency_us=500)
+    srv.warm(16)
     frames = np.stack([_frame(i) for i in range(5)])
     st = srv.closed_loop([i % 2 for i in range(16)], frames, seconds=0.5, warmup_seconds=0.1)
     assert st["streams"] == 16 and st["frames"] > 100 and st["detections"] == st["frames"]
@@ -89,6 +90,7 @@ def test_two_models_co_resident_on_one_gpu_match_the_detector():
     full = modelgen.build_onnx("tiny", 80, 416, 1)
     rsu = modelgen.build_onnx("tiny", 9, 416, 4)
     srv = DetectServer({"a": (full, 80), "b": (rsu, 9)}, devices=[0], max_batch=8, max_det=256, max_delay_ms=20.0)
+    srv.warm(8)
     frames = [modelgen.synthetic_frame(600 + i, 416) for i in range(6)]
     out = {}
 

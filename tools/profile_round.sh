@@ -5,7 +5,7 @@
 # then, on the build box: python tools/summarize_profiles.py <tag> gpurun_out/layers_<x>.json
 tag=${1:-x}
 mkdir -p gpurun_out
-CMD="python bench.py --steps 2 --warmup 3 --quick"
+CMD="python bench.py --steps 2 --warmup 3 --quick --no-parity"
 $CMD > gpurun_out/plain_$tag.log 2> gpurun_out/plain_${tag}_err.log || { echo "plain run failed"; tail -5 gpurun_out/plain_${tag}_err.log; exit 1; }
 tail -c 600 gpurun_out/plain_$tag.log
 # warm-up: 3 bench warm-ups + graph capture; skip everything before the two timed steps (77 launches each)

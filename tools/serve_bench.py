@@ -40,6 +40,7 @@ def run(gpus, streams, seconds, max_batch=64, max_delay_ms=0.0, python_clients=F
     names = list(specs)
     t0 = time.time()
     srv = DetectServer(specs, devices=range(gpus), max_batch=max_batch, max_det=256, max_delay_ms=max_delay_ms)
+    srv.warm(min(max_batch, 2 * -(-streams // (gpus * len(names)))))  # every bucket a lane can see, built before the clock starts
     load_s = time.time() - t0
     frames = np.stack([modelgen.synthetic_frame(5000 + i, 416) for i in range(32)])
     # stream s -> GPU s mod N; models alternate per GPU so every GPU serves both: stream s -> model (s // N) mod 2

@@ -24,7 +24,7 @@ for d in seg:
     a = agg.setdefault(d["name"], [0, 0.0, 0.0, 0.0]); a[0] += 1; a[1] += d["us"]
     a[2] += d.get("dram__bytes_read.sum", 0); a[3] += d.get("dram__bytes_write.sum", 0)
 tot = sum(a[1] for a in agg.values())
-out = ["# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none : python bench.py --steps 2 --warmup 3 --quick",
+out = ["# ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none : python bench.py --steps 2 --warmup 3 --quick --no-parity",
        f"# the two timed device-resident steps (2 x {per_fwd} kernel launches), full-416-80cls, batch 64, 1 B200; cold-cache serialised times: compare SHARES"]
 for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     out.append(f"{k:<30} n={a[0]:4d} {a[1]:10.1f} us {100 * a[1] / tot:5.1f}%   dram read {a[2] / 2e6:9.1f} MB/step  write {a[3] / 2e6:9.1f} MB/step")
@@ -58,7 +58,7 @@ if os.path.exists(rep):
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_requests.sum", "lts__t_sectors.sum",
             "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__cycles_elapsed.avg.per_second", "sm__cycles_elapsed.max", "sm__cycles_active.avg", "smsp__inst_executed.sum"]
-    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 : python bench.py --steps 2 --warmup 3 --quick",
+    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 : python bench.py --steps 2 --warmup 3 --quick --no-parity",
              "# four consecutive conv_tc launches of a timed step (full-416-80cls, batch 64)"]
     for j, h in enumerate(hdr):
         if h in want:
