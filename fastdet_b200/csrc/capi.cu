@@ -245,8 +245,10 @@ int prepare_conv_layer(fd_model* m, Exec* e, size_t i, int frames, int k, int ch
         h.w = m->d_w + L.w_off; h.bias_host = P.bias_f32.data() + L.b_off; h.act = L.act; h.alpha = L.alpha;
         if (res) { h.residual = res; h.res_pitch = L.res.pitch; }
         h.out = out; h.out_pitch = L.out.pitch; h.out_fp32 = L.out_fp32; h.upsample2x = L.upsample2x;
+        h.pool2 = L.pool2;
         char herr[256] = "";
         if (conv_halo_supported(h) && conv_halo_prepare(h, m->num_sms, hl, herr, sizeof(herr)) == 0) { *use_halo = 1; return FD_OK; }
+        if (L.pool2) return fail(FD_ERR_CUDA, "layer %zu (%s): its fused max-pool needs the halo-patch kernel (%s)", i, L.name.c_str(), herr);
     }
     *use_halo = 0;
     ConvDesc d;
@@ -354,7 +356,7 @@ int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, co
         case LAYER_CONV0:
             rc = launch_conv0_u8(e->frames + static_cast<size_t>(k) * chunk * P.net_h * P.net_w * 3, m->d_conv0 + L.w_off, m->d_bias + L.b_off,
                                  static_cast<__nv_bfloat16*>(loc_ptr(*e, P, L.out, false, k, chunk)), frames, L.in.h, L.in.w, L.cout,
-                                 L.out.pitch, L.act, L.alpha, s);
+                                 L.out.pitch, L.act, L.alpha, L.pool2, s);
             break;
         case LAYER_CONV: rc = halo ? conv_halo_launch(*hl, s) : conv_tc_launch(*cl, s); break;
         case LAYER_MAXPOOL:
@@ -470,7 +472,7 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     struct Cleanup { void operator()(fd_model* p) const { fd_model_destroy(p); } };  // frees whatever a failed create had already allocated
     std::unique_ptr<fd_model, Cleanup> m(new fd_model());
     m->device = -1;  // until a device is attached: destroy then only frees host state
-    if (!build_plan(g, net_w, net_h, num_classes, &m->plan, &err)) return fail(FD_ERR_MODEL, "unsupported ONNX graph: %s", err.c_str());
+    if (!build_plan(g, net_w, net_h, num_classes, options().fuse_pool && options().halo, &m->plan, &err)) return fail(FD_ERR_MODEL, "unsupported ONNX graph: %s", err.c_str());
     ModelPlan& P = m->plan;
     if (P.head_layers.size() > FD_MAX_HEADS) return fail(FD_ERR_MODEL, "graph has %zu outputs (max %d)", P.head_layers.size(), FD_MAX_HEADS);
 

@@ -72,6 +72,10 @@ __device__ __forceinline__ uint32_t pack2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 __device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
     const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
     return *reinterpret_cast<const uint32_t*>(&r);
@@ -283,20 +287,34 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
 #pragma unroll
                     for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
                 }
+                // MaxPool(2, 2) in place: lane = (row lane >> 3, column lane & 7) of the warp's 4 x 8 pixels, so a 2x2 window is
+                // lanes l, l^1, l^8, l^9; the lane with even row and even column keeps the maximum (bf16 max is exact)
+                if (p.pool2) {
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) {
+                        uint32_t v = max_bf16x2(pk[g], __shfl_xor_sync(0xffffffffu, pk[g], 1));
+                        pk[g] = max_bf16x2(v, __shfl_xor_sync(0xffffffffu, v, 8));
+                    }
+                }
                 // 32 pixels x 64 B with the 64-byte swizzle (chunk c of row r at slot c ^ ((r >> 1) & 3)): a SWIZZLE_64B box
                 uint8_t* so = stage + ((rotate ? sbuf : (c0 >> 5)) & 1) * 2048;
                 if (rotate) {
                     if (lane == 0) ptx::tma_store_wait_read<1>();  // the store that used this buffer two chunks ago is done with it
                     __syncwarp();
                 }
+                // pooled: the 8 surviving pixels [2 rows][4 columns] are rows 0..7 of the (smaller) box
+                const int srow = p.pool2 ? ((lane >> 4) * 4 + ((lane & 7) >> 1)) : lane;
+                if (!p.pool2 || (lane & 9) == 0) {
 #pragma unroll
-                for (int c = 0; c < 4; ++c)
-                    *reinterpret_cast<uint4*>(so + lane * 64 + ((c ^ ((lane >> 1) & 3)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    for (int c = 0; c < 4; ++c)
+                        *reinterpret_cast<uint4*>(so + srow * 64 + ((c ^ ((srow >> 1) & 3)) << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                }
                 if (rotate) {
                     ptx::fence_proxy_async();
                     __syncwarp();
                     if (lane == 0) {
-                        ptx::tma_store_4d(&tm_out, so, c0, tx * TW, ty * TH + 4 * quarter, f);
+                        if (p.pool2) ptx::tma_store_4d(&tm_out, so, c0, tx * (TW / 2), ty * (TH / 2) + 2 * quarter, f);
+                        else ptx::tma_store_4d(&tm_out, so, c0, tx * TW, ty * TH + 4 * quarter, f);
                         ptx::tma_store_commit();
                     }
                     ++sbuf;
@@ -306,8 +324,10 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                 ptx::fence_proxy_async();
                 __syncwarp();
                 if (lane == 0) {
-                    for (int c0 = 0; c0 < cout; c0 += 32)
-                        ptx::tma_store_4d(&tm_out, stage + (c0 >> 5) * 2048, c0, tx * TW, ty * TH + 4 * quarter, f);  // clipped at the edges
+                    for (int c0 = 0; c0 < cout; c0 += 32) {
+                        if (p.pool2) ptx::tma_store_4d(&tm_out, stage + (c0 >> 5) * 2048, c0, tx * (TW / 2), ty * (TH / 2) + 2 * quarter, f);
+                        else ptx::tma_store_4d(&tm_out, stage + (c0 >> 5) * 2048, c0, tx * TW, ty * TH + 4 * quarter, f);  // clipped at the edges
+                    }
                     ptx::tma_store_commit();
                 }
             }
@@ -337,6 +357,7 @@ bool conv_halo_supported(const HaloDesc& d) {
     if (!options().halo) return false;
     if (!(d.cin == 64 || d.cin == 32 || d.cin == 16) || d.ksize != 3 || d.pad_lo != 1 || d.pad_hi > 1 || !(d.stride == 1 || d.stride == 2)) return false;
     if (!(d.cout == 32 || d.cout == 64 || d.cout == 128) || d.out_fp32 || d.upsample2x) return false;
+    if (d.pool2 && (d.stride != 1 || d.residual || d.hi % 2 || d.wi % 2 || d.pad_hi != 1)) return false;
     if (d.cin == 64 && d.stride != 1) return false;  // the 78 KB stride-2 patch does not fit next to the resident filters
     if (d.in_pitch % 8 || d.out_pitch % 8 || (reinterpret_cast<uintptr_t>(d.in) & 15) || (reinterpret_cast<uintptr_t>(d.out) & 15) ||
         (reinterpret_cast<uintptr_t>(d.w) & 15))
@@ -361,6 +382,7 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
     p.act = d.act ? ((d.alpha >= 0.f && d.alpha <= 1.f) ? 1 : 2) : 0;
     p.alpha = d.alpha;
     p.residual = d.residual; p.res_pitch = d.res_pitch;
+    p.pool2 = d.pool2;
     p.tiles_x = (p.wo + TW - 1) / TW;
     p.tiles_y = (p.ho + TH - 1) / TH;
     p.per_frame = p.tiles_x * p.tiles_y;
@@ -370,10 +392,12 @@ int conv_halo_prepare(const HaloDesc& d, int num_sms, HaloLaunch* L, char* err, 
     p.m_tiles_x = (one40 + p.tiles_x - 1) / p.tiles_x;
     memset(p.bias_c, 0, sizeof(p.bias_c));
     memcpy(p.bias_c, d.bias_host, sizeof(float) * d.cout);
-    const unsigned long long dims[4] = {static_cast<unsigned long long>(d.cout), static_cast<unsigned long long>(p.wo),
-                                        static_cast<unsigned long long>(p.ho), static_cast<unsigned long long>(d.n)};
-    const unsigned long long strides[3] = {2ULL * d.out_pitch, 2ULL * d.out_pitch * p.wo, 2ULL * d.out_pitch * p.wo * p.ho};
-    const unsigned box[4] = {32, TW, 4, 1};
+    // output map: the conv's (ho, wo) grid, or the pooled (ho/2, wo/2) one; a warp's box = its 4 x 8 pixels (2 x 4 pooled)
+    const int oh = d.pool2 ? p.ho / 2 : p.ho, ow = d.pool2 ? p.wo / 2 : p.wo;
+    const unsigned long long dims[4] = {static_cast<unsigned long long>(d.cout), static_cast<unsigned long long>(ow),
+                                        static_cast<unsigned long long>(oh), static_cast<unsigned long long>(d.n)};
+    const unsigned long long strides[3] = {2ULL * d.out_pitch, 2ULL * d.out_pitch * ow, 2ULL * d.out_pitch * ow * oh};
+    const unsigned box[4] = {32, d.pool2 ? TW / 2u : TW, d.pool2 ? 2u : 4u, 1};
     if (encode_tiled_bf16(&L->tm_out, d.out, 4, dims, strides, box, 2)) { if (err && errlen) snprintf(err, errlen, "conv_halo: output tensor map encode failed"); return -1; }
     L->stride = d.stride;
     L->cin = d.cin;

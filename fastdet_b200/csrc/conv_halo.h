@@ -19,6 +19,7 @@ struct HaloDesc {  // same meaning as ConvDesc (conv_tc.h)
     int res_pitch;
     void* out;
     int out_pitch, out_fp32, upsample2x;
+    int pool2;  // 1: MaxPool(2, stride 2) of the activation in the epilogue; `out` is the (ho/2, wo/2) map
 };
 
 struct HaloParams {
@@ -32,6 +33,7 @@ struct HaloParams {
     const __nv_bfloat16* residual;
     long long res_pitch;
     int tiles_x, tiles_y, per_frame, total;
+    int pool2;
     int plane_bytes, slots;  // chunk-plane stride and patch ring depth (conv_halo.cu: Plane / Ring)
     unsigned long long m_per_frame, m_tiles_x;  // ceil(2^40 / d): x / d == (x * m) >> 40 for the ranges checked on the host
     float bias_c[128];

@@ -33,6 +33,7 @@ static float bf16r(float x) { return __bfloat162float(__float2bfloat16(x)); }
 struct Case {
     const char* name;
     int n, h, w, cin, cout, k, stride, pad_lo, pad_hi, act, residual, fp32, upsample, in_pitch_extra, block_n;
+    int pool;  // 1: MaxPool(2, 2) fused into the epilogue (halo-patch kernel only); omitted = 0
 };
 
 static int run_case(const Case& c, int num_sms) {
@@ -42,7 +43,7 @@ static int run_case(const Case& c, int num_sms) {
     const long long M = 1LL * c.n * ho * wo;
     const int K = c.k * c.k * c.cin;
     const int out_pitch = c.fp32 ? ((c.cout + 15) / 16) * 16 : c.cout + 8;  // exercise pitch != cout
-    const int oh = c.upsample ? 2 * ho : ho, ow = c.upsample ? 2 * wo : wo;
+    const int oh = c.upsample ? 2 * ho : (c.pool ? ho / 2 : ho), ow = c.upsample ? 2 * wo : (c.pool ? wo / 2 : wo);
 
     std::vector<float> x(1LL * c.n * c.h * c.w * in_pitch), wt(1LL * c.cout * K), bias(1024, 0.f),
         res(c.residual ? M * c.cout : 0);
@@ -91,6 +92,7 @@ static int run_case(const Case& c, int num_sms) {
         hd.cout = d.cout; hd.ksize = d.ksize; hd.stride = d.stride; hd.pad_lo = d.pad_lo; hd.pad_hi = d.pad_hi;
         hd.w = d.w; hd.bias_host = d.bias_host; hd.act = d.act; hd.alpha = d.alpha;
         hd.residual = d.residual; hd.res_pitch = d.res_pitch; hd.out = d.out; hd.out_pitch = d.out_pitch;
+        hd.pool2 = c.pool;
         static HaloLaunch H;
         if (conv_halo_prepare(hd, num_sms, &H, err, sizeof(err))) { printf("[%s] halo prepare failed: %s\n", c.name, err); return 1; }
         if (conv_halo_launch(H, 0)) { printf("[%s] halo launch failed: %s\n", c.name, cudaGetErrorString(cudaGetLastError())); return 1; }
@@ -128,6 +130,7 @@ static int run_case(const Case& c, int num_sms) {
     double max_err = 0, max_ref = 0;
     long long bad = 0, first_bad_m = -1;
     int first_bad_n = -1;
+    std::vector<double> pooled(c.pool ? 1ULL * c.n * oh * ow * c.cout : 0, -1e300);
     for (long long m = 0; m < M; ++m) {
         const int img = (int)(m / (ho * wo));
         const int rem = (int)(m % (ho * wo));
@@ -145,6 +148,11 @@ static int run_case(const Case& c, int num_sms) {
             double v = acc + bias[co];
             if (c.act) v = v > 0 ? v : v * 0.1f;
             if (c.residual) v += res[m * c.cout + co];
+            if (c.pool) {  // compared after the loop: maximum over the 2x2 window
+                double& pm = pooled[((1ULL * img * oh + oy / 2) * ow + ox / 2) * c.cout + co];
+                if (v > pm) pm = v;
+                continue;
+            }
             const int ndst = c.upsample ? 4 : 1;
             for (int dd = 0; dd < ndst; ++dd) {
                 long long row = m;
@@ -162,6 +170,16 @@ static int run_case(const Case& c, int num_sms) {
                 if (fabs(v) > max_ref) max_ref = fabs(v);
             }
         }
+    }
+    for (size_t i = 0; i < pooled.size(); ++i) {
+        const long long row = static_cast<long long>(i / c.cout);
+        const int co = static_cast<int>(i % c.cout);
+        const double v = pooled[i];
+        const float got = __bfloat162float(reinterpret_cast<__nv_bfloat16*>(hout.data())[row * out_pitch + co]);
+        const double er = fabs(double(got) - v);
+        if (!(er <= 2e-2 + 1e-2 * fabs(v))) { if (bad == 0) { first_bad_m = row; first_bad_n = co; } ++bad; }
+        if (er > max_err || er != er) max_err = er;
+        if (fabs(v) > max_ref) max_ref = fabs(v);
     }
     // untouched padding channels of a bf16 slice must still hold the 0xFF fill
     long long clobbered = 0;
@@ -320,6 +338,11 @@ int main(int argc, char** argv) {
             {"halo 3x3 64->64 s1",      1, 64, 64, 64, 64, 3, 1, 1, 1, 1, 0, 0, 0, 64, 2048},
             {"halo 3x3 16->64 s2 res",  1, 130, 128, 16, 64, 3, 2, 1, 1, 1, 1, 0, 0, 16, 2048},
             {"1x1 48->64 (bk16)",       1, 20, 20, 48, 64, 1, 1, 0, 0, 1, 0, 0, 0, 16, 0},
+            // MaxPool(2, 2) fused into the halo-patch kernel's epilogue (YOLOv3-tiny: conv2 / conv3), incl. a map that is not a
+            // multiple of the 16 x 8 tile and the rotating-buffer form (Cout 128)
+            {"halo 3x3 16->32 pool",    2, 72, 68, 16, 32, 3, 1, 1, 1, 1, 0, 0, 0, 0, 2048, 1},
+            {"halo 3x3 32->64 pool",    1, 104, 104, 32, 64, 3, 1, 1, 1, 1, 0, 0, 0, 0, 2048, 1},
+            {"halo 3x3 64->128 pool",   1, 64, 66, 64, 128, 3, 1, 1, 1, 0, 0, 0, 0, 8, 2048, 1},
         };
         for (const Case& c : cases) fails += run_case(c, sms);
         printf("check: %d failing case(s)\n", fails);

@@ -373,7 +373,7 @@ struct Builder {
 
 }  // namespace
 
-bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, ModelPlan* plan, std::string* err) {
+bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, bool fuse_pool, ModelPlan* plan, std::string* err) {
     Builder B(g, err);
     if (!B.walk()) return false;
     plan->net_w = net_w; plan->net_h = net_h; plan->num_classes = num_classes;
@@ -541,6 +541,18 @@ bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, Model
                 if (other != cur && other < a) { f.add = nx; f.residual = other; owner[nx] = id; cur = nx; }
             }
             if (f.kind == LAYER_CONV && (nx = sole_consumer(cur)) >= 0 && an[nx].kind == A_RESIZE) { f.resize = nx; owner[nx] = id; cur = nx; }
+            // MaxPool(2, stride 2, no padding) straight after the activation: done in the epilogue of the kernels whose tile is
+            // a 16 x 8 pixel patch (each epilogue warp holds whole 2x2 windows): the first convolution (Cout 16 / 32) and the
+            // halo-patch layers.  The shape rules mirror conv_halo_supported() / launch_conv0_u8().
+            if (fuse_pool && f.add < 0 && f.resize < 0 && (nx = sole_consumer(cur)) >= 0 && an[nx].kind == A_MAXPOOL &&
+                an[nx].ksize == 2 && an[nx].stride == 2 && an[nx].pad_lo == 0 && an[nx].pad_hi == 0 && an[a].ksize == 3 &&
+                an[a].stride == 1 && an[a].pad_lo == 1 && an[a].pad_hi == 1 && an[a].h % 2 == 0 && an[a].w % 2 == 0) {
+                const int cin = an[an[a].in[0]].c, cout = an[a].c;
+                const bool first = f.kind == LAYER_CONV0 && (cout == 16 || cout == 32);
+                const bool halo = f.kind == LAYER_CONV && (cin == 16 || cin == 32 || cin == 64) && (cout == 32 || cout == 64 || cout == 128) &&
+                                  an[a].h >= 64 && an[a].w >= 64;
+                if (first || halo) { f.pool = nx; owner[nx] = id; cur = nx; }
+            }
             f.final_anode = cur;
         } else if (an[a].kind == A_PAD) {
             const int nx = sole_consumer(a);
@@ -675,6 +687,7 @@ bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, Model
             L.act = f.leaky >= 0 ? 1 : 0;
             L.alpha = f.leaky >= 0 ? an[f.leaky].alpha : 0.f;
             L.upsample2x = f.resize >= 0 ? 1 : 0;
+            L.pool2 = f.pool >= 0 ? 1 : 0;
             L.out_fp32 = value_of(f.final_anode).fp32 ? 1 : 0;
             if (f.residual >= 0) {
                 if (an[f.residual].value < 0) return B.fail("residual operand of '" + fin.out_name + "' has no value");
@@ -705,7 +718,7 @@ bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, Model
             plan->bias_f32.resize(L.b_off + (L.cout + 255) / 256 * 256, 0.f);
             memcpy(plan->bias_f32.data() + L.b_off, shift.data(), sizeof(float) * L.cout);
             if (f.kind == LAYER_CONV0) {
-                if (L.cin != 3 || k != 3 || L.stride != 1 || L.pad_lo != 1 || L.pad_hi != 1 || L.cout % 8 || L.cout > 64 || L.upsample2x || L.res.buf != -1 || L.out_fp32)
+                if (L.cin != 3 || k != 3 || L.stride != 1 || L.pad_lo != 1 || L.pad_hi != 1 || L.cout % 8 || L.cout > 64 || L.upsample2x || L.res.buf != -1 || L.out_fp32)  // (pool2 only with Cout 16 / 32, checked where it is set)
                     return B.fail(L.name + ": the first convolution must be 3x3 stride 1 pad 1 over 3 channels with Cout in {8..64}");
                 L.w_off = plan->conv0_w.size();
                 plan->conv0_w.resize(L.w_off + static_cast<size_t>(K) * L.cout);

@@ -34,6 +34,7 @@ struct LayerPlan {
     int act = 0;  // 0 linear, 1 leaky
     float alpha = 0.f;
     int out_fp32 = 0, upsample2x = 0;
+    int pool2 = 0;  // 1: a MaxPool(2, stride 2) that follows the convolution is applied in its epilogue; `out` is the pooled tensor
     size_t w_off = 0;  // LAYER_CONV: element offset into weights_bf16; LAYER_CONV0: into conv0_w
     size_t b_off = 0;  // float offset into bias_f32
     // max-pool (window k, stride s); padding cells hold pad_value (-inf for ONNX MaxPool pads)
@@ -59,7 +60,9 @@ struct ModelPlan {
     size_t num_params = 0;
 };
 
-bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, ModelPlan* plan, std::string* err);
+// fuse_pool: fold MaxPool(2, 2) into the producing convolution where a kernel that can do it will run the layer
+// (the first convolution and the halo-patch layers: 3x3 stride 1, 16/32/64 input channels, maps >= 64x64)
+bool build_plan(const OnnxGraph& g, int net_w, int net_h, int num_classes, bool fuse_pool, ModelPlan* plan, std::string* err);
 
 uint16_t f32_to_bf16_rn(float f);
 

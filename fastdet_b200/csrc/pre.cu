@@ -131,6 +131,10 @@ __device__ __forceinline__ uint32_t c0_pack(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+__device__ __forceinline__ uint32_t c0_max(uint32_t a, uint32_t b) {  // bf16x2 maximum
+    const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 
 __global__ void __launch_bounds__(C0_THREADS)
 conv0_u8_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wgt, const float* __restrict__ bias,
@@ -256,7 +260,7 @@ static constexpr int C0W_PPL = (C0D_PH * C0D_PW + 31) / 32;  // patch pixels per
 __global__ void __launch_bounds__(C0W_THREADS)
 conv0_ws_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wgt, const float* __restrict__ bias,
                 const __grid_constant__ CUtensorMap tm_out, int n, int h, int wd, int cout, int act, float alpha,
-                unsigned long long m_per_frame, unsigned long long m_tiles_x) {
+                unsigned long long m_per_frame, unsigned long long m_tiles_x, int pool2) {
     extern __shared__ __align__(1024) uint8_t c0w_dyn[];        // patch ring
     uint8_t (*s_patch)[C0D_PATCH_BYTES] = reinterpret_cast<uint8_t (*)[C0D_PATCH_BYTES]>(c0w_dyn);
     __shared__ __align__(1024) uint8_t s_w[12 * 32 * 16];       // B: [K chunk 0..11][32 filters][16 B]
@@ -457,9 +461,40 @@ conv0_ws_kernel(const uint8_t* __restrict__ frames, const float* __restrict__ wg
                 }
                 pk[c] = c0_pack(x.x, x.y);
             }
+            // MaxPool(2, 2) of the activation (YOLOv3-tiny's first pool), in place: the 2x2 window of lane l = (row l >> 3,
+            // column l & 7) is lanes l, l^1, l^8, l^9; lanes with even row and column keep the maximum
+            if (pool2) {
+#pragma unroll
+                for (int c = 0; c < 16; ++c) {
+                    uint32_t v = c0_max(pk[c], __shfl_xor_sync(0xffffffffu, pk[c], 1));
+                    pk[c] = c0_max(v, __shfl_xor_sync(0xffffffffu, v, 8));
+                }
+            }
             uint8_t* so = s_out[warp];
             if (lane == 0) ptx::tma_store_wait_read<0>();  // this warp's previous store (two tiles ago) has finished reading the buffer
             __syncwarp();
+            if (pool2) {
+                // pooled box [2 rows][4 pixels x cout]: the 8 surviving pixels, dense
+                const int pp = (lane >> 4) * 4 + ((lane & 7) >> 1);
+                if ((lane & 9) == 0) {
+                    if (cout == 32) {
+#pragma unroll
+                        for (int c = 0; c < 4; ++c)
+                            *reinterpret_cast<uint4*>(so + pp * 64 + (c << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 2; ++c)
+                            *reinterpret_cast<uint4*>(so + pp * 32 + (c << 4)) = make_uint4(pk[4 * c], pk[4 * c + 1], pk[4 * c + 2], pk[4 * c + 3]);
+                    }
+                }
+                ptx::fence_proxy_async();
+                __syncwarp();
+                if (lane == 0) {
+                    ptx::tma_store_3d(&tm_out, so, tx * (C0D_TW / 2) * cout, ty * (C0D_TH / 2) + 2 * quarter, f);  // clipped at the frame edges
+                    ptx::tma_store_commit();
+                }
+                continue;
+            }
             // dense rows [4 image rows][8 pixels][cout]: with pitch == cout the 8 pixels of an image row are one contiguous
             // 8*cout*2-byte run in global memory: the TMA store moves 4 wide rows
             if (cout == 32) {
@@ -496,7 +531,7 @@ int kernels_init() {
 }
 
 int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __nv_bfloat16* out, int n, int h,
-                    int wd, int cout, int out_pitch, int act, float alpha, cudaStream_t s) {
+                    int wd, int cout, int out_pitch, int act, float alpha, int pool2, cudaStream_t s) {
     const int act_mode = act ? ((alpha >= 0.f && alpha <= 1.f) ? 1 : 2) : 0;
     const long long tiles = 1LL * n * ((wd + C0D_TW - 1) / C0D_TW) * ((h + C0D_TH - 1) / C0D_TH);
     const int tx = (wd + C0D_TW - 1) / C0D_TW, per_frame = tx * ((h + C0D_TH - 1) / C0D_TH);
@@ -504,18 +539,22 @@ int launch_conv0_u8(const uint8_t* frames, const float* w, const float* bias, __
         tiles < (1LL << 24) && per_frame < 65536) {  // (ranges of the multiply-shift division)
         // dense NHWC output: an image row is one run of W*C elements; TMA store box = 8 pixels x 4 rows
         CUtensorMap tm;
-        const unsigned long long dims[3] = {static_cast<unsigned long long>(cout) * wd, static_cast<unsigned long long>(h),
+        // (pooled: the output map is (h/2, wd/2) and a warp's box its 2 x 4 surviving pixels)
+        const int oh = pool2 ? h / 2 : h, ow = pool2 ? wd / 2 : wd;
+        if (pool2 && ((h | wd) & 1)) return -1;
+        const unsigned long long dims[3] = {static_cast<unsigned long long>(cout) * ow, static_cast<unsigned long long>(oh),
                                             static_cast<unsigned long long>(n)};
-        const unsigned long long strides[2] = {2ULL * cout * wd, 2ULL * cout * wd * h};
-        const unsigned box[3] = {static_cast<unsigned>(cout) * C0D_TW, 4, 1};
+        const unsigned long long strides[2] = {2ULL * cout * ow, 2ULL * cout * ow * oh};
+        const unsigned box[3] = {static_cast<unsigned>(cout) * (pool2 ? C0D_TW / 2 : C0D_TW), pool2 ? 2u : 4u, 1};
         if (encode_tiled_bf16(&tm, out, 3, dims, strides, box, 0)) return -1;
         const int blocks = static_cast<int>(tiles < 148LL ? tiles : 148LL);
         const unsigned long long one40 = 1ULL << 40;
         conv0_ws_kernel<<<blocks, C0W_THREADS, C0W_PATCHES * C0D_PATCH_BYTES, s>>>(frames, w, bias, tm, n, h, wd, cout, act_mode, alpha,
-                                                                                  (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx);
+                                                                                  (one40 + per_frame - 1) / per_frame, (one40 + tx - 1) / tx, pool2);
         return cudaPeekAtLastError() == cudaSuccess ? 0 : -1;  // (peek: the caller reports the reason)
     }
     // any other first layer (Cout up to 64, any pitch): CUDA cores
+    if (pool2) return -1;  // (the planner fuses the pool only for shapes the kernel above takes)
     const size_t smem = (256 + (C0_TH + 2) * (C0_TW + 2) * 3 + 4 + 27 * cout + cout) * sizeof(float) +
                         static_cast<size_t>(C0_TH) * C0_TW * cout * 2;
     dim3 grid((wd + C0_TW - 1) / C0_TW, (h + C0_TH - 1) / C0_TH, n);

@@ -143,6 +143,32 @@ def test_full_608_batch_with_strips_against_oracle():
     m.close()
 
 
+def test_fused_maxpool_equals_the_pool_kernel():
+    """YOLOv3-tiny: MaxPool(2, 2) in the epilogue of conv1 (conv0_ws_kernel) and conv2 / conv3 (halo-patch kernel) gives the
+    very values the stand-alone pool kernel gives (a maximum of bf16 values is exact), layer by layer and at the heads;
+    batch 5 so that edge tiles and several frames are involved."""
+    data = modelgen.build_onnx("tiny", 80, 416, seed=1)
+    frames = frames_for(5, 416, first_seed=230)
+    m = _native.Model(data, 80, (416, 416), device=0)
+    L = m.layers()
+    assert len(L) == 16 and [l["h"] for l in L[:3]] == [208, 104, 52]  # conv1..conv3 write the pooled maps
+    got, _ = _check_heads(data, m, frames, per_layer=True)
+    pooled = {l["out_name"]: m.layer_output(i, 5) for i, l in enumerate(L[:3])}
+    m.close()
+    with _native.option("fuse_pool", 0):
+        m2 = _native.Model(data, 80, (416, 416), device=0)
+        L2 = m2.layers()
+        assert len(L2) == 19
+        m2.preprocess(frames, 5, (416, 416))
+        m2.forward(5)
+        for i, l in enumerate(L2):
+            if l["out_name"] in pooled:
+                assert l["kind"] == 2 and np.array_equal(m2.layer_output(i, 5), pooled[l["out_name"]]), l["out_name"]
+        for a, b in zip(got, m2.heads(5)):
+            assert np.array_equal(a, b)
+        m2.close()
+
+
 def test_nms_general_path_equals_register_path():
     """Option nms_general forces the global-memory Soft-NMS loop: same records as the one-candidate-per-thread path."""
     data = modelgen.build_onnx("tiny", 80, 416, seed=1)
