@@ -200,7 +200,7 @@ void plan_segments(const ModelPlan& P, int n, std::vector<Segment>* out) {
     std::vector<int> downs;  // layers that halve the map
     for (size_t i = 0; i < P.layers.size(); ++i) {
         const LayerPlan& L = P.layers[i];
-        const bool down = (L.kind == LAYER_CONV && L.stride == 2) || (L.kind == LAYER_MAXPOOL && L.pool_s == 2);
+        const bool down = (L.kind == LAYER_CONV && L.stride == 2) || (L.kind == LAYER_MAXPOOL && L.pool_s == 2) || L.pool2;
         if (down) downs.push_back(static_cast<int>(i));
     }
     if (downs.size() < 3) return;
@@ -791,7 +791,7 @@ static int build_overlap_plan(fd_model* m, Exec* e) {
     int downs = 0, depth = 0;
     for (size_t i = 0; i < P.layers.size(); ++i) {
         const LayerPlan& L = P.layers[i];
-        const bool down = (L.kind == LAYER_CONV && L.stride == 2) || (L.kind == LAYER_MAXPOOL && L.pool_s == 2);
+        const bool down = (L.kind == LAYER_CONV && L.stride == 2) || (L.kind == LAYER_MAXPOOL && L.pool_s == 2) || L.pool2;
         if (down && ++downs == 2) break;
         if (L.out_fp32 || L.upsample2x || L.kind == LAYER_COPY) return FD_OK;
         // every tensor these layers touch must be written inside the front (or be the input frames): nothing may reach back

@@ -1071,7 +1071,7 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
     // many CTAs, each with a proportionally shorter main loop.  A launch is as long as ONE CTA's work, and at batch 1 that
     // is what a layer costs: full-416 batch 1 0.90 -> 0.64 ms.  64-wide tiles where they still fit the GPU in one wave,
     // 128-wide otherwise (measured: 64 everywhere makes batch 4 slower than the 256-wide default, 128 faster).
-    if (O.latency_bn && !block_n_hint && !d.out_fp32) {
+    if (O.latency_bn && !block_n_hint && !d.out_fp32 && O.strip != 2) {  // (strip = 2 forces the CTA-pair strip form wherever it is legal)
         const long long tiles256 = ((M + 255) / 256) * ((d.cout + 255) / 256);
         if (tiles256 * 4 <= num_sms) {
             int lb = O.latency_bn;

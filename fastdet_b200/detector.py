@@ -143,6 +143,10 @@ class ONNXDetector(Detector):
                     results[i] = self._perform_host_one(datas[i], threshold, allow_resize, source_coords)
                 todo = [i for i in todo if i not in set(bad)]
                 continue
+            if (counts >= self.max_det).any():
+                # a frame filled its record buffer: it may hold more detections than max_det, and the reference has no cap
+                self.logger.warning(f'perform: a frame reached max_det={self.max_det}; re-running uncapped')
+                dets, counts = self.model.detect_jpeg(batch, threshold, max_det=int(self.model.info.boxes_per_frame), allow_resize=allow_resize)
             self.jpeg_device_frames += len(batch)
             if allow_resize and source_coords and batch:
                 info = _native.jpeg_probe(bytes(batch[0]))

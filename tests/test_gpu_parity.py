@@ -534,12 +534,9 @@ def test_wire_format_and_batching_service_on_device():
     assert svc.batches_run < len(pngs)
     # a frame's tuples do not depend on the batch it rode in beyond the split-K reassociation: same
     # boxes / classes, scores within the spec's 1e-2
+    from tests.compare import same_detections
     for g, w in zip(got, want):
-        gs = {(k, round(x), round(y)): c for k, c, x, y, _, _ in g if c >= 0.11}
-        ws = {(k, round(x), round(y)): c for k, c, x, y, _, _ in w if c >= 0.11}
-        common = set(gs) & set(ws)
-        assert len(common) >= max(len(gs), len(ws)) - 2
-        assert all(abs(gs[k] - ws[k]) <= 1e-2 for k in common)
+        assert same_detections(g, w, 0.1), (g, w)
 
 
 def test_letterboxed_frames_report_source_pixels():
