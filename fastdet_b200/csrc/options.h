@@ -32,6 +32,8 @@ struct Options {
                               // 0 = sized from chunk_mb, -1 = no chunking (default)
     int chunk_mb = 48;        // auto chunk size: largest tensor of a first-segment chunk at most this many MB (half of it in the second)
     int chunk_interleave = 0; // run the second chunked segment's chunk right after the first-segment chunks that feed it
+    int server_inflight = 2;  // fd_server: micro-batches in flight per lane (2: copy / compute overlap at saturation; 1: a closed loop
+                              // of few streams per lane gathers larger batches)
     int detect_overlap = 1;   // synchronous fd_detect: the frame copy in four pieces, overlapped with the first layers
 };
 

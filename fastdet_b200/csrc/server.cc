@@ -28,6 +28,7 @@
 #include <cuda_runtime.h>
 
 #include "../../include/fastdet_b200.h"
+#include "options.h"
 
 void* fd_internal_pinned_alloc(int device, size_t bytes);  // capi.cu
 void fd_internal_pinned_free(int device, void* p);
@@ -113,6 +114,7 @@ struct Lane {
     Batch* open = nullptr;
     std::deque<Batch*> closed, inflight;
     std::vector<Batch*> pool, all;
+    int max_inflight = FD_MAX_SLOTS;  // batches in flight (option server_inflight)
     int cur_cap = 8;  // pinned frames per new batch: doubles (up to max_batch) whenever a batch fills up, so a lane's pinned
                       // footprint follows its load instead of being max_batch x 0.5 MB per batch from the start
     bool stop = false;
@@ -146,7 +148,7 @@ struct Lane {
         std::unique_lock<std::mutex> lk(mu);
         bool slot_busy[FD_MAX_SLOTS] = {false, false};
         for (;;) {
-            if (static_cast<int>(inflight.size()) < FD_MAX_SLOTS) {
+            if (static_cast<int>(inflight.size()) < max_inflight) {
                 Batch* b = nullptr;
                 if (!closed.empty()) { b = closed.front(); closed.pop_front(); }
                 else if (open && open->n > 0) {
@@ -246,6 +248,7 @@ int fd_server_create(const fd_server_model* models, int n_models, const int32_t*
                 return rc;  // fd_last_error() holds the reason; lanes built so far are destroyed with `s`
             std::unique_ptr<Lane> l(new Lane());
             l->max_batch = max_batch; l->max_det = max_det; l->max_delay_s = max_delay_ms * 1e-3; l->cur_cap = std::min(8, max_batch);
+            l->max_inflight = std::max(1, std::min<int>(FD_MAX_SLOTS, fd::options().server_inflight));
             l->frame_bytes = static_cast<size_t>(be->w) * be->h * 3;
             l->be = std::move(be);
             s->lanes.push_back(std::move(l));
@@ -267,6 +270,7 @@ int fd_server_create_fake(int n_models, int n_devices, int net_w, int net_h, int
             be->w = net_w; be->h = net_h; be->device = d; be->model = m; be->latency_us = latency_us;
             std::unique_ptr<Lane> l(new Lane());
             l->max_batch = max_batch; l->max_det = 1; l->max_delay_s = max_delay_ms * 1e-3; l->cur_cap = std::min(8, max_batch);
+            l->max_inflight = std::max(1, std::min<int>(FD_MAX_SLOTS, fd::options().server_inflight));
             l->frame_bytes = static_cast<size_t>(net_w) * net_h * 3;
             l->be = std::move(be);
             s->lanes.push_back(std::move(l));

@@ -24,10 +24,12 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def run(gpus, streams, seconds, max_batch=64, max_delay_ms=0.0, python_clients=False, warmup=2.0, models=("full", "rsu")):
+def run(gpus, streams, seconds, max_batch=64, max_delay_ms=0.0, python_clients=False, warmup=2.0, models=("full", "rsu"), inflight=None):
     from fastdet_b200 import _native, modelgen
     from fastdet_b200.server import DetectServer
     _native.set_option("segv_backtrace", 1)
+    if inflight:
+        _native.set_option("server_inflight", inflight)
     have = _native.device_count()
     if have < 1:
         raise SystemExit("serve bench needs a CUDA device (there is no CPU fallback)")
@@ -47,7 +49,7 @@ def run(gpus, streams, seconds, max_batch=64, max_delay_ms=0.0, python_clients=F
     stream_models = [names[(s // gpus) % len(names)] for s in range(streams)]
     # warm every lane's execution state for the batch sizes the closed loop will produce (graph capture, buffers)
     st = srv.closed_loop(stream_models, frames, threshold=0.1, warmup_seconds=warmup, seconds=seconds)
-    out = {"streams": streams, "gpus": gpus, "models": {n: specs[n][1] for n in names}, "load_seconds": round(load_s, 2),
+    out = {"streams": streams, "gpus": gpus, "inflight_per_lane": _native.get_option("server_inflight"), "models": {n: specs[n][1] for n in names}, "load_seconds": round(load_s, 2),
            "frames_per_second": round(st["frames_per_second"], 1), "latency_ms": {k: round(v, 3) for k, v in st["latency_ms"].items()},
            "mean_batch": round(st["mean_batch"], 2), "batches": st["batches"], "frames": st["frames"], "seconds": round(st["seconds"], 2),
            "frames_per_device": st["frames_per_device"], "frames_per_model": st["frames_per_model"],
@@ -110,5 +112,6 @@ if __name__ == "__main__":
     ap.add_argument("--max-delay-ms", type=float, default=0.0)
     ap.add_argument("--python-clients", action="store_true")
     ap.add_argument("--models", default="full,rsu")
+    ap.add_argument("--inflight", type=int, default=0)
     a = ap.parse_args()
-    print(json.dumps(run(a.gpus, a.streams, a.seconds, a.max_batch, a.max_delay_ms, a.python_clients, models=tuple(a.models.split(",")))))
+    print(json.dumps(run(a.gpus, a.streams, a.seconds, a.max_batch, a.max_delay_ms, a.python_clients, models=tuple(a.models.split(",")), inflight=a.inflight)))
