@@ -72,6 +72,9 @@ struct Exec {  // everything that depends on the batch size
     std::vector<char> use_halo;
     float* splitk_ws = nullptr;     // shared by the split-K launches of this batch size (they run one after another)
     int* splitk_counters = nullptr;
+    int* tile_flags = nullptr;      // per-M-tile completion counters of the layers linked by tile-level dependencies
+    size_t tile_flag_ints = 0;      // (zeroed at the start of every forward pass)
+    int linked_layers = 0;
     uint8_t* frames = nullptr;     // [n, net_h, net_w, 3]
     uint8_t* src = nullptr;        // staging for frames that need the letterbox
     size_t src_cap = 0;
@@ -160,7 +163,7 @@ size_t buf_bytes(const BufferPlan& b, int n) { return size_t(n) * b.h * b.w * b.
 
 void free_exec(Exec* e) {
     for (void* p : e->bufs) cudaFree(p);
-    cudaFree(e->splitk_ws); cudaFree(e->splitk_counters);
+    cudaFree(e->splitk_ws); cudaFree(e->splitk_counters); cudaFree(e->tile_flags);
     cudaFree(e->frames); cudaFree(e->src); cudaFree(e->cand); cudaFree(e->cand_count); cudaFree(e->scores);
     cudaFree(e->dets); cudaFree(e->det_count); cudaFree(e->scratch);
     if (e->h_dets) cudaFreeHost(e->h_dets);
@@ -341,6 +344,33 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
             for (ConvLaunch& c : v)
                 if (c.ws_bytes) conv_tc_bind_workspace(&c, e->splitk_ws, e->splitk_counters);
     }
+    // Tile-level dependencies between consecutive conv_tc layers (conv_tc_link_tiles): the consumer must read exactly the
+    // tensor its predecessor writes (a plain chain: no concat slice, no route, no up-sampling in between).
+    if (e->segs.empty() && options().tile_deps) {
+        std::vector<size_t> cand;
+        size_t ints = 0;
+        for (size_t i = 1; i < P.layers.size(); ++i) {
+            const LayerPlan& A = P.layers[i - 1];
+            const LayerPlan& B = P.layers[i];
+            if (A.kind != LAYER_CONV || B.kind != LAYER_CONV || e->use_halo[i - 1] || e->use_halo[i]) continue;
+            if (A.out_fp32 || A.upsample2x || A.pool2 || A.out.pitch != A.out.c) continue;
+            if (B.in.buf != A.out.buf || B.in.ch_off != A.out.ch_off || B.in.c != A.out.c || B.in.pitch != A.out.pitch || B.stride != 1) continue;
+            cand.push_back(i);
+            ints += static_cast<size_t>(conv_tc_tile_counters(e->conv[i - 1][0]));
+        }
+        if (ints) {
+            if (cudaMalloc(&e->tile_flags, ints * sizeof(int)) != cudaSuccess || cudaMemset(e->tile_flags, 0, ints * sizeof(int)) != cudaSuccess) {
+                free_exec(e.get());
+                return fail(FD_ERR_CUDA, "cudaMalloc(tile flags, batch %d) failed: %s", n, cudaGetErrorString(cudaGetLastError()));
+            }
+            e->tile_flag_ints = ints;
+            size_t off = 0;
+            for (size_t i : cand) {
+                e->linked_layers += conv_tc_link_tiles(&e->conv[i - 1][0], &e->conv[i][0], e->tile_flags + off, m->num_sms);
+                off += static_cast<size_t>(conv_tc_tile_counters(e->conv[i - 1][0]));
+            }
+        }
+    }
     *out = e.get();
     m->execs[n] = std::move(e);
     return FD_OK;
@@ -387,6 +417,8 @@ int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
 int launch_layers(fd_model* m, Exec* e, cudaStream_t s, int from_layer = 0) {
     const ModelPlan& P = m->plan;
     size_t i = static_cast<size_t>(from_layer);  // 0, or the first layer after a segment
+    if (from_layer == 0 && e->tile_flags)  // a new pass: no tile of any linked layer is done yet
+        if (cudaMemsetAsync(e->tile_flags, 0, e->tile_flag_ints * sizeof(int), s) != cudaSuccess) return fail(FD_ERR_CUDA, "tile-flag reset failed");
     while (i < P.layers.size()) {
         const int sgi = e->seg_of[i];
         if (sgi < 0) {
@@ -605,6 +637,7 @@ int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
                 out->kernel = c.p.strip ? FD_KERNEL_TC_PAIR_STRIP : c.two_cta ? FD_KERNEL_TC_PAIR : c.p.swap ? FD_KERNEL_TC_SWAPPED : FD_KERNEL_TC_SINGLE;
                 out->block_n = c.block_n; out->split_k = c.p.split_k; out->grid = c.grid; out->num_stages = c.p.num_stages;
                 out->kb_per_stage = c.p.kb_per_stage; out->b_resident = c.p.b_resident;
+                out->tile_linked = c.p.dep != nullptr;
                 out->smem_bytes = static_cast<int32_t>(c.smem_bytes);
             }
     }
@@ -836,6 +869,7 @@ static int forward_overlapping_copy(fd_model* m, Exec* e, const uint8_t* frames,
         if (f1 > f0) CU(cudaMemcpyAsync(e->frames + f0 * frame_bytes, frames + f0 * frame_bytes, (f1 - f0) * frame_bytes, cudaMemcpyHostToDevice, m->copy_stream));
         CU(cudaEventRecord(m->h2d_ev[p], m->copy_stream));
     }
+    if (e->tile_flags) CU(cudaMemsetAsync(e->tile_flags, 0, e->tile_flag_ints * sizeof(int), s));  // (launch_layers does it for a whole pass)
     for (int k = 0; k < 4; ++k) {
         CU(cudaStreamWaitEvent(s, m->h2d_ev[k], 0));
         for (int i = 0; i < e->ov_layers; ++i) {

@@ -102,7 +102,8 @@ typedef struct fd_layer_exec {
     int32_t smem_bytes;
     int32_t chunk_frames; /* frames per launch of this layer (< bucket: the layer belongs to an L2-resident chunked segment) */
     int32_t launches;     /* launches of this layer per forward pass */
-    int32_t reserved[5];
+    int32_t tile_linked;  /* 1: waits for its predecessor tile by tile (per-M-tile completion counters) instead of grid-wide */
+    int32_t reserved[4];
 } fd_layer_exec;
 
 const char* fd_last_error(void);

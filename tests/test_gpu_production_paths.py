@@ -143,6 +143,39 @@ def test_full_608_batch_with_strips_against_oracle():
     m.close()
 
 
+def test_tile_level_dependencies_change_nothing():
+    """Batch 64: most consecutive conv_tc layers synchronise tile by tile (the consumer's TMA warp waits for the producer
+    tiles that cover its rows; SMs the producer leaves idle in its last wave start the consumer early) instead of
+    grid by grid.  A missed dependency would show as a race: the heads must be bit-identical over repeated passes, on two
+    different input sets, and identical to a model built with the option switched off."""
+    import hashlib
+    data = modelgen.build_onnx("rsu", 9, 416, seed=3)
+    sets = [frames_for(64, 416, first_seed=100), frames_for(64, 416, first_seed=300)]
+    m = _native.Model(data, 9, (416, 416), device=0)
+    info = m.exec_info(64)
+    linked = [i for i, e in enumerate(info) if e["tile_linked"]]
+    assert len(linked) >= 40, linked
+    L = m.layers()
+    assert all(L[i]["kind"] == 1 and L[i]["stride"] == 1 for i in linked)
+
+    def digest(model, frames):
+        model.preprocess(frames, 64, (416, 416))
+        model.forward(64)
+        return [hashlib.sha256(h.tobytes()).hexdigest() for h in model.heads(64)]
+
+    want = [digest(m, f) for f in sets]
+    for rep in range(6):
+        for f, w in zip(sets, want):
+            assert digest(m, f) == w, rep
+    m.close()
+    with _native.option("tile_deps", 0):
+        m2 = _native.Model(data, 9, (416, 416), device=0)
+        assert not any(e["tile_linked"] for e in m2.exec_info(64))
+        for f, w in zip(sets, want):
+            assert digest(m2, f) == w
+        m2.close()
+
+
 def test_fused_maxpool_equals_the_pool_kernel():
     """YOLOv3-tiny: MaxPool(2, 2) in the epilogue of conv1 (conv0_ws_kernel) and conv2 / conv3 (halo-patch kernel) gives the
     very values the stand-alone pool kernel gives (a maximum of bf16 values is exact), layer by layer and at the heads;
