@@ -1333,9 +1333,12 @@ int conv_tc_prepare(const ConvDesc& d, int num_sms, int block_n_hint, ConvLaunch
 int conv_tc_tile_counters(const ConvLaunch& producer) { return producer.p.num_m_tiles; }
 
 int conv_tc_link_tiles(ConvLaunch* P, ConvLaunch* C, int* counters, int num_sms) {
-    if (!options().tile_deps || !counters) return 0;
+    const int mode = options().tile_deps;  // bit 0 on, bit 1 strip producers, bit 2 other producers, bit 3 only the 13x13-sized grids
+    if (!(mode & 1) || !counters) return 0;
     const ConvParams& pp = P->p;
     ConvParams& cp = C->p;
+    if (pp.strip ? !(mode & 2) : !(mode & 4)) return 0;
+    if ((mode & 8) && pp.M > options().tile_deps_max_m) return 0;
     // producer: CTA-pair kernel (im2col / tiled / strip) or the swapped form, plain bf16 output, whole-K tiles
     if (!(P->two_cta || pp.swap) || pp.split_k != 1 || pp.epi_mode != 0 || pp.out_fp32) return 0;
     // consumer: a 1x1 layer on the pair kernel or the swapped form, or a strip 3x3 layer; whole-K tiles, stride 1

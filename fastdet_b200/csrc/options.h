@@ -21,7 +21,10 @@ struct Options {
     int halo = 1;             // halo-patch kernel for 16/32/64-channel 3x3 layers on large maps
     int halo_skew = 1;        // ... with chunk planes skewed against shared-memory bank conflicts
     int halo_slots = 0;       // ... patch ring depth cap (0: the kernel's maximum)
-    int tile_deps = 1;        // consecutive conv_tc layers synchronise tile by tile instead of grid by grid (conv_tc_link_tiles)
+    int tile_deps = 0;        // experiment kept as an option (measured 3-4 % SLOWER when on everywhere, no reliable gain when limited to
+                              // the 13x13 stage): consecutive conv_tc layers synchronise tile by tile instead of grid by grid;
+                              // bit 0 on, bit 1 strip producers, bit 2 other producers, bit 3 only grids of <= tile_deps_max_m pixels
+    int tile_deps_max_m = 12000;
     int fuse_pool = 1;        // MaxPool(2, 2) after the first convolution / a halo-patch layer runs in that kernel's epilogue
     int pdl = 1;              // programmatic dependent launch between layers
     int graph = 1;            // replay the forward pass as a captured CUDA graph
