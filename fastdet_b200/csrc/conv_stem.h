@@ -37,6 +37,8 @@ struct StemParams {
     int tiles_x, per_frame, total;
     unsigned long long m_per_frame, m_tiles_x;  // ceil(2^40 / d): x / d == (x * m) >> 40 for the ranges checked on the host
     float bias1[32], bias2[64];
+    int debug;  // developer switches, honoured by the harness build only (0 in production)
+    long long* prof;  // developer: per-CTA cycle counters [grid][16] (null in production)
 };
 
 struct StemLaunch {

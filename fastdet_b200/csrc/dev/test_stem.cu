@@ -185,12 +185,13 @@ static int check_case(const char* name, int n, int h, int w, int pad_hi, int sms
     return fail ? 1 : 0;
 }
 
-static void time_case(int n, int hw, int sms) {
+static void time_case(int n, int hw, int sms, int debug = 0) {
     Net N;
     make_net(N, n, hw, hw, 1);
     HaloLaunch hl;
     StemLaunch sl;
     if (prepare_two(N, sms, &hl) || prepare_stem(N, sms, &sl)) return;
+    sl.p.debug = debug;
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0));
     CK(cudaEventCreate(&e1));
@@ -211,7 +212,27 @@ static void time_case(int n, int hw, int sms) {
         CK(cudaEventElapsedTime(&ms_stem, e0, e1));
     }
     CK(cudaDeviceSynchronize());
-    printf("time n %d %dx%d: two kernels %.1f us, stem %.1f us (%.2fx), stem %.1f TFLOP/s algorithmic, out %.0f MB\n", n, hw, hw,
+    {   // one profiled launch: per role, cycles per tile in its loop and in its barrier waits (averaged over the CTAs)
+        long long* dprof;
+        CK(cudaMalloc(&dprof, sl.grid * 16 * sizeof(long long)));
+        CK(cudaMemset(dprof, 0, sl.grid * 16 * sizeof(long long)));
+        StemLaunch pl = sl;
+        pl.p.prof = dprof;
+        conv_stem_launch(pl, 0);
+        CK(cudaDeviceSynchronize());
+        std::vector<long long> hp(sl.grid * 16);
+        CK(cudaMemcpy(hp.data(), dprof, hp.size() * sizeof(long long), cudaMemcpyDeviceToHost));
+        double avg[16] = {0};
+        for (int b = 0; b < sl.grid; ++b)
+            for (int i = 0; i < 16; ++i) avg[i] += static_cast<double>(hp[b * 16 + i]) / sl.grid;
+        const double tiles = 1.0 * sl.p.total / sl.grid;
+        printf("   cycles/tile  builder: loop %.0f wait in_empty %.0f publish %.0f signal %.0f | mma: loop %.0f wait in_full %.0f acc1_empty %.0f acc2_empty+c1_full %.0f | "
+               "epi1(g0): loop %.0f wait c1_empty %.0f acc1_full %.0f | epi2: loop %.0f wait acc2_full %.0f store_read %.0f\n",
+               avg[0] / tiles, avg[1] / tiles, avg[2] / tiles, avg[3] / tiles, avg[4] / tiles, avg[5] / tiles, avg[6] / tiles, avg[7] / tiles, avg[8] / tiles, avg[9] / tiles,
+               avg[10] / tiles, avg[12] / tiles, avg[13] / tiles, avg[14] / tiles);
+        cudaFree(dprof);
+    }
+    printf("dbg %3d time n %d %dx%d: two kernels %.1f us, stem %.1f us (%.2fx), stem %.1f TFLOP/s algorithmic, out %.0f MB\n", debug, n, hw, hw,
            ms_two * 1000 / reps, ms_stem * 1000 / reps, ms_two / ms_stem, sl.flops / (ms_stem / reps * 1e-3) / 1e12,
            1.0 * n * N.ho * N.wo * 128 / 1e6);
     free_net(N);
@@ -229,8 +250,8 @@ int main(int argc, char** argv) {
     if (!strcmp(mode, "check") || !strcmp(mode, "all")) {
         fails += check_case("one tile row", 1, 128, 128, 1, sms);
         fails += check_case("416", 2, 416, 416, 1, sms);
-        fails += check_case("ragged 150x138", 3, 150, 138, 1, sms);
-        fails += check_case("odd 131x129", 2, 131, 129, 1, sms);
+        fails += check_case("ragged 150x140", 3, 150, 140, 1, sms);
+        fails += check_case("odd rows 131x132", 2, 131, 132, 1, sms);
         fails += check_case("pad (1,0) 160x192", 2, 160, 192, 0, sms);
         fails += check_case("many tiles per CTA", 12, 224, 224, 1, sms);
         printf("check: %d failing case(s)\n", fails);
@@ -240,5 +261,7 @@ int main(int argc, char** argv) {
         time_case(16, 416, sms);
         time_case(32, 608, sms);
     }
+    if (!strcmp(mode, "probe"))
+        for (int dbg : {0, 12, 1, 2, 16}) time_case(64, 416, sms, dbg);
     return fails ? 1 : 0;
 }

@@ -95,6 +95,20 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// shared-space stores by 32-bit shared address (a generic pointer into shared memory compiles to generic ST.E)
+__device__ __forceinline__ void st_shared_v2(uint32_t addr, uint32_t x, uint32_t y) {
+    asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(x), "r"(y) : "memory");
+}
+__device__ __forceinline__ void st_shared_v2_if(uint32_t addr, uint32_t x, uint32_t y, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\t@q st.shared.v2.b32 [%0], {%1, %2};\n\t}" ::"r"(addr), "r"(x), "r"(y), "r"(static_cast<uint32_t>(pred)) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w) {
+    asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4_if(uint32_t addr, uint32_t x, uint32_t y, uint32_t z, uint32_t w, bool pred) {
+    asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(static_cast<uint32_t>(pred)) : "memory");
+}
+
 // 16-byte asynchronous copy global -> shared (LDGSTS), L1-allocating; src_bytes = 0 writes zeros (padding)
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
