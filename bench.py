@@ -548,11 +548,22 @@ def run_b200(args):
         layer_ms = model.time_layers(n, 10)
         px = n * size * size
         L0 = model.layers()[0]
-        pre_bytes = px * 3 + px * L0["c"] * 2  # u8 frame in + bf16 first-conv output out (normalisation fused: no f32 tensor)
-        pre_gbs = pre_bytes / (float(layer_ms[0]) * 1e-3) * 1e-9
+        exec_rows = model.exec_info(n)
+        stem = exec_rows[0]["kernel_name"] == "fused_next"  # conv_stem_kernel: the first convolution runs inside the second one's kernel
+        if stem:
+            L1 = model.layers()[1]
+            pre_bytes = px * 3 + n * L1["h"] * L1["w"] * L1["c"] * 2  # u8 frames in + the SECOND convolution's bf16 output out
+            pre_ms = float(layer_ms[1])
+            pre_kernel = ("conv_stem_kernel = /255 normalise + first conv (3->32) + second conv (32->64, stride 2) in one kernel: u8 frames in, "
+                          "bf16 NHWC of the half-size map out; the first conv's activation (64 B/pixel) stays in shared memory. MMA-issue bound, not HBM bound: "
+                          "as two kernels the same work moved %d MB" % ((px * 3 + 2 * px * L0["c"] * 2 + n * L1["h"] * L1["w"] * L1["c"] * 2) // 1000000))
+        else:
+            pre_bytes = px * 3 + px * L0["c"] * 2  # u8 frame in + bf16 first-conv output out (normalisation fused: no f32 tensor)
+            pre_ms = float(layer_ms[0])
+            pre_kernel = "conv0_ws_kernel = /255 normalise + layout + first conv fused: u8 frames in (3 B/pixel), bf16 NHWC out"
+        pre_gbs = pre_bytes / (pre_ms * 1e-3) * 1e-9
         head_bytes = n * sum(c * h * ww for (c, h, ww) in model.head_shapes) * 4
         post_gbs = head_bytes / (post_ms * 1e-3) * 1e-9
-        exec_rows = model.exec_info(n)
         launches_per_batch = sum(e["launches"] for e in exec_rows) + 2  # conv stack (chunked layers launch once per chunk) + decode + Soft-NMS
         chunked = sorted({(e["chunk_frames"], e["launches"]) for e in exec_rows if e["launches"] > 1})
         line = {
@@ -568,15 +579,15 @@ def run_b200(args):
             "gpu_launches": int(world * args.steps * batches_per_step * launches_per_batch),
             "roofline": {"bound": "tensor", "achieved": round(achieved, 1), "peak": peaks["bf16"], "unit": "TFLOP/s",
                          "frac": round(achieved / peaks["bf16"], 4), "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "conv stack (conv_tc_kernel / conv_halo_kernel / conv0_ws_kernel, all tcgen05/TMEM), timed as fd_forward inside the timed steps",
+                         "kernel": "conv stack (conv_tc_kernel / conv_halo_kernel / conv_stem_kernel, all tcgen05/TMEM), timed as fd_forward inside the timed steps",
                          "launches_per_batch": launches_per_batch, "l2_resident_chunks": [{"frames": c, "launches_per_layer": k} for c, k in chunked],
                          "peak_kind": "bf16_tflops (burst: the timed region is well under 1 s of tensor work), " + peaks["source"],
                          "frac_of_sustained_peak": round(achieved / peaks["bf16_sustained"], 4), "peak_sustained": peaks["bf16_sustained"],
                          "forward_ms_per_batch": round(fwd_ms, 4), "flops_per_batch": flops_batch},
             "roofline_pre": {"bound": "hbm", "achieved": round(pre_gbs, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(pre_gbs / peaks["hbm"], 4),
-                             "traffic": None, "kernel": "conv0_ws_kernel = /255 normalise + layout + first conv fused: u8 frames in (3 B/pixel), bf16 NHWC out",
-                             "bytes_per_launch": int(pre_bytes), "ms": round(float(layer_ms[0]), 4),
-                             "how": "fd_time_layers in this run: CUDA events around 10 back-to-back launches of the layer alone (709 MB of output per launch > L2)"},
+                             "traffic": None, "kernel": pre_kernel,
+                             "bytes_per_launch": int(pre_bytes), "ms": round(pre_ms, 4),
+                             "how": "fd_time_layers in this run: CUDA events around 10 back-to-back launches of the kernel alone (its output per launch is larger than L2)"},
             "roofline_post": {"bound": "hbm", "achieved": round(post_gbs, 1), "peak": peaks["hbm"], "unit": "GB/s", "frac": round(post_gbs / peaks["hbm"], 4),
                               "traffic": None, "kernel": "decode_kernel + soft_nms_kernel (+ record copy-out)", "bytes_per_launch": int(head_bytes),
                               "ms": round(post_ms, 4),

@@ -21,6 +21,7 @@
 
 #include "../../include/fastdet_b200.h"
 #include "conv_halo.h"
+#include "conv_stem.h"
 #include "conv_tc.h"
 #include "jpeg.h"
 #include "kernels.h"
@@ -70,6 +71,10 @@ struct Exec {  // everything that depends on the batch size
     std::vector<std::vector<ConvLaunch>> conv;
     std::vector<std::vector<HaloLaunch>> halo;  // used where use_halo[layer]
     std::vector<char> use_halo;
+    // Fused stem (conv_stem.cu): layer 0 (u8 frames -> first convolution) runs inside layer 1's kernel; layer 0 has no launch
+    // and its output tensor is never written (its buffer is only allocated when a parity hook asks for that tensor)
+    bool use_stem = false;
+    std::vector<StemLaunch> stem;  // per chunk of layer 1's segment (one entry outside segments)
     float* splitk_ws = nullptr;     // shared by the split-K launches of this batch size (they run one after another)
     int* splitk_counters = nullptr;
     int* tile_flags = nullptr;      // per-M-tile completion counters of the layers linked by tile-level dependencies
@@ -96,6 +101,7 @@ struct Exec {  // everything that depends on the batch size
     std::vector<std::vector<ConvLaunch>> ov_conv;
     std::vector<std::vector<HaloLaunch>> ov_halo;
     std::vector<char> ov_use_halo;
+    std::vector<StemLaunch> ov_stem;
     cudaGraphExec_t graph_tail = nullptr;
     bool graph_tail_tried = false;
 };
@@ -232,6 +238,46 @@ void plan_segments(const ModelPlan& P, int n, std::vector<Segment>* out) {
     }
 }
 
+// The fused stem applies when layer 0 is the u8 first convolution, layer 1 a 3x3 stride-2 convolution that is the ONLY
+// reader of layer 0's output (no residual, no route), and conv_stem.cu takes the shapes (3 -> 32 -> 64: YOLOv3).
+bool stem_candidate(const ModelPlan& P) {
+    if (P.layers.size() < 2) return false;
+    const LayerPlan& A = P.layers[0];
+    const LayerPlan& B = P.layers[1];
+    if (A.kind != LAYER_CONV0 || B.kind != LAYER_CONV || A.pool2 || B.pool2 || A.out_fp32 || B.out_fp32 || B.upsample2x || B.res.buf >= 0) return false;
+    if (B.ksize != 3 || B.stride != 2 || B.pad_lo != 1 || A.ksize != 3 || A.stride != 1 || A.pad_lo != 1 || A.pad_hi != 1) return false;
+    if (B.in.buf != A.out.buf || B.in.ch_off != A.out.ch_off || B.in.c != A.out.c || B.cin != A.cout) return false;
+    for (size_t i = 2; i < P.layers.size(); ++i)
+        if (P.layers[i].in.buf == A.out.buf || P.layers[i].res.buf == A.out.buf || P.layers[i].out.buf == A.out.buf) return false;
+    for (int h : P.head_layers)
+        if (h == 0) return false;
+    return true;
+}
+
+// shapes and filters of the fused stem for `frames` frames; no frame / output pointers yet (null passes the kernel's alignment rules)
+StemDesc stem_desc(const fd_model* m, int frames) {
+    const ModelPlan& P = m->plan;
+    const LayerPlan& A = P.layers[0];
+    const LayerPlan& B = P.layers[1];
+    StemDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n = frames; d.h = A.in.h; d.w = A.in.w;
+    d.c1 = A.cout; d.w1 = m->d_conv0 + A.w_off; d.bias1_host = P.bias_f32.data() + A.b_off; d.act1 = A.act; d.alpha1 = A.alpha;
+    d.c2 = B.cout; d.pad_hi2 = B.pad_hi; d.w2 = m->d_w + B.w_off; d.bias2_host = P.bias_f32.data() + B.b_off; d.act2 = B.act; d.alpha2 = B.alpha;
+    d.out_pitch = B.out.pitch;
+    return d;
+}
+
+int prepare_stem(fd_model* m, Exec* e, int frames, int k, int chunk, StemLaunch* sl) {
+    const ModelPlan& P = m->plan;
+    StemDesc d = stem_desc(m, frames);
+    d.frames = e->frames + static_cast<size_t>(k) * chunk * P.net_h * P.net_w * 3;
+    d.out = static_cast<__nv_bfloat16*>(loc_ptr(*e, P, P.layers[1].out, false, k, chunk));
+    char err[256] = "";
+    if (conv_stem_prepare(d, m->num_sms, sl, err, sizeof(err))) return fail(FD_ERR_CUDA, "stem (layers 0 + 1): %s", err);
+    return FD_OK;
+}
+
 // tensor maps + launch geometry of conv layer i for `frames` frames, chunk k of its segment (k = chunk = 0: whole batch)
 int prepare_conv_layer(fd_model* m, Exec* e, size_t i, int frames, int k, int chunk, ConvLaunch* cl, HaloLaunch* hl, char* use_halo) {
     const ModelPlan& P = m->plan;
@@ -268,6 +314,18 @@ int prepare_conv_layer(fd_model* m, Exec* e, size_t i, int frames, int k, int ch
     return FD_OK;
 }
 
+// layer 0's output buffer, which an Exec with the fused stem does not allocate up front
+int ensure_stem_input_buffer(fd_model* m, Exec* e) {
+    const ModelPlan& P = m->plan;
+    const int b = P.layers[0].out.buf;
+    if (e->bufs[b]) return FD_OK;
+    DEVICE_SETUP_LOCK(m);
+    const int frames = e->buf_internal[b] ? e->segs[e->seg_of[0]].chunk : e->n;
+    cudaError_t err = cudaMalloc(&e->bufs[b], buf_bytes(P.buffers[b], frames));
+    if (err != cudaSuccess) return fail(FD_ERR_CUDA, "cudaMalloc(first convolution's output, batch %d) failed: %s", e->n, cudaGetErrorString(err));
+    return FD_OK;
+}
+
 int get_exec(fd_model* m, int n_frames, Exec** out) {
     if (n_frames <= 0) return fail(FD_ERR_ARG, "batch size must be positive (got %d)", n_frames);
     const int n = bucket_of(n_frames);
@@ -295,7 +353,14 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
         for (size_t b = 0; b < P.buffers.size(); ++b) e->buf_internal[b] = seg_of_buf[b] >= 0 ? 1 : 0;
     }
     e->bufs.assign(P.buffers.size(), nullptr);
+    // fused stem: decided here, from the shapes, because layer 0's output buffer is then not allocated at all
+    bool want_stem = false;
+    if (options().stem && stem_candidate(P) && e->seg_of[0] == e->seg_of[1]) {
+        const int sgi = e->seg_of[1];
+        want_stem = conv_stem_supported(stem_desc(m, sgi >= 0 ? e->segs[sgi].chunk : n));
+    }
     for (size_t i = 0; i < P.buffers.size(); ++i) {
+        if (want_stem && static_cast<int>(i) == P.layers[0].out.buf) continue;  // never written: allocated on demand by the parity hook
         int frames = n;
         if (e->buf_internal[i])
             for (size_t li = 0; li < P.layers.size(); ++li)
@@ -325,11 +390,20 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
         const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, chunks = sgi >= 0 ? n / chunk : 1;
         e->conv[i].resize(chunks);
         e->halo[i].resize(chunks);
+        if (want_stem && i == 1) continue;  // launched as the fused stem (its input tensor does not exist)
         for (int k = 0; k < chunks; ++k) {
             char uh = 0;
             if (int rc = prepare_conv_layer(m, e.get(), i, sgi >= 0 ? chunk : n, k, chunk, &e->conv[i][k], &e->halo[i][k], &uh)) { free_exec(e.get()); return rc; }
             e->use_halo[i] = uh;
         }
+    }
+    if (want_stem) {
+        const int sgi = e->seg_of[1];
+        const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, chunks = sgi >= 0 ? n / chunk : 1;
+        e->stem.resize(chunks);
+        for (int k = 0; k < chunks; ++k)
+            if (int rc = prepare_stem(m, e.get(), sgi >= 0 ? chunk : n, k, chunk, &e->stem[k])) { free_exec(e.get()); return rc; }
+        e->use_stem = true;
     }
     size_t ws_bytes = 0, counter_ints = 0;
     for (const auto& v : e->conv)
@@ -377,11 +451,17 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
 }
 
 // layer i on frames [k * chunk, (k + 1) * chunk) (chunk = 0: the whole batch) with the given conv launch descriptors
-int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, const ConvLaunch* cl, const HaloLaunch* hl, cudaStream_t s) {
+// sl: the fused stem's launch for these frames (layers 0 and 1 only; null = every layer launches its own kernel)
+int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, const ConvLaunch* cl, const HaloLaunch* hl, const StemLaunch* sl, cudaStream_t s) {
     const ModelPlan& P = m->plan;
     const LayerPlan& L = P.layers[i];
     const int frames = chunk ? chunk : e->n;
     int rc = 0;
+    if (sl && i == 0) return FD_OK;  // computed inside layer 1's kernel
+    if (sl && i == 1) {
+        if (conv_stem_launch(*sl, s)) return fail(FD_ERR_CUDA, "launch of the fused stem (layers 0 + 1) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return FD_OK;
+    }
     switch (L.kind) {
         case LAYER_CONV0:
             rc = launch_conv0_u8(e->frames + static_cast<size_t>(k) * chunk * P.net_h * P.net_w * 3, m->d_conv0 + L.w_off, m->d_bias + L.b_off,
@@ -410,7 +490,7 @@ int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
     const int sgi = e->seg_of[i];
     const bool conv = m->plan.layers[i].kind == LAYER_CONV;
     return launch_layer(m, e, i, k, sgi >= 0 ? e->segs[sgi].chunk : 0, e->use_halo[i] != 0, conv ? &e->conv[i][k] : nullptr,
-                        conv ? &e->halo[i][k] : nullptr, s);
+                        conv ? &e->halo[i][k] : nullptr, (e->use_stem && i < 2) ? &e->stem[k] : nullptr, s);
 }
 
 // The forward pass: chunked segments chunk by chunk (all layers of the segment per chunk), then the rest layer by layer.
@@ -553,6 +633,7 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     if (conv_tc_init(cerr, sizeof(cerr))) return fail(FD_ERR_CUDA, "conv_tc_init: %s", cerr);
     if (kernels_init()) return fail(FD_ERR_CUDA, "kernels_init failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (conv_halo_init()) return fail(FD_ERR_CUDA, "conv_halo_init failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (conv_stem_init()) return fail(FD_ERR_CUDA, "conv_stem_init failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&m->d_w, std::max<size_t>(P.weights_bf16.size(), 64) * 2));
     CU(cudaMalloc(&m->d_bias, std::max<size_t>(P.bias_f32.size(), 64) * 4));
@@ -623,6 +704,12 @@ int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
     out->bucket = e->n;
     out->chunk_frames = e->seg_of[layer] >= 0 ? e->segs[e->seg_of[layer]].chunk : e->n;
     out->launches = e->n / out->chunk_frames;
+    if (e->use_stem && layer < 2) {
+        out->kernel = layer == 0 ? FD_KERNEL_FUSED_NEXT : FD_KERNEL_STEM;
+        if (layer == 0) out->launches = 0;
+        else { out->grid = e->stem[0].grid; out->smem_bytes = static_cast<int32_t>(e->stem[0].smem_bytes); }
+        return FD_OK;
+    }
     switch (L.kind) {
         case LAYER_CONV0: out->kernel = FD_KERNEL_CONV0; break;
         case LAYER_MAXPOOL: out->kernel = FD_KERNEL_MAXPOOL; break;
@@ -839,12 +926,20 @@ static int build_overlap_plan(fd_model* m, Exec* e) {
         if (P.layers[i].kind != LAYER_CONV) continue;
         e->ov_conv[i].resize(4);
         e->ov_halo[i].resize(4);
+        if (e->use_stem && i == 1) continue;
         for (int k = 0; k < 4; ++k) {
             char uh = 0;
             if (int rc = prepare_conv_layer(m, e, i, chunk, k, chunk, &e->ov_conv[i][k], &e->ov_halo[i][k], &uh)) return rc;
             if (e->ov_conv[i][k].ws_bytes) return FD_OK;  // (a split-K layer this early would need its own workspace: leave the plain path)
             e->ov_use_halo[i] = uh;
         }
+    }
+    if (e->use_stem) {
+        if (depth < 2) return FD_OK;
+        e->ov_stem.resize(4);
+        if (!conv_stem_supported(stem_desc(m, chunk))) return FD_OK;  // (cannot happen for shapes the whole-batch stem took; leave the plain path)
+        for (int k = 0; k < 4; ++k)
+            if (int rc = prepare_stem(m, e, chunk, k, chunk, &e->ov_stem[k])) return rc;
     }
     e->ov_chunk = chunk;
     e->ov_layers = depth;
@@ -874,7 +969,8 @@ static int forward_overlapping_copy(fd_model* m, Exec* e, const uint8_t* frames,
         CU(cudaStreamWaitEvent(s, m->h2d_ev[k], 0));
         for (int i = 0; i < e->ov_layers; ++i) {
             const bool conv = P.layers[i].kind == LAYER_CONV;
-            if (int rc = launch_layer(m, e, i, k, chunk, e->ov_use_halo[i] != 0, conv ? &e->ov_conv[i][k] : nullptr, conv ? &e->ov_halo[i][k] : nullptr, s))
+            if (int rc = launch_layer(m, e, i, k, chunk, e->ov_use_halo[i] != 0, conv ? &e->ov_conv[i][k] : nullptr, conv ? &e->ov_halo[i][k] : nullptr,
+                                      (e->use_stem && i < 2) ? &e->ov_stem[k] : nullptr, s))
                 return rc;
         }
     }
@@ -1356,12 +1452,20 @@ int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, i
 // `layer`: the layer that produces `t`.  A buffer internal to a chunked segment only ever holds one chunk of frames, so
 // its value for the whole batch is gathered by replaying the segment chunk by chunk up to that layer (the same launches
 // the forward pass makes) and copying each chunk out.
+// With the fused stem the first convolution's output never exists during a forward pass; the hook for that tensor runs the
+// first convolution's own kernel (the two-kernel path's, which the stem is checked against) into a buffer allocated on demand.
 static int tensor_to_host_nchw(fd_model* m, Exec* e, int layer, const TensorLoc& t, bool fp32, float* dst, int n) {
     const size_t per_frame = size_t(t.c) * t.h * t.w;
+    const bool stem_input = e->use_stem && layer == 0;
+    if (stem_input)
+        if (int rc = ensure_stem_input_buffer(m, e)) return rc;
     if (t.buf >= 0 && e->buf_internal[t.buf]) {
         const Segment& sg = e->segs[e->seg_of[layer]];
         if (int rc = ensure_scratch(e, per_frame * sg.chunk * 4)) return rc;
         for (int k = 0; k * sg.chunk < n; ++k) {
+            if (stem_input) {
+                if (int rc = launch_layer(m, e, 0, k, sg.chunk, false, nullptr, nullptr, nullptr, m->stream)) return rc;
+            } else
             for (int j = sg.first; j <= layer; ++j)
                 if (int rc = launch_one(m, e, j, k, m->stream)) return rc;
             const int frames = std::min(sg.chunk, n - k * sg.chunk);
@@ -1374,6 +1478,8 @@ static int tensor_to_host_nchw(fd_model* m, Exec* e, int layer, const TensorLoc&
     }
     const size_t elems = size_t(n) * per_frame;
     if (int rc = ensure_scratch(e, elems * 4)) return rc;
+    if (stem_input)
+        if (int rc = launch_layer(m, e, 0, 0, 0, false, nullptr, nullptr, nullptr, m->stream)) return rc;
     if (launch_nhwc_to_nchw_f32(loc_ptr(*e, m->plan, t, fp32), t.pitch, fp32, e->scratch, n, t.h, t.w, t.c, m->stream))
         return fail(FD_ERR_CUDA, "layout kernel launch failed");
     CU(cudaMemcpyAsync(dst, e->scratch, elems * 4, cudaMemcpyDeviceToHost, m->stream));

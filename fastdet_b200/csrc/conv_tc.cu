@@ -63,11 +63,6 @@ __device__ __forceinline__ uint32_t pack_bf16(float a, float b) {
 __device__ __forceinline__ float bf16_lo(uint32_t u) { return __uint_as_float(u << 16); }
 __device__ __forceinline__ float bf16_hi(uint32_t u) { return __uint_as_float(u & 0xFFFF0000u); }
 
-// bf16x2 add with one rounding (HADD2.BF16): residual + branch value, both already bf16
-__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
-    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
-    return *reinterpret_cast<const uint32_t*>(&r);
-}
 // bias + activation on two accumulator columns at once (FADD2 / FMUL2 are two fp32 lanes per instruction).
 // Branch-free for the two cases YOLO has: LeakyReLU with 0 <= alpha <= 1 is max(x, alpha*x), and a linear layer is
 // the same expression with alpha = 1 (x*1 = x exactly).  GENERIC (alpha outside [0,1]) uses the select form.
@@ -205,13 +200,17 @@ __device__ __forceinline__ void epilogue_tile(const ConvParams& p, const CUtenso
             lap(2);
             return;
         }
+        if (has_res) {  // ONNX Add after LeakyRelu, in fp32 like the reference graph: ONE rounding, of the sum (rounding the branch value first
+                        // and the bf16 sum again doubled the rounding noise of every residual layer)
+#pragma unroll
+            for (int g = 0; g < 16; ++g) {
+                const uint32_t r = rcur[g >> 3].v[g & 7];
+                x[g] = __fadd2_rn(x[g], make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xFFFF0000u)));
+            }
+        }
         uint32_t pk[16];
 #pragma unroll
         for (int g = 0; g < 16; ++g) pk[g] = pack_bf16(x[g].x, x[g].y);
-        if (has_res) {  // ONNX Add after LeakyRelu; both terms are bf16, the sum is rounded once
-#pragma unroll
-            for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
-        }
         lap(2);
         if (STRIP && !RES) {
             // The lane's rows are scattered over the image (pad positions in between), so no TMA box fits them: 64 bytes
@@ -526,16 +525,16 @@ __device__ __forceinline__ void epilogue_tile_swapped(const ConvParams& p, const
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
             const int q = 8 * i + sub;
-            const float4 lo = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j);
-            const float4 hi = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j + 4);
-            uint4 v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
-            if (has_res) {  // same arithmetic as the normal mode: branch value rounded to bf16, bf16x2 add rounded once
+            float4 lo = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j);
+            float4 hi = *reinterpret_cast<const float4*>(stage_buf + q * 32 + 8 * j + 4);
+            if (has_res) {  // same arithmetic as the normal mode: fp32 sum, rounded once
                 const uint4 rr = res[i];
-                v.x = add_bf16x2(v.x, rr.x);
-                v.y = add_bf16x2(v.y, rr.y);
-                v.z = add_bf16x2(v.z, rr.z);
-                v.w = add_bf16x2(v.w, rr.w);
+                lo.x += __uint_as_float(rr.x << 16); lo.y += __uint_as_float(rr.x & 0xFFFF0000u);
+                lo.z += __uint_as_float(rr.y << 16); lo.w += __uint_as_float(rr.y & 0xFFFF0000u);
+                hi.x += __uint_as_float(rr.z << 16); hi.y += __uint_as_float(rr.z & 0xFFFF0000u);
+                hi.z += __uint_as_float(rr.w << 16); hi.w += __uint_as_float(rr.w & 0xFFFF0000u);
             }
+            const uint4 v = make_uint4(pack_bf16(lo.x, lo.y), pack_bf16(lo.z, lo.w), pack_bf16(hi.x, hi.y), pack_bf16(hi.z, hi.w));
             if (!ok[i]) continue;
             __nv_bfloat16* op = reinterpret_cast<__nv_bfloat16*>(p.out) + orow[i] * p.out_pitch + ch;
             *reinterpret_cast<uint4*>(op) = v;

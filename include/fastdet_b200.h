@@ -95,6 +95,8 @@ typedef struct fd_layer_desc {
 #define FD_KERNEL_HALO 5          /* conv_halo_kernel (narrow 3x3 on large maps) */
 #define FD_KERNEL_MAXPOOL 6
 #define FD_KERNEL_COPY 7
+#define FD_KERNEL_STEM 8          /* conv_stem_kernel: normalise + first conv + second (stride-2) conv in one kernel; reported for the second */
+#define FD_KERNEL_FUSED_NEXT 9    /* no launch of its own: computed inside the next layer's kernel (the first conv under FD_KERNEL_STEM) */
 typedef struct fd_layer_exec {
     int32_t kernel;       /* FD_KERNEL_* */
     int32_t bucket;       /* batch-size bucket whose execution state answered (n rounded up) */

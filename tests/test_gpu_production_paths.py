@@ -60,7 +60,9 @@ def test_default_plan_batch8_per_layer():
     L = m.layers()
     strips52 = [i for i in strip_candidates(m) if L[i]["h"] == 52]
     assert len(strips52) == 11 and all(f[i] == "tc_pair_strip" for i in strips52)
-    assert all(e["launches"] == 1 for e in m.exec_info(8))  # no chunking by default
+    info = m.exec_info(8)
+    assert f[:2] == ["fused_next", "stem"] and info[0]["launches"] == 0  # conv1 runs inside conv2's kernel (conv_stem.cu)
+    assert all(e["launches"] == 1 for e in info[1:])  # no chunking by default
     _check_heads(data, m, frames_for(8, 416, first_seed=150), per_layer=True)
     m.close()
 
@@ -76,11 +78,11 @@ def test_chunked_segments_batch16_per_layer():
         m = _native.Model(data, 80, (416, 416), device=0)
         info = m.exec_info(16)
         assert [e["chunk_frames"] for e in info[:10]] == [4, 4, 4, 4, 8, 8, 8, 8, 8, 16]
-        assert [e["launches"] for e in info[:10]] == [4, 4, 4, 4, 2, 2, 2, 2, 2, 1]
+        assert [e["launches"] for e in info[:10]] == [0, 4, 4, 4, 2, 2, 2, 2, 2, 1]  # (conv1 is computed inside conv2's kernel)
         got, _ = _check_heads(data, m, frames, per_layer=True, layers=range(10))
         m.close()
     m2 = _native.Model(data, 80, (416, 416), device=0)
-    assert all(e["launches"] == 1 for e in m2.exec_info(16))
+    assert all(e["launches"] == 1 for e in m2.exec_info(16)[1:])
     m2.preprocess(frames, 16, (416, 416))
     m2.forward(16)
     for a, b in zip(got, m2.heads(16)):
@@ -214,6 +216,42 @@ def test_nms_general_path_equals_register_path():
     for i in range(3):
         assert np.array_equal(a[i, :ca[i]], b[i, :cb[i]])
     m.close()
+
+
+def test_fused_stem_against_two_kernel_path():
+    """conv_stem_kernel (/255 + conv1 + conv2 in one kernel; the default for YOLOv3-shaped graphs) against the two-kernel path
+    it replaces (option stem=0: conv0_ws_kernel + conv_halo_kernel<32, 2>): conv2's output agrees to bf16 rounding flips (the
+    two forms add the same products in a different order before conv1's bf16 rounding), conv1's tensor — which the fused
+    form never materialises — is still served by the parity hook, and both plans pass the oracle check at the heads.
+    Batch 3 (bucket 4) of full-416 and batch 1 of full-608."""
+    for size, batch in ((416, 3), (608, 1)):
+        data = modelgen.build_onnx("full", 80, size, seed=2)
+        frames = frames_for(batch, size, first_seed=400)
+        m = _native.Model(data, 80, (size, size), device=0)
+        info = m.exec_info(batch)
+        assert [e["kernel_name"] for e in info[:2]] == ["fused_next", "stem"] and info[0]["launches"] == 0
+        _check_heads(data, m, frames, per_layer=True, layers=range(4))
+        c1, c2 = m.layer_output(0, batch), m.layer_output(1, batch)
+        m.close()
+        with _native.option("stem", 0):
+            m2 = _native.Model(data, 80, (size, size), device=0)
+            assert [e["kernel_name"] for e in m2.exec_info(batch)[:2]] == ["conv0", "halo"]
+            _check_heads(data, m2, frames)
+            assert np.array_equal(m2.layer_output(0, batch), c1)
+            d = np.abs(m2.layer_output(1, batch) - c2)
+            m2.close()
+        assert (d > 0).mean() < 1e-3 and d.max() <= 2.0 ** -6 * max(1.0, np.abs(c2).max()), ((d > 0).mean(), d.max())
+
+
+def test_stem_checker():
+    """csrc/dev/test_stem: the fused stem against a float64 CPU loop (every border pixel, tile seams, random interior pixels) and
+    against the two-kernel path, on six shapes (ragged maps, odd heights, pad (1, 0), many tiles per CTA)."""
+    exe = os.path.join(ROOT, "build", "test_stem")
+    if not os.path.exists(exe):
+        from fastdet_b200 import build
+        exe = build.build_stem_harness()
+    r = subprocess.run([exe, "check"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    assert r.returncode == 0 and "check: 0 failing case(s)" in r.stdout, "\n".join(r.stdout.splitlines()[-20:])
 
 
 def test_kernel_checker_all_forms():

@@ -135,3 +135,17 @@ def test_dbgout_dump(tmp_path):
     p = tmp_path / "dump.bin"
     fdet.DummyDetector(dbgout=str(p)).perform(b"\x01\x02\x03")
     assert p.read_bytes() == b"\x01\x02\x03"
+
+
+def test_stem_normalisation_formula():
+    """conv_stem.cu normalises without a table: fma(2^23 + k, c, -2^23 c) with c = float32(1 / 255), rounded to bf16.  For every
+    byte that equals bf16(float32(k / 255.0)) — the reference's float64 division rounded to float32
+    (/root/reference/server/detector.py:134), rounded once more for the tensor core — which is what the table in
+    conv0_ws_kernel holds.  The fma is emulated exactly: both products are exact in float64 (24-bit x 24-bit)."""
+    k = np.arange(256)
+    table = torch.tensor((k / 255.0).astype(np.float32)).to(torch.bfloat16)
+    c = np.float32(1.0) / np.float32(255.0)
+    x = np.float32(8388608.0) + k.astype(np.float32)
+    assert np.array_equal(x.view(np.uint32), 0x4B000000 | k.astype(np.uint32))  # the PRMT builds this bit pattern from the byte
+    fma = (x.astype(np.float64) * np.float64(c) - np.float64(8388608.0) * np.float64(c)).astype(np.float32)
+    assert torch.equal(torch.tensor(fma).to(torch.bfloat16).view(torch.int16), table.view(torch.int16))

@@ -23,13 +23,20 @@ rows = []
 tot_fl = 0.0
 prev = (3, a.size, a.size)
 print(f"{'#':>3} {'name':<9} {'cin':>5}->{'c':<5} k s {'hw':>4} {'bn':>3} {'ms':>8} {'TFLOP/s':>8} {'%tens':>6} {'GB/s':>7} {'%hbm':>5} {'t_roof':>7} {'eff':>5}")
+X = m.exec_info(n)
 for i, (l, t) in enumerate(zip(L, ms)):
-    fl = l["flops"] * n
+    if X[i]["kernel_name"] == "fused_next":  # no launch of its own: its work and FLOPs are in the next row (conv_stem_kernel)
+        print(f"{i:3d} {l['name']:<9} {l['cin']:5d}->{l['c']:<5d} {l['ksize']} {l['stride']} {l['h']:4d}  (computed inside the next layer's kernel)")
+        rows.append(dict(i=i, name=l["name"], ms=0.0, flops=0.0, bytes=0, t_roof_ms=0.0))
+        continue
+    fl = l["flops"] * n + (L[i - 1]["flops"] * n if X[i]["kernel_name"] == "stem" else 0.0)
     hw_out = l["h"] * l["w"]
     if l["kind"] in (0, 1):
         ho = l["h"] // (2 if l["upsample2x"] else 1)
         hin = ho * l["stride"]
         in_b = n * hin * hin * l["cin"] * (1 if l["kind"] == 0 else 2)
+        if X[i]["kernel_name"] == "stem":
+            in_b = n * hin * hin * 3  # the u8 frames
         out_b = n * hw_out * l["c"] * (4 if l["out_fp32"] else 2)
         w_b = l["c"] * l["cin"] * l["ksize"] ** 2 * 2
         res_b = out_b if l["has_residual"] else 0
