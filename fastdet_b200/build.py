@@ -16,8 +16,8 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libfastdet_b200.so")
-SOURCES = ["capi.cu", "conv_tc.cu", "conv_halo.cu", "conv_stem.cu", "jpeg.cu", "pre.cu", "pool.cu", "post.cu", "plan.cc", "onnx_reader.cc", "options.cc", "server.cc"]
-HEADERS = ["conv_tc.h", "conv_halo.h", "conv_stem.h", "kernels.h", "jpeg.h", "plan.h", "onnx_reader.h", "options.h", "ptx.cuh", os.path.join("..", "..", "include", "fastdet_b200.h")]
+SOURCES = ["capi.cu", "conv_tc.cu", "conv_halo.cu", "conv_stem.cu", "conv_block.cu", "jpeg.cu", "pre.cu", "pool.cu", "post.cu", "plan.cc", "onnx_reader.cc", "options.cc", "server.cc"]
+HEADERS = ["conv_tc.h", "conv_halo.h", "conv_stem.h", "conv_block.h", "kernels.h", "jpeg.h", "plan.h", "onnx_reader.h", "options.h", "ptx.cuh", os.path.join("..", "..", "include", "fastdet_b200.h")]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 
 
@@ -83,7 +83,7 @@ def build_dev_harness() -> str:
 def build_stem_harness() -> str:
     """csrc/dev/test_stem: stand-alone checker/timer of the fused stem kernel against a float64 loop and the two-kernel path."""
     out = os.path.join(os.path.dirname(HERE), "build", "test_stem")
-    srcs = [os.path.join(CSRC, f) for f in ("conv_tc.cu", "conv_halo.cu", "conv_stem.cu", "pre.cu", "options.cc", os.path.join("dev", "test_stem.cu"))]
+    srcs = [os.path.join(CSRC, f) for f in ("conv_tc.cu", "conv_halo.cu", "conv_stem.cu", "conv_block.cu", "pre.cu", "options.cc", os.path.join("dev", "test_stem.cu"))]
     if os.path.exists(out) and not _stale(out, srcs + [os.path.join(CSRC, h) for h in HEADERS]):
         return out
     cmd = [nvcc(), "-O3", "-std=c++17", "-lineinfo", "-DFASTDET_DEV"] + ARCH + ["-x", "cu"] + srcs + ["-o", out]

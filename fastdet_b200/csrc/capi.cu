@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "../../include/fastdet_b200.h"
+#include "conv_block.h"
 #include "conv_halo.h"
 #include "conv_stem.h"
 #include "conv_tc.h"
@@ -75,6 +76,12 @@ struct Exec {  // everything that depends on the batch size
     // and its output tensor is never written (its buffer is only allocated when a parity hook asks for that tensor)
     bool use_stem = false;
     std::vector<StemLaunch> stem;  // per chunk of layer 1's segment (one entry outside segments)
+    // Fused residual block (conv_block.cu): layer block_layer (1x1) runs inside layer block_layer + 1's kernel (3x3 + residual)
+    int block_layer = -1;          // -1: none
+    std::vector<BlockLaunch> block;
+    // per layer: 0 launches its own kernel, 1 computed inside the next layer's kernel (no launch, no output tensor), 2 launches a
+    // fused kernel that also does the previous layer's work
+    std::vector<char> fused_role;
     float* splitk_ws = nullptr;     // shared by the split-K launches of this batch size (they run one after another)
     int* splitk_counters = nullptr;
     int* tile_flags = nullptr;      // per-M-tile completion counters of the layers linked by tile-level dependencies
@@ -102,6 +109,7 @@ struct Exec {  // everything that depends on the batch size
     std::vector<std::vector<HaloLaunch>> ov_halo;
     std::vector<char> ov_use_halo;
     std::vector<StemLaunch> ov_stem;
+    std::vector<BlockLaunch> ov_block;
     cudaGraphExec_t graph_tail = nullptr;
     bool graph_tail_tried = false;
 };
@@ -278,6 +286,53 @@ int prepare_stem(fd_model* m, Exec* e, int frames, int k, int chunk, StemLaunch*
     return FD_OK;
 }
 
+// A residual block conv_block.cu can fuse: layer i a 1x1 stride-1 convolution, layer i + 1 the 3x3 stride-1 convolution that
+// is the ONLY reader of layer i's output and adds layer i's INPUT tensor as its residual.  Returns the first such i, or -1.
+int block_candidate(const ModelPlan& P) {
+    for (size_t i = 1; i + 1 < P.layers.size(); ++i) {
+        const LayerPlan& A = P.layers[i];
+        const LayerPlan& B = P.layers[i + 1];
+        if (A.kind != LAYER_CONV || B.kind != LAYER_CONV || A.ksize != 1 || A.stride != 1 || A.res.buf >= 0 || A.pool2 || B.pool2 ||
+            A.out_fp32 || B.out_fp32 || A.upsample2x || B.upsample2x)
+            continue;
+        if (B.ksize != 3 || B.stride != 1 || B.pad_lo != 1 || B.pad_hi != 1 || B.res.buf < 0) continue;
+        if (B.in.buf != A.out.buf || B.in.ch_off != A.out.ch_off || B.in.c != A.out.c || B.cin != A.cout) continue;
+        if (B.res.buf != A.in.buf || B.res.ch_off != A.in.ch_off || B.res.pitch != A.in.pitch || B.cout != A.cin) continue;
+        bool sole = true;
+        for (size_t j = 0; j < P.layers.size(); ++j)
+            if (j != i && j != i + 1 && (P.layers[j].in.buf == A.out.buf || P.layers[j].res.buf == A.out.buf || P.layers[j].out.buf == A.out.buf)) sole = false;
+        for (int h : P.head_layers)
+            if (h == static_cast<int>(i)) sole = false;
+        if (sole) return static_cast<int>(i);
+    }
+    return -1;
+}
+
+// shapes and filters of the fused block for `frames` frames; no tensor pointers yet (null passes the kernel's alignment rules)
+BlockDesc block_desc(const fd_model* m, int layer, int frames) {
+    const ModelPlan& P = m->plan;
+    const LayerPlan& A = P.layers[layer];
+    const LayerPlan& B = P.layers[layer + 1];
+    BlockDesc d;
+    memset(&d, 0, sizeof(d));
+    d.n = frames; d.h = A.in.h; d.w = A.in.w; d.in_pitch = A.in.pitch;
+    d.cin = A.cin; d.cmid = A.cout; d.cout = B.cout;
+    d.wa = m->d_w + A.w_off; d.bias_a_host = P.bias_f32.data() + A.b_off; d.act_a = A.act; d.alpha_a = A.alpha;
+    d.wb = m->d_w + B.w_off; d.bias_b_host = P.bias_f32.data() + B.b_off; d.act_b = B.act; d.alpha_b = B.alpha;
+    d.out_pitch = B.out.pitch;
+    return d;
+}
+
+int prepare_block(fd_model* m, Exec* e, int layer, int frames, int k, int chunk, BlockLaunch* bl) {
+    const ModelPlan& P = m->plan;
+    BlockDesc d = block_desc(m, layer, frames);
+    d.in = static_cast<const __nv_bfloat16*>(loc_ptr(*e, P, P.layers[layer].in, false, k, chunk));
+    d.out = static_cast<__nv_bfloat16*>(loc_ptr(*e, P, P.layers[layer + 1].out, false, k, chunk));
+    char err[256] = "";
+    if (conv_block_prepare(d, m->num_sms, bl, err, sizeof(err))) return fail(FD_ERR_CUDA, "residual block (layers %d + %d): %s", layer, layer + 1, err);
+    return FD_OK;
+}
+
 // tensor maps + launch geometry of conv layer i for `frames` frames, chunk k of its segment (k = chunk = 0: whole batch)
 int prepare_conv_layer(fd_model* m, Exec* e, size_t i, int frames, int k, int chunk, ConvLaunch* cl, HaloLaunch* hl, char* use_halo) {
     const ModelPlan& P = m->plan;
@@ -314,15 +369,16 @@ int prepare_conv_layer(fd_model* m, Exec* e, size_t i, int frames, int k, int ch
     return FD_OK;
 }
 
-// layer 0's output buffer, which an Exec with the fused stem does not allocate up front
-int ensure_stem_input_buffer(fd_model* m, Exec* e) {
+// the output buffer of a layer that is computed inside the next layer's kernel: not allocated up front (nothing writes it
+// during a forward pass), only when a parity hook asks for that tensor
+int ensure_fused_away_buffer(fd_model* m, Exec* e, int layer) {
     const ModelPlan& P = m->plan;
-    const int b = P.layers[0].out.buf;
+    const int b = P.layers[layer].out.buf;
     if (e->bufs[b]) return FD_OK;
     DEVICE_SETUP_LOCK(m);
-    const int frames = e->buf_internal[b] ? e->segs[e->seg_of[0]].chunk : e->n;
+    const int frames = e->buf_internal[b] ? e->segs[e->seg_of[layer]].chunk : e->n;
     cudaError_t err = cudaMalloc(&e->bufs[b], buf_bytes(P.buffers[b], frames));
-    if (err != cudaSuccess) return fail(FD_ERR_CUDA, "cudaMalloc(first convolution's output, batch %d) failed: %s", e->n, cudaGetErrorString(err));
+    if (err != cudaSuccess) return fail(FD_ERR_CUDA, "cudaMalloc(output of layer %d, batch %d) failed: %s", layer, e->n, cudaGetErrorString(err));
     return FD_OK;
 }
 
@@ -359,8 +415,20 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
         const int sgi = e->seg_of[1];
         want_stem = conv_stem_supported(stem_desc(m, sgi >= 0 ? e->segs[sgi].chunk : n));
     }
+    int want_block = -1;
+    if (options().block) {
+        const int bc = block_candidate(P);
+        if (bc >= 0 && e->seg_of[bc] == e->seg_of[bc + 1] && conv_block_supported(block_desc(m, bc, e->seg_of[bc] >= 0 ? e->segs[e->seg_of[bc]].chunk : n)))
+            want_block = bc;
+    }
+    e->fused_role.assign(P.layers.size(), 0);
+    if (want_stem) { e->fused_role[0] = 1; e->fused_role[1] = 2; }
+    if (want_block >= 0) { e->fused_role[want_block] = 1; e->fused_role[want_block + 1] = 2; }
     for (size_t i = 0; i < P.buffers.size(); ++i) {
-        if (want_stem && static_cast<int>(i) == P.layers[0].out.buf) continue;  // never written: allocated on demand by the parity hook
+        bool skip = false;  // outputs of fused-away layers are never written: allocated on demand by the parity hook
+        for (size_t li = 0; li < P.layers.size(); ++li)
+            if (e->fused_role[li] == 1 && P.layers[li].out.buf == static_cast<int>(i)) skip = true;
+        if (skip) continue;
         int frames = n;
         if (e->buf_internal[i])
             for (size_t li = 0; li < P.layers.size(); ++li)
@@ -390,7 +458,7 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
         const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, chunks = sgi >= 0 ? n / chunk : 1;
         e->conv[i].resize(chunks);
         e->halo[i].resize(chunks);
-        if (want_stem && i == 1) continue;  // launched as the fused stem (its input tensor does not exist)
+        if (e->fused_role[i]) continue;  // fused layers: a tensor of the pair does not exist, the pair has its own launch below
         for (int k = 0; k < chunks; ++k) {
             char uh = 0;
             if (int rc = prepare_conv_layer(m, e.get(), i, sgi >= 0 ? chunk : n, k, chunk, &e->conv[i][k], &e->halo[i][k], &uh)) { free_exec(e.get()); return rc; }
@@ -404,6 +472,14 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
         for (int k = 0; k < chunks; ++k)
             if (int rc = prepare_stem(m, e.get(), sgi >= 0 ? chunk : n, k, chunk, &e->stem[k])) { free_exec(e.get()); return rc; }
         e->use_stem = true;
+    }
+    if (want_block >= 0) {
+        const int sgi = e->seg_of[want_block];
+        const int chunk = sgi >= 0 ? e->segs[sgi].chunk : 0, chunks = sgi >= 0 ? n / chunk : 1;
+        e->block.resize(chunks);
+        for (int k = 0; k < chunks; ++k)
+            if (int rc = prepare_block(m, e.get(), want_block, sgi >= 0 ? chunk : n, k, chunk, &e->block[k])) { free_exec(e.get()); return rc; }
+        e->block_layer = want_block;
     }
     size_t ws_bytes = 0, counter_ints = 0;
     for (const auto& v : e->conv)
@@ -426,7 +502,7 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
         for (size_t i = 1; i < P.layers.size(); ++i) {
             const LayerPlan& A = P.layers[i - 1];
             const LayerPlan& B = P.layers[i];
-            if (A.kind != LAYER_CONV || B.kind != LAYER_CONV || e->use_halo[i - 1] || e->use_halo[i]) continue;
+            if (A.kind != LAYER_CONV || B.kind != LAYER_CONV || e->use_halo[i - 1] || e->use_halo[i] || e->fused_role[i - 1] || e->fused_role[i]) continue;
             if (A.out_fp32 || A.upsample2x || A.pool2 || A.out.pitch != A.out.c) continue;
             if (B.in.buf != A.out.buf || B.in.ch_off != A.out.ch_off || B.in.c != A.out.c || B.in.pitch != A.out.pitch || B.stride != 1) continue;
             cand.push_back(i);
@@ -451,15 +527,27 @@ int get_exec(fd_model* m, int n_frames, Exec** out) {
 }
 
 // layer i on frames [k * chunk, (k + 1) * chunk) (chunk = 0: the whole batch) with the given conv launch descriptors
-// sl: the fused stem's launch for these frames (layers 0 and 1 only; null = every layer launches its own kernel)
-int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, const ConvLaunch* cl, const HaloLaunch* hl, const StemLaunch* sl, cudaStream_t s) {
+// The fused kernels' launches for these frames: stem = layers 0 + 1, block = layers block_layer + block_layer + 1 (null: the
+// layers launch their own kernels — the parity hook's way to materialise a fused-away tensor).
+struct FusedLaunch {
+    const StemLaunch* stem = nullptr;
+    const BlockLaunch* block = nullptr;
+    int block_layer = -1;
+};
+
+int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, const ConvLaunch* cl, const HaloLaunch* hl, const FusedLaunch& fz, cudaStream_t s) {
     const ModelPlan& P = m->plan;
     const LayerPlan& L = P.layers[i];
     const int frames = chunk ? chunk : e->n;
     int rc = 0;
-    if (sl && i == 0) return FD_OK;  // computed inside layer 1's kernel
-    if (sl && i == 1) {
-        if (conv_stem_launch(*sl, s)) return fail(FD_ERR_CUDA, "launch of the fused stem (layers 0 + 1) failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (fz.stem && i == 0) return FD_OK;  // computed inside layer 1's kernel
+    if (fz.stem && i == 1) {
+        if (conv_stem_launch(*fz.stem, s)) return fail(FD_ERR_CUDA, "launch of the fused stem (layers 0 + 1) failed: %s", cudaGetErrorString(cudaGetLastError()));
+        return FD_OK;
+    }
+    if (fz.block && static_cast<int>(i) == fz.block_layer) return FD_OK;  // computed inside the next layer's kernel
+    if (fz.block && static_cast<int>(i) == fz.block_layer + 1) {
+        if (conv_block_launch(*fz.block, s)) return fail(FD_ERR_CUDA, "launch of the fused residual block (layers %zu + %zu) failed: %s", i - 1, i, cudaGetErrorString(cudaGetLastError()));
         return FD_OK;
     }
     switch (L.kind) {
@@ -489,8 +577,11 @@ int launch_layer(fd_model* m, Exec* e, size_t i, int k, int chunk, bool halo, co
 int launch_one(fd_model* m, Exec* e, size_t i, int k, cudaStream_t s) {
     const int sgi = e->seg_of[i];
     const bool conv = m->plan.layers[i].kind == LAYER_CONV;
+    FusedLaunch fz;
+    if (e->use_stem && i < 2) fz.stem = &e->stem[k];
+    if (e->block_layer >= 0 && (static_cast<int>(i) == e->block_layer || static_cast<int>(i) == e->block_layer + 1)) { fz.block = &e->block[k]; fz.block_layer = e->block_layer; }
     return launch_layer(m, e, i, k, sgi >= 0 ? e->segs[sgi].chunk : 0, e->use_halo[i] != 0, conv ? &e->conv[i][k] : nullptr,
-                        conv ? &e->halo[i][k] : nullptr, (e->use_stem && i < 2) ? &e->stem[k] : nullptr, s);
+                        conv ? &e->halo[i][k] : nullptr, fz, s);
 }
 
 // The forward pass: chunked segments chunk by chunk (all layers of the segment per chunk), then the rest layer by layer.
@@ -634,6 +725,7 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
     if (kernels_init()) return fail(FD_ERR_CUDA, "kernels_init failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (conv_halo_init()) return fail(FD_ERR_CUDA, "conv_halo_init failed: %s", cudaGetErrorString(cudaGetLastError()));
     if (conv_stem_init()) return fail(FD_ERR_CUDA, "conv_stem_init failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (conv_block_init()) return fail(FD_ERR_CUDA, "conv_block_init failed: %s", cudaGetErrorString(cudaGetLastError()));
     CU(cudaStreamCreateWithFlags(&m->stream, cudaStreamNonBlocking));
     CU(cudaMalloc(&m->d_w, std::max<size_t>(P.weights_bf16.size(), 64) * 2));
     CU(cudaMalloc(&m->d_bias, std::max<size_t>(P.bias_f32.size(), 64) * 4));
@@ -708,6 +800,12 @@ int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
         out->kernel = layer == 0 ? FD_KERNEL_FUSED_NEXT : FD_KERNEL_STEM;
         if (layer == 0) out->launches = 0;
         else { out->grid = e->stem[0].grid; out->smem_bytes = static_cast<int32_t>(e->stem[0].smem_bytes); }
+        return FD_OK;
+    }
+    if (e->block_layer >= 0 && (layer == e->block_layer || layer == e->block_layer + 1)) {
+        out->kernel = layer == e->block_layer ? FD_KERNEL_FUSED_NEXT : FD_KERNEL_BLOCK;
+        if (layer == e->block_layer) out->launches = 0;
+        else { out->grid = e->block[0].grid; out->smem_bytes = static_cast<int32_t>(e->block[0].smem_bytes); }
         return FD_OK;
     }
     switch (L.kind) {
@@ -926,7 +1024,7 @@ static int build_overlap_plan(fd_model* m, Exec* e) {
         if (P.layers[i].kind != LAYER_CONV) continue;
         e->ov_conv[i].resize(4);
         e->ov_halo[i].resize(4);
-        if (e->use_stem && i == 1) continue;
+        if (e->fused_role[i]) continue;
         for (int k = 0; k < 4; ++k) {
             char uh = 0;
             if (int rc = prepare_conv_layer(m, e, i, chunk, k, chunk, &e->ov_conv[i][k], &e->ov_halo[i][k], &uh)) return rc;
@@ -940,6 +1038,12 @@ static int build_overlap_plan(fd_model* m, Exec* e) {
         if (!conv_stem_supported(stem_desc(m, chunk))) return FD_OK;  // (cannot happen for shapes the whole-batch stem took; leave the plain path)
         for (int k = 0; k < 4; ++k)
             if (int rc = prepare_stem(m, e, chunk, k, chunk, &e->ov_stem[k])) return rc;
+    }
+    if (e->block_layer >= 0 && e->block_layer < depth) {
+        if (e->block_layer + 1 >= depth || !conv_block_supported(block_desc(m, e->block_layer, chunk))) return FD_OK;  // (the pair must lie inside the front)
+        e->ov_block.resize(4);
+        for (int k = 0; k < 4; ++k)
+            if (int rc = prepare_block(m, e, e->block_layer, chunk, k, chunk, &e->ov_block[k])) return rc;
     }
     e->ov_chunk = chunk;
     e->ov_layers = depth;
@@ -969,8 +1073,10 @@ static int forward_overlapping_copy(fd_model* m, Exec* e, const uint8_t* frames,
         CU(cudaStreamWaitEvent(s, m->h2d_ev[k], 0));
         for (int i = 0; i < e->ov_layers; ++i) {
             const bool conv = P.layers[i].kind == LAYER_CONV;
-            if (int rc = launch_layer(m, e, i, k, chunk, e->ov_use_halo[i] != 0, conv ? &e->ov_conv[i][k] : nullptr, conv ? &e->ov_halo[i][k] : nullptr,
-                                      (e->use_stem && i < 2) ? &e->ov_stem[k] : nullptr, s))
+            FusedLaunch fz;
+            if (e->use_stem && i < 2) fz.stem = &e->ov_stem[k];
+            if (e->block_layer >= 0 && (i == e->block_layer || i == e->block_layer + 1)) { fz.block = &e->ov_block[k]; fz.block_layer = e->block_layer; }
+            if (int rc = launch_layer(m, e, i, k, chunk, e->ov_use_halo[i] != 0, conv ? &e->ov_conv[i][k] : nullptr, conv ? &e->ov_halo[i][k] : nullptr, fz, s))
                 return rc;
         }
     }
@@ -1452,22 +1558,34 @@ int fd_pack_wire(const fd_det* dets, int count, uint32_t reqid, uint32_t msec, i
 // `layer`: the layer that produces `t`.  A buffer internal to a chunked segment only ever holds one chunk of frames, so
 // its value for the whole batch is gathered by replaying the segment chunk by chunk up to that layer (the same launches
 // the forward pass makes) and copying each chunk out.
-// With the fused stem the first convolution's output never exists during a forward pass; the hook for that tensor runs the
-// first convolution's own kernel (the two-kernel path's, which the stem is checked against) into a buffer allocated on demand.
+// The output of a layer that is computed inside the next layer's kernel never exists during a forward pass; the hook for
+// that tensor runs the layer's own kernel (the two-kernel path's, which the fused kernel is checked against) into a buffer
+// allocated on demand.
+static int launch_unfused(fd_model* m, Exec* e, int layer, int k, int chunk) {
+    const LayerPlan& L = m->plan.layers[layer];
+    if (L.kind == LAYER_CONV0) return launch_layer(m, e, layer, k, chunk, false, nullptr, nullptr, FusedLaunch(), m->stream);
+    ConvLaunch cl;
+    HaloLaunch hl;
+    char uh = 0;
+    if (int rc = prepare_conv_layer(m, e, layer, chunk ? chunk : e->n, k, chunk, &cl, &hl, &uh)) return rc;
+    if (!uh && cl.ws_bytes) return fail(FD_ERR_ARG, "layer %d: its unfused form would need a split-K workspace", layer);
+    return launch_layer(m, e, layer, k, chunk, uh != 0, &cl, &hl, FusedLaunch(), m->stream);
+}
+
 static int tensor_to_host_nchw(fd_model* m, Exec* e, int layer, const TensorLoc& t, bool fp32, float* dst, int n) {
     const size_t per_frame = size_t(t.c) * t.h * t.w;
-    const bool stem_input = e->use_stem && layer == 0;
-    if (stem_input)
-        if (int rc = ensure_stem_input_buffer(m, e)) return rc;
+    const bool fused_away = e->fused_role[layer] == 1;
+    if (fused_away)
+        if (int rc = ensure_fused_away_buffer(m, e, layer)) return rc;
     if (t.buf >= 0 && e->buf_internal[t.buf]) {
         const Segment& sg = e->segs[e->seg_of[layer]];
         if (int rc = ensure_scratch(e, per_frame * sg.chunk * 4)) return rc;
         for (int k = 0; k * sg.chunk < n; ++k) {
-            if (stem_input) {
-                if (int rc = launch_layer(m, e, 0, k, sg.chunk, false, nullptr, nullptr, nullptr, m->stream)) return rc;
-            } else
-            for (int j = sg.first; j <= layer; ++j)
-                if (int rc = launch_one(m, e, j, k, m->stream)) return rc;
+            // replay the segment up to the layer (a fused-away layer's input is whole or has just been produced by this replay)
+            for (int j = sg.first; j <= layer; ++j) {
+                if (j == layer && fused_away) { if (int rc = launch_unfused(m, e, layer, k, sg.chunk)) return rc; }
+                else if (int rc = launch_one(m, e, j, k, m->stream)) return rc;
+            }
             const int frames = std::min(sg.chunk, n - k * sg.chunk);
             if (launch_nhwc_to_nchw_f32(loc_ptr(*e, m->plan, t, fp32), t.pitch, fp32, e->scratch, frames, t.h, t.w, t.c, m->stream))
                 return fail(FD_ERR_CUDA, "layout kernel launch failed");
@@ -1478,8 +1596,8 @@ static int tensor_to_host_nchw(fd_model* m, Exec* e, int layer, const TensorLoc&
     }
     const size_t elems = size_t(n) * per_frame;
     if (int rc = ensure_scratch(e, elems * 4)) return rc;
-    if (stem_input)
-        if (int rc = launch_layer(m, e, 0, 0, 0, false, nullptr, nullptr, nullptr, m->stream)) return rc;
+    if (fused_away)
+        if (int rc = launch_unfused(m, e, layer, 0, 0)) return rc;
     if (launch_nhwc_to_nchw_f32(loc_ptr(*e, m->plan, t, fp32), t.pitch, fp32, e->scratch, n, t.h, t.w, t.c, m->stream))
         return fail(FD_ERR_CUDA, "layout kernel launch failed");
     CU(cudaMemcpyAsync(dst, e->scratch, elems * 4, cudaMemcpyDeviceToHost, m->stream));

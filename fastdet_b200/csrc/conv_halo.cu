@@ -76,6 +76,10 @@ __device__ __forceinline__ uint32_t max_bf16x2(uint32_t a, uint32_t b) {
     const __nv_bfloat162 r = __hmax2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
     return *reinterpret_cast<const uint32_t*>(&r);
 }
+__device__ __forceinline__ uint32_t add_bf16x2(uint32_t a, uint32_t b) {
+    const __nv_bfloat162 r = __hadd2(*reinterpret_cast<const __nv_bfloat162*>(&a), *reinterpret_cast<const __nv_bfloat162*>(&b));
+    return *reinterpret_cast<const uint32_t*>(&r);
+}
 // un-swizzled K-major shared-memory descriptor: start, LBO (K chunk stride), SBO (8-row group stride), all bytes
 __device__ __forceinline__ uint64_t desc_kmajor(uint32_t addr, uint32_t lbo, uint32_t sbo) {
     return static_cast<uint64_t>((addr >> 4) & 0x3FFF) | (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
@@ -277,11 +281,11 @@ conv_halo_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_consta
                         x.x = x.x > 0.f ? x.x : x.x * p.alpha;
                         x.y = x.y > 0.f ? x.y : x.y * p.alpha;
                     }
-                    if (has_res) {  // ONNX Add after LeakyRelu in fp32: one rounding, of the sum
-                        const uint32_t r = rcur[g >> 3].v[g & 7];
-                        x = __fadd2_rn(x, make_float2(__uint_as_float(r << 16), __uint_as_float(r & 0xFFFF0000u)));
-                    }
                     pk[g] = pack2(x.x, x.y);
+                }
+                if (has_res) {  // (bf16x2 add: the fp32 form used by conv_tc.cu costs this kernel 20 % on its three residual layers, conv4 / conv7 / conv9)
+#pragma unroll
+                    for (int g = 0; g < 16; ++g) pk[g] = add_bf16x2(pk[g], rcur[g >> 3].v[g & 7]);
                 }
                 // MaxPool(2, 2) in place: lane = (row lane >> 3, column lane & 7) of the warp's 4 x 8 pixels, so a 2x2 window is
                 // lanes l, l^1, l^8, l^9; the lane with even row and even column keeps the maximum (bf16 max is exact)

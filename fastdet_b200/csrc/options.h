@@ -19,6 +19,7 @@ struct Options {
                               // (1: chosen per layer, 64 / 128: forced, 0: off)
     int b_resident = 1;       // keep a narrow layer's whole filter bank in shared memory
     int stem = 1;             // first two convolutions (3 -> 32 s1, 32 -> 64 s2) of a YOLOv3-shaped graph in one kernel (conv_stem.cu)
+    int block = 1;            // a 1x1 (64 -> 32) + 3x3 (32 -> 64) + residual block on a large map in one kernel (conv_block.cu)
     int halo = 1;             // halo-patch kernel for 16/32/64-channel 3x3 layers on large maps
     int halo_skew = 1;        // ... with chunk planes skewed against shared-memory bank conflicts
     int halo_slots = 0;       // ... patch ring depth cap (0: the kernel's maximum)

@@ -109,6 +109,12 @@ __device__ __forceinline__ void st_shared_v4_if(uint32_t addr, uint32_t x, uint3
     asm volatile("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %5, 0;\n\t@q st.shared.v4.b32 [%0], {%1, %2, %3, %4};\n\t}" ::"r"(addr), "r"(x), "r"(y), "r"(z), "r"(w), "r"(static_cast<uint32_t>(pred)) : "memory");
 }
 
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 r;
+    asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr) : "memory");
+    return r;
+}
+
 // 16-byte asynchronous copy global -> shared (LDGSTS), L1-allocating; src_bytes = 0 writes zeros (padding)
 __device__ __forceinline__ void cp_async_16(uint32_t dst, const void* src, uint32_t src_bytes) {
     asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");

@@ -96,7 +96,8 @@ typedef struct fd_layer_desc {
 #define FD_KERNEL_MAXPOOL 6
 #define FD_KERNEL_COPY 7
 #define FD_KERNEL_STEM 8          /* conv_stem_kernel: normalise + first conv + second (stride-2) conv in one kernel; reported for the second */
-#define FD_KERNEL_FUSED_NEXT 9    /* no launch of its own: computed inside the next layer's kernel (the first conv under FD_KERNEL_STEM) */
+#define FD_KERNEL_FUSED_NEXT 9    /* no launch of its own: computed inside the next layer's kernel (FD_KERNEL_STEM / FD_KERNEL_BLOCK) */
+#define FD_KERNEL_BLOCK 10        /* conv_block_kernel: 1x1 + 3x3 + residual of one block in one kernel; reported for the 3x3 */
 typedef struct fd_layer_exec {
     int32_t kernel;       /* FD_KERNEL_* */
     int32_t bucket;       /* batch-size bucket whose execution state answered (n rounded up) */

@@ -61,8 +61,9 @@ def test_default_plan_batch8_per_layer():
     strips52 = [i for i in strip_candidates(m) if L[i]["h"] == 52]
     assert len(strips52) == 11 and all(f[i] == "tc_pair_strip" for i in strips52)
     info = m.exec_info(8)
-    assert f[:2] == ["fused_next", "stem"] and info[0]["launches"] == 0  # conv1 runs inside conv2's kernel (conv_stem.cu)
-    assert all(e["launches"] == 1 for e in info[1:])  # no chunking by default
+    # conv1 runs inside conv2's kernel (conv_stem.cu), conv3 inside conv4's (conv_block.cu)
+    assert f[:4] == ["fused_next", "stem", "fused_next", "block"]
+    assert all(e["launches"] == (0 if e["kernel_name"] == "fused_next" else 1) for e in info)  # no chunking by default
     _check_heads(data, m, frames_for(8, 416, first_seed=150), per_layer=True)
     m.close()
 
@@ -78,11 +79,11 @@ def test_chunked_segments_batch16_per_layer():
         m = _native.Model(data, 80, (416, 416), device=0)
         info = m.exec_info(16)
         assert [e["chunk_frames"] for e in info[:10]] == [4, 4, 4, 4, 8, 8, 8, 8, 8, 16]
-        assert [e["launches"] for e in info[:10]] == [0, 4, 4, 4, 2, 2, 2, 2, 2, 1]  # (conv1 is computed inside conv2's kernel)
+        assert [e["launches"] for e in info[:10]] == [0, 4, 0, 4, 2, 2, 2, 2, 2, 1]  # (conv1 / conv3 are computed inside conv2's / conv4's kernel)
         got, _ = _check_heads(data, m, frames, per_layer=True, layers=range(10))
         m.close()
     m2 = _native.Model(data, 80, (416, 416), device=0)
-    assert all(e["launches"] == 1 for e in m2.exec_info(16)[1:])
+    assert all(e["launches"] == (0 if e["kernel_name"] == "fused_next" else 1) for e in m2.exec_info(16))
     m2.preprocess(frames, 16, (416, 416))
     m2.forward(16)
     for a, b in zip(got, m2.heads(16)):
@@ -218,40 +219,50 @@ def test_nms_general_path_equals_register_path():
     m.close()
 
 
-def test_fused_stem_against_two_kernel_path():
-    """conv_stem_kernel (/255 + conv1 + conv2 in one kernel; the default for YOLOv3-shaped graphs) against the two-kernel path
-    it replaces (option stem=0: conv0_ws_kernel + conv_halo_kernel<32, 2>): conv2's output agrees to bf16 rounding flips (the
-    two forms add the same products in a different order before conv1's bf16 rounding), conv1's tensor — which the fused
-    form never materialises — is still served by the parity hook, and both plans pass the oracle check at the heads.
-    Batch 3 (bucket 4) of full-416 and batch 1 of full-608."""
+def test_fused_stem_and_block_against_the_unfused_path():
+    """conv_stem_kernel (/255 + conv1 + conv2 in one kernel) and conv_block_kernel (conv3 + conv4 + residual in one kernel) — the
+    default for YOLOv3-shaped graphs — against the four kernels they replace (options stem=0, block=0: conv0_ws_kernel,
+    conv_halo_kernel<32, 2>, conv_tc_kernel, conv_halo_kernel<32, 1>).  conv2's output agrees up to rare bf16 rounding flips
+    (the same products added in another order before conv1's rounding); conv4's to one bf16 step (the fused block adds the
+    residual in fp32 and rounds once, the halo kernel rounds the branch value first).  The tensors the fused forms never
+    materialise (conv1, conv3) are still served by the parity hook, and both plans pass the oracle check, layer by layer and at
+    the heads.  Batch 3 (bucket 4) of full-416 and batch 1 of full-608."""
     for size, batch in ((416, 3), (608, 1)):
         data = modelgen.build_onnx("full", 80, size, seed=2)
         frames = frames_for(batch, size, first_seed=400)
         m = _native.Model(data, 80, (size, size), device=0)
         info = m.exec_info(batch)
-        assert [e["kernel_name"] for e in info[:2]] == ["fused_next", "stem"] and info[0]["launches"] == 0
-        _check_heads(data, m, frames, per_layer=True, layers=range(4))
-        c1, c2 = m.layer_output(0, batch), m.layer_output(1, batch)
+        assert [e["kernel_name"] for e in info[:4]] == ["fused_next", "stem", "fused_next", "block"]
+        assert [e["launches"] for e in info[:4]] == [0, 1, 0, 1]
+        _check_heads(data, m, frames, per_layer=True, layers=range(5))
+        fused = [m.layer_output(i, batch) for i in range(4)]
         m.close()
-        with _native.option("stem", 0):
+        with _native.option("stem", 0), _native.option("block", 0):
             m2 = _native.Model(data, 80, (size, size), device=0)
-            assert [e["kernel_name"] for e in m2.exec_info(batch)[:2]] == ["conv0", "halo"]
-            _check_heads(data, m2, frames)
-            assert np.array_equal(m2.layer_output(0, batch), c1)
-            d = np.abs(m2.layer_output(1, batch) - c2)
+            names = [e["kernel_name"] for e in m2.exec_info(batch)[:4]]
+            assert names[0] == "conv0" and names[1] == "halo" and names[3] == "halo" and "fused_next" not in names
+            _check_heads(data, m2, frames, per_layer=True, layers=range(5))
+            plain = [m2.layer_output(i, batch) for i in range(4)]
             m2.close()
-        assert (d > 0).mean() < 1e-3 and d.max() <= 2.0 ** -6 * max(1.0, np.abs(c2).max()), ((d > 0).mean(), d.max())
+        assert np.array_equal(plain[0], fused[0])  # conv1: the hook runs the very kernel of the unfused plan
+        d1 = np.abs(plain[1] - fused[1])
+        assert (d1 > 0).mean() < 1e-3 and d1.max() <= 2.0 ** -6 * max(1.0, np.abs(fused[1]).max()), ((d1 > 0).mean(), d1.max())
+        d2 = np.abs(plain[2] - fused[2])
+        assert (d2 > 0).mean() < 1e-2, (d2 > 0).mean()  # conv3 from the hook: same kernel, inputs differ by conv2's rare flips
+        d3 = np.abs(plain[3] - fused[3])
+        assert d3.max() <= 2.0 ** -6 * max(1.0, np.abs(fused[3]).max()), d3.max()
 
 
 def test_stem_checker():
-    """csrc/dev/test_stem: the fused stem against a float64 CPU loop (every border pixel, tile seams, random interior pixels) and
-    against the two-kernel path, on six shapes (ragged maps, odd heights, pad (1, 0), many tiles per CTA)."""
+    """csrc/dev/test_stem: the fused stem and the fused residual block against a float64 CPU loop (every border pixel, tile seams,
+    random interior pixels) and against the kernels they replace, on ten shapes (ragged maps, odd heights, pad (1, 0), many
+    tiles per CTA)."""
     exe = os.path.join(ROOT, "build", "test_stem")
     if not os.path.exists(exe):
         from fastdet_b200 import build
         exe = build.build_stem_harness()
     r = subprocess.run([exe, "check"], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
-    assert r.returncode == 0 and "check: 0 failing case(s)" in r.stdout, "\n".join(r.stdout.splitlines()[-20:])
+    assert r.returncode == 0 and "check: 0 failing case(s)" in r.stdout and "block 208" in r.stdout, "\n".join(r.stdout.splitlines()[-20:])
 
 
 def test_kernel_checker_all_forms():

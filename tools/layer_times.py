@@ -29,7 +29,7 @@ for i, (l, t) in enumerate(zip(L, ms)):
         print(f"{i:3d} {l['name']:<9} {l['cin']:5d}->{l['c']:<5d} {l['ksize']} {l['stride']} {l['h']:4d}  (computed inside the next layer's kernel)")
         rows.append(dict(i=i, name=l["name"], ms=0.0, flops=0.0, bytes=0, t_roof_ms=0.0))
         continue
-    fl = l["flops"] * n + (L[i - 1]["flops"] * n if X[i]["kernel_name"] == "stem" else 0.0)
+    fl = l["flops"] * n + (L[i - 1]["flops"] * n if X[i]["kernel_name"] in ("stem", "block") else 0.0)
     hw_out = l["h"] * l["w"]
     if l["kind"] in (0, 1):
         ho = l["h"] // (2 if l["upsample2x"] else 1)
@@ -40,6 +40,8 @@ for i, (l, t) in enumerate(zip(L, ms)):
         out_b = n * hw_out * l["c"] * (4 if l["out_fp32"] else 2)
         w_b = l["c"] * l["cin"] * l["ksize"] ** 2 * 2
         res_b = out_b if l["has_residual"] else 0
+        if X[i]["kernel_name"] == "block":  # reads the block's input once (it is also the residual), writes the output once
+            in_b, res_b = out_b, 0
         byts = in_b + out_b + w_b + res_b
     else:
         byts = n * hw_out * l["c"] * 2 * 2
