@@ -15,7 +15,9 @@ for r in rows:
     else:
         d[m] = v * {"byte": 1, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1)
 ids = sorted(L)
-starts = [k for k, i in enumerate(ids) if L[i]["name"].startswith("conv0")]
+for d in L.values():
+    d["name"] = d["name"].split("::")[-1]  # (kernels in anonymous namespaces print as "unnamed>::name")
+starts = [k for k, i in enumerate(ids) if L[i]["name"].startswith("conv0") or L[i]["name"].startswith("conv_stem")]
 per_fwd = starts[1] - starts[0]
 step = lambda k0: [L[ids[k]] for k in range(k0, k0 + per_fwd)]
 seg = step(starts[3]) + step(starts[4])  # bench.py: 3 warm-up forwards, then the two timed device-resident steps
@@ -46,9 +48,11 @@ json.dump({"conv_stack_dram_bytes_per_step_bs64": rd + wr, "read": rd, "write": 
            "note": "ncu flushes the caches before every profiled launch, so each layer re-reads from DRAM what the previous one left in the 126 MB L2; in the un-profiled step part of that traffic never reaches DRAM",
            "source": f"profiles/{tag}_ncu_step_launches.txt (dram__bytes_read.sum + dram__bytes_write.sum, summed over the conv launches of one timed step)"},
           open(f"{P}/roofline_traffic.json", "w"), indent=1)
-# full capture -> raw metric summary
-rep = f"{G}/prof_convtc_{tag}.ncu-rep"
-if os.path.exists(rep):
+# full captures -> raw metric summaries
+for rep, outname, what in ((f"{G}/prof_convtc_{tag}.ncu-rep", f"{P}/{tag}_ncu_conv_tc_full.txt", "consecutive conv_tc launches of a timed step: a 52x52 strip 3x3 layer and the 1x1 layer after it"),
+                           (f"{G}/prof_stemblock_{tag}.ncu-rep", f"{P}/{tag}_ncu_stem_block_full.txt", "conv_stem_kernel (conv1 + conv2) and conv_block_kernel (conv3 + conv4 + residual) of one pass")):
+    if not os.path.exists(rep):
+        continue
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     r = list(csv.reader(raw.splitlines()))
     hdr, units = r[0], r[1]
@@ -58,10 +62,10 @@ if os.path.exists(rep):
             "lts__throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_sector_hit_rate.pct", "lts__t_requests.sum", "lts__t_sectors.sum",
             "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
             "sm__cycles_elapsed.avg.per_second", "sm__cycles_elapsed.max", "sm__cycles_active.avg", "smsp__inst_executed.sum"]
-    lines = [f"# ncu --set full --clock-control none --import-source on -k regex:conv_tc_kernel -c 4 : python bench.py --steps 2 --warmup 3 --quick --no-parity",
-             "# four consecutive conv_tc launches of a timed step (full-416-80cls, batch 64)"]
+    lines = [f"# ncu --set full --clock-control none --import-source on (tools/profile_round.sh) : python bench.py --steps 2 --warmup 3 --quick --no-parity",
+             f"# {what} (full-416-80cls, batch 64)"]
     for j, h in enumerate(hdr):
         if h in want:
             lines.append(f"{h:<80} {units[j]:<14} {[x[j][:60] for x in r[2:]]}")
-    open(f"{P}/{tag}_ncu_conv_tc_full.txt", "w").write("\n".join(lines) + "\n")
+    open(outname, "w").write("\n".join(lines) + "\n")
     print("\n".join(lines[2:]))
