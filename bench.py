@@ -368,8 +368,10 @@ def parity_in_run(model, onnx_bytes, w, frames, n, sp):
                 out["solid_reference_detections"] += 1
                 out["found_same_box_and_class"] += int(got.get(box) == r[0])
     worst = max(max(e) for e in out["head_err_over_max_ref"])
-    out["ok"] = bool(worst <= 2e-2 and out["found_same_box_and_class"] >= out["solid_reference_detections"] - 1)
-    out["bound"] = "heads: max|gpu-ref| <= 2e-2 * max|ref| vs the fp32 oracle; detections clearing the threshold by 2e-2 at the same anchor box and class (one Soft-NMS near-tie flip tolerated)"
+    flips_allowed = max(1, out["solid_reference_detections"] // 40)  # Soft-NMS near-tie flips: one per 40 solid detections (at least one)
+    out["ok"] = bool(worst <= 2e-2 and out["found_same_box_and_class"] >= out["solid_reference_detections"] - flips_allowed)
+    out["bound"] = ("heads: max|gpu-ref| <= 2e-2 * max|ref| vs the fp32 oracle; detections clearing the threshold by 2e-2 at the same anchor box and class "
+                    "(Soft-NMS near-tie flips tolerated: one per 40 such detections, here %d; the GPU tests decide each such case by nudging the oracle's own scores)" % flips_allowed)
     return out
 
 
