@@ -7,7 +7,8 @@
 // memory, in exactly the layout conv_halo.cu's stride-2 form reads its nine taps from.  The price is recomputing the first
 // convolution on the patch overlap (33 x 17 conv1 pixels for 32 x 16 owned ones: 1.1x) and on the padding rows of the MMA
 // blocks below; the kernel is bound by MMA issue (~45 cycles per tcgen05.mma whatever its N) and by its epilogues'
-// instruction issue, not by HBM.
+// instruction issue, not by HBM.  Measured at batch 64, 416x416: 224 us against 488 us for conv0_ws_kernel +
+// conv_halo_kernel<32, 2> (dev/test_stem.cu; per-role cycle accounting in profiles/r02q_stem_role_cycles.txt).
 //
 // Per tile of 16 x 8 output pixels of the second convolution (M = 128 rows of its MMA):
 //   builders   gather the 35 x 19 u8 halo patch of the frame, convert to bf16(float32(k / 255)) and store it with
