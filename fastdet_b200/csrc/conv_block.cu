@@ -314,6 +314,9 @@ conv_block_kernel(const __grid_constant__ CUtensorMap tm_out, const __grid_const
             const uint32_t buf = stage_u;
             if (lane == 0) PROF_WAIT(1, ptx::tma_store_wait_read<0>());  // this warp's previous stores (two tiles ago) have finished reading the buffer
             __syncwarp();
+            // the x patch was written by the builders' cp.async: observe its barrier here too (long complete — the 1x1 ran on it —
+            // but this warp's generic loads of the residual then have their own acquire on those writes)
+            ptx::mbar_wait(&in_full[slot], (it / IN_SLOTS) & 1);
             const uint32_t res = in_base + slot * IN_SLOT_BYTES + res_off;
 #pragma unroll
             for (int c0 = 0; c0 < COUT; c0 += 32) {
