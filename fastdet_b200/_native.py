@@ -92,6 +92,7 @@ _PROTOS = {
     "fd_model_info": (C.c_int, [C.c_void_p, C.POINTER(FdInfo)]),
     "fd_layer_info": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(FdLayerDesc)]),
     "fd_layer_exec_info": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(FdLayerExec)]),
+    "fd_planned_fusions": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "fd_set_option": (C.c_int, [C.c_char_p, C.c_int]),
     "fd_get_option": (C.c_int, [C.c_char_p, C.POINTER(C.c_int)]),
     "fd_preprocess": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
@@ -215,6 +216,13 @@ class Model:
             out.append({k: (getattr(d, k).decode() if isinstance(getattr(d, k), bytes) else getattr(d, k))
                         for k, _ in FdLayerDesc._fields_})
         return out
+
+    def planned_fusions(self, n: int) -> Tuple[bool, int]:
+        """(stem, block_layer): whether layers 0 + 1 would run as the fused stem kernel, and the first layer of the pair that
+        would run as the fused residual-block kernel (-1: none) at batch n.  Host logic: works on a plan-only model."""
+        stem, block = C.c_int32(0), C.c_int32(-1)
+        _check(lib().fd_planned_fusions(self._h, n, C.byref(stem), C.byref(block)))
+        return bool(stem.value), int(block.value)
 
     def exec_info(self, n: int) -> List[dict]:
         """Kernel form of every fused layer in the execution state of batch size n (built if needed)."""

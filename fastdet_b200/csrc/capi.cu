@@ -785,6 +785,22 @@ int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out) {
     return FD_OK;
 }
 
+// Host logic only (works on a plan-only model): which layers the planner would hand to the fused kernels at batch n under the
+// current options — *stem = 1 when layers 0 + 1 run as conv_stem_kernel, *block_layer = the 1x1 layer of the pair that runs
+// as conv_block_kernel (or -1).  Chunked segments (option chunk_frames) can still keep a pair apart; fd_layer_exec_info
+// reports what an execution state really does.
+int fd_planned_fusions(const fd_model* m, int n, int32_t* stem, int32_t* block_layer) {
+    if (!m || !stem || !block_layer || n < 1) return fail(FD_ERR_ARG, "fd_planned_fusions: bad argument");
+    const ModelPlan& P = m->plan;
+    *stem = (options().stem && stem_candidate(P) && conv_stem_supported(stem_desc(m, n))) ? 1 : 0;
+    *block_layer = -1;
+    if (options().block) {
+        const int bc = block_candidate(P);
+        if (bc >= 0 && conv_block_supported(block_desc(m, bc, n))) *block_layer = bc;
+    }
+    return FD_OK;
+}
+
 int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out) {
     if (!m || !out || layer < 0 || layer >= static_cast<int>(m->plan.layers.size())) return fail(FD_ERR_ARG, "fd_layer_exec_info: bad layer %d", layer);
     NEED_DEVICE(m);

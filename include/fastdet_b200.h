@@ -124,6 +124,10 @@ int fd_model_create(const void* onnx_bytes, size_t len, int num_classes, int net
 void fd_model_destroy(fd_model* m);
 int fd_model_info(const fd_model* m, fd_info* out);
 int fd_layer_info(const fd_model* m, int layer, fd_layer_desc* out);
+/* Host logic only (also on a plan-only model, device -1): the layer pairs the planner hands to the fused kernels at batch n under
+ * the current options.  *stem: 1 when layers 0 + 1 run as one kernel (FD_KERNEL_STEM); *block_layer: the first layer of the pair
+ * that runs as FD_KERNEL_BLOCK, or -1. */
+int fd_planned_fusions(const fd_model* m, int n, int32_t* stem, int32_t* block_layer);
 /* Builds (if needed) the execution state for batch size n and reports the kernel form of `layer` in it. */
 int fd_layer_exec_info(fd_model* m, int layer, int n, fd_layer_exec* out);
 

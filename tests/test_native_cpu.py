@@ -149,3 +149,26 @@ def test_stem_normalisation_formula():
     assert np.array_equal(x.view(np.uint32), 0x4B000000 | k.astype(np.uint32))  # the PRMT builds this bit pattern from the byte
     fma = (x.astype(np.float64) * np.float64(c) - np.float64(8388608.0) * np.float64(c)).astype(np.float32)
     assert torch.equal(torch.tensor(fma).to(torch.bfloat16).view(torch.int16), table.view(torch.int16))
+
+
+def test_planned_fusions_host_logic():
+    """Which layer pairs go to the fused kernels (conv_stem.cu: layers 0 + 1; conv_block.cu: a 1x1 + 3x3 + residual block) is
+    decided on the host from the plan alone: YOLOv3-shaped graphs at 416 and 608 get both, YOLOv3-tiny (max-pool behind the
+    first convolution, no residuals) neither, maps under 64 x 64 keep the separate kernels, and the options switch each
+    fusion off."""
+    full = _native.Model(modelgen.build_onnx("full", 80, 416, seed=2), 80, (416, 416), device=-1)
+    L = full.layers()
+    assert full.planned_fusions(64) == (True, 2) and full.planned_fusions(1) == (True, 2)
+    # the fused block = the 1x1 (64 -> 32) and the 3x3 (32 -> 64) + residual of the first residual block
+    assert (L[2]["ksize"], L[2]["cin"], L[2]["c"], L[3]["ksize"], L[3]["cin"], L[3]["c"], L[3]["has_residual"]) == (1, 64, 32, 3, 32, 64, 1)
+    assert (L[0]["kind"], L[0]["c"], L[1]["ksize"], L[1]["stride"], L[1]["c"]) == (0, 32, 3, 2, 64)
+    with _native.option("stem", 0):
+        assert full.planned_fusions(64) == (False, 2)
+    with _native.option("block", 0):
+        assert full.planned_fusions(64) == (True, -1)
+    full.close()
+    for arch, nc, size, want in (("rsu", 9, 416, (True, 2)), ("full", 80, 608, (True, 2)), ("tiny", 80, 416, (False, -1)),
+                                 ("full", 80, 96, (False, -1))):  # 96: conv2's map is 48 x 48
+        m = _native.Model(modelgen.build_onnx(arch, nc, size, seed=2), nc, (size, size), device=-1)
+        assert m.planned_fusions(8) == want, (arch, size, m.planned_fusions(8))
+        m.close()
